@@ -1,0 +1,194 @@
+"""Pins the CPU oracle (oracle/) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pandas as pd
+
+from conftest import golden, golden_genome, assert_pvals_close
+
+
+def test_context_column_order(oracle):
+    z = golden("scan")
+    assert oracle.context_names(1, 1) == list(z["columns_1_1"])
+    assert oracle.context_names(2, 2) == list(z["columns_2_2"])
+
+
+def test_scan_counts_bit_exact(oracle):
+    z = golden("scan")
+    seq, off, ln = golden_genome()
+    wins = z["windows"]
+    for (u, d) in [(1, 1), (2, 2), (0, 0), (1, 2), (2, 0)]:
+        rows = z["rows_%d_%d" % (u, d)]
+        w = wins[rows]
+        got, n_other = oracle.count_regions(seq, off, ln, w[:, 0] - 1, w[:, 1], w[:, 2], n_up=u, n_down=d)
+        assert n_other == 0
+        assert np.array_equal(got, z["counts_%d_%d" % (u, d)]), (u, d)
+        assert list(z["index_%d_%d" % (u, d)]) == ["chr%d:%d-%d" % tuple(r) for r in w]
+
+
+def test_scan_python_port_matches_reference(oracle):
+    z = golden("scan")
+    wins = z["windows"][z["rows_2_2"]][:25]
+    seqs = {"chr1": z["seq_chr1"].tobytes().decode(), "chr2": z["seq_chr2"].tobytes().decode()}
+    got = oracle.py_count_regions(seqs, ["chr%d" % c for c in wins[:, 0]], wins[:, 1], wins[:, 2], 2, 2)
+    assert np.array_equal(got, z["counts_2_2"][:25])
+
+
+def test_scan_pool_chunking(oracle):
+    z = golden("scan")
+    seq, off, ln = golden_genome()
+    w = z["windows"][:60]
+    got, _ = oracle.count_regions(seq, off, ln, w[:, 0] - 1, w[:, 1], w[:, 2], n_up=1, n_down=1)
+    assert np.array_equal(got, z["pool_counts_1_1"])
+
+
+def test_scan_rejects_start_inside_halo(oracle):
+    seq, off, ln = golden_genome()
+    import pytest
+    with pytest.raises(ValueError):
+        oracle.count_regions(seq, off, ln, [0], [1], [50], n_up=2, n_down=2)
+
+
+def test_block_counts_strand_aware(oracle):
+    z = golden("scan")
+    seq, off, ln = golden_genome()
+    c64, _ = oracle.count_regions(seq, off, ln, z["blk_chrom"] - 1, z["blk_start"], z["blk_end"],
+                                  n_up=1, n_down=1, strand=z["blk_strand"])
+    assert list(z["blk_columns"]) == oracle.substitution_names()
+    assert np.array_equal(np.repeat(c64, 3, axis=1).astype(np.float64), z["blk_L192"])
+
+
+def test_index_tables(oracle):
+    z = golden("tables")
+    assert oracle.substitution_names() == list(z["trans_idx"])
+    tab = oracle.mutation_context_table()
+    assert [m for m, _ in tab] == list(z["mutctx_mut"])
+    assert [c for _, c in tab] == list(z["mutctx_ctx"])
+    perm, _ = oracle.revcomp_permutation_192()
+    assert np.array_equal(z["revc_in"][perm], z["revc_out"])
+    # the permutation is "new[name] = old[revcomp(name)]", an involution
+    assert np.array_equal(perm[perm], np.arange(192))
+
+
+def test_mutation_contexts(oracle):
+    z = golden("mutctx")
+    seq, off, ln = golden_genome()
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    ref = np.array([code.get(r, 255) for r in z["in_REF"]], dtype=np.uint8)
+    for (u, d) in [(1, 1), (2, 2)]:
+        ctx = oracle.mutation_contexts(seq, off, ln, z["in_CHROM"] - 1, z["in_START"], ref, n_up=u, n_down=d)
+        kept = np.flatnonzero(ctx >= 0)
+        assert np.array_equal(kept, z["kept_rows_%d_%d" % (u, d)])
+        names = np.array(oracle.context_names(u, d))
+        assert list(names[ctx[kept]]) == list(z["context_%d_%d" % (u, d)])
+        mt = ["%s>%s" % (r, a) for r, a in zip(z["in_REF"][kept], z["in_ALT"][kept])]
+        assert mt == list(z["mut_type_%d_%d" % (u, d)])
+
+
+def test_ideal_overlaps(oracle):
+    z = golden("overlaps")
+    for i in range(8):
+        for W in (10000, 1000):
+            blocks = z["case%d_w%d_in" % (i, W)]
+            want = z["case%d_w%d_out" % (i, W)]
+            got = oracle.ideal_overlaps(blocks[0], blocks[1], W)
+            assert got == list(want[:, 1])
+            assert np.all(want[:, 2] - want[:, 1] == W)
+
+
+def _transfer_inputs(z):
+    idx = z["idx"]
+    win_index = {(int(c), int(s)): i for i, (c, s, e) in enumerate(idx)}
+    return idx, win_index
+
+
+def test_element_transfer(oracle):
+    z = golden("transfer")
+    seq, off, ln = golden_genome()
+    idx, win_index = _transfer_inputs(z)
+    w64, _ = oracle.count_regions(seq, off, ln, idx[:, 0] - 1, idx[:, 1], idx[:, 2], n_up=1, n_down=1)
+    assert np.array_equal(oracle.model192_to_dpr(z["FREQ_192"]), z["d_pr_sorted"])
+    # L from the oracle's own strand-aware block counts
+    nb = len(z["blk_start"])
+    blk_elt = np.repeat(np.arange(len(z["elt_chrom"])), np.diff(z["blk_ptr"]))
+    c64, _ = oracle.count_regions(seq, off, ln, z["elt_chrom"][blk_elt] - 1, z["blk_start"], z["blk_end"],
+                                  n_up=1, n_down=1, strand=z["elt_strand"][blk_elt])
+    L = np.zeros((len(z["elt_chrom"]), 192))
+    np.add.at(L, blk_elt, np.repeat(c64, 3, axis=1))
+    assert nb == len(blk_elt)
+    assert np.array_equal(L, z["L192"])
+    out = oracle.element_transfer(z["elt_chrom"], z["elt_strand"], z["blk_ptr"], z["blk_start"], z["blk_end"], L,
+                                  int(z["window"]), win_index, w64, z["Y_PRED"], z["STD"], z["Y_TRUE"], z["FLAG"],
+                                  z["d_pr_sorted"])
+    for k in ("MU", "SIGMA", "P_SUM", "P_INDEL"):
+        np.testing.assert_allclose(out[k], z["out_" + k], rtol=1e-12)
+    for k in ("R_OBS", "R_SIZE", "ELT_SIZE"):
+        assert np.array_equal(out[k], z["out_" + k])
+    assert np.array_equal(out["FLAG"], z["out_FLAG"])
+    a, t = oracle.normal_params_to_gamma(out["MU"], out["SIGMA"])
+    np.testing.assert_allclose(a, z["out_ALPHA"], rtol=1e-12)
+    np.testing.assert_allclose(t, z["out_THETA"], rtol=1e-12)
+
+
+def test_nb_midp_is_the_reference_expression(oracle):
+    z = golden("nbtest")
+    with np.errstate(all="ignore"):
+        got = oracle.nb_pvalue_greater_midp(z["k"], z["alpha"], z["p"])
+    assert_pvals_close(got, z["pval"], tol=1e-12)
+
+
+def test_element_test_stage(oracle):
+    z = golden("nbtest")
+    alpha, theta = oracle.normal_params_to_gamma(z["elt_MU"], z["elt_SIGMA"])
+    assert np.array_equal(alpha, z["elt_out_ALPHA"])
+    theta_c = theta * float(z["elt_cj"])
+    np.testing.assert_allclose(theta_c, z["elt_out_THETA"], rtol=0, atol=0)
+    exp, p = oracle.burden_test(z["elt_OBS_SNV"], alpha, theta_c, z["elt_Pi_SUM"])
+    np.testing.assert_allclose(exp, z["elt_out_EXP_SNV"], rtol=1e-15)
+    assert_pvals_close(p, z["elt_out_PVAL_SNV_BURDEN"], tol=1e-12)
+    _, ps = oracle.burden_test(z["elt_OBS_SAMPLES"], alpha, theta_c, z["elt_Pi_SUM"])
+    assert_pvals_close(ps, z["elt_out_PVAL_SAMPLE_BURDEN"], tol=1e-12)
+    theta_i = theta * float(z["elt_cj_indel"])
+    exp_i, pi = oracle.burden_test(z["elt_OBS_INDEL"], alpha, theta_i, z["elt_Pi_INDEL"])
+    np.testing.assert_allclose(exp_i, z["elt_out_EXP_INDEL"], rtol=1e-15)
+    assert_pvals_close(pi, z["elt_out_PVAL_INDEL_BURDEN"], tol=1e-12)
+    assert_pvals_close(oracle.fisher2(p, pi), z["elt_out_PVAL_MUT_BURDEN"], tol=1e-12)
+
+
+def test_gene_observed_counts(oracle):
+    z = golden("genes")
+    df = pd.DataFrame({c: z["in_" + c] for c in ("CHROM", "START", "END", "REF", "ALT", "SAMPLE", "GENE", "ANNOT")})
+    for cap, tag in ((3e9, "cap0"), (2, "cap2")):
+        got = oracle.gene_observed_counts(df, max_muts_per_gene_per_sample=cap)
+        assert list(got.index) == list(z[tag + "_genes"])
+        for c in ("OBS_SYN", "OBS_MIS", "OBS_NONS", "OBS_SPL", "OBS_INDEL"):
+            assert np.array_equal(got[c].values, z[tag + "_" + c]), (tag, c)
+    got = oracle.gene_observed_counts(df).reindex(z["pre_genes"]).fillna(0)
+    for c in ("N_SAMP_SYN", "N_SAMP_MIS", "N_SAMP_NONS", "N_SAMP_SPL", "N_SAMP_TRUNC", "N_SAMP_NONSYN",
+              "N_SAMP_INDEL", "OBS_SYN", "OBS_MIS", "OBS_NONS", "OBS_SPL", "OBS_INDEL"):
+        assert np.array_equal(got[c].values.astype(np.float64), z["out_" + c]), c
+
+
+def test_tabulate_mutations_in_element_small(oracle):
+    # hand-checked case for the bedtools-intersect restatement (mutation_tools.py:191-230, :155-189)
+    mut = pd.DataFrame([
+        (1, 100, 101, "A", "C", "S1", "Missense"),
+        (1, 100, 101, "A", "C", "S1", "Missense"),     # exact duplicate row -> counted once
+        (1, 150, 151, "G", "T", "S1", "Noncoding"),
+        (1, 199, 200, "G", "T", "S2", "Noncoding"),    # last base of block [100,200)
+        (1, 200, 201, "G", "T", "S2", "Noncoding"),    # first base past the block -> no hit
+        (1, 120, 125, "GTTTT", "G", "S3", "INDEL"),
+        (1, 298, 303, "GTTTT", "G", "S3", "INDEL"),    # spans blocks [250,300) and [300,350) of E2 -> once
+        (2, 100, 101, "A", "C", "S1", "Missense"),     # other chromosome
+    ], columns=["CHROM", "START", "END", "REF", "ALT", "SAMPLE", "ANNOT"])
+    blocks = pd.DataFrame([(1, 100, 200, "E1"), (1, 250, 300, "E2"), (1, 300, 350, "E2"), (1, 110, 130, "E3")],
+                          columns=["CHROM", "START", "END", "ELT"])
+    summ, black = oracle.tabulate_mutations_in_element(mut, blocks)
+    assert black == []
+    assert summ.loc["E1"].tolist() == [3, 3, 1]
+    assert summ.loc["E2"].tolist() == [1, 0, 1]
+    assert summ.loc["E3"].tolist() == [1, 0, 1]
+    summ, black = oracle.tabulate_mutations_in_element(mut, blocks, max_muts_per_sample=2.5)
+    assert sorted(black) == ["S3"]
+    assert summ.loc["E1"].tolist() == [2, 3, 0]
+    summ, _ = oracle.tabulate_mutations_in_element(mut, blocks, max_muts_per_elt_per_sample=1)
+    assert summ.loc["E1"].tolist() == [3, 2, 1]
