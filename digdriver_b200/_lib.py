@@ -1,0 +1,65 @@
+"""ctypes binding of libdigb200.so (include/dig_b200.h).
+
+There is deliberately no CPU fallback: if the shared library is missing or a call fails,
+an exception is raised.
+"""
+import ctypes
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libdigb200.so")
+
+_c = ctypes
+_P = _c.c_void_p
+_I64 = _c.c_int64
+_I = _c.c_int
+_U64 = _c.c_uint64
+_D = _c.c_double
+
+# name -> (restype, argtypes); mirrors include/dig_b200.h one to one
+SIGNATURES = {
+    "dig_version": (_I, []),
+    "dig_last_error": (_c.c_char_p, []),
+    "dig_device_sm_count": (_I, []),
+    "dig_packed_words": (_I64, [_I64]),
+    "dig_nmask_words": (_I64, [_I64]),
+    "dig_pack_genome": (_I, [_P, _I64, _P, _P, _P, _P]),
+    "dig_count_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P]),
+    "dig_synth_genome": (_I, [_P, _I64, _I64, _U64, _I, _P]),
+}
+
+_lib = None
+
+
+class DigError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdigb200.so; raises if it has not been built (python -m digdriver_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DigError(
+            "libdigb200.so not found at %s: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -m digdriver_b200.build`." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().dig_last_error()
+        raise DigError("%s failed with code %d: %s" % (what or "libdigb200 call", rc, (msg or b"").decode()))
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    fn = getattr(load(), name)
+    check(fn(*args), name)

@@ -1,0 +1,102 @@
+// K1: ASCII genome -> 2-bit packed bases (MSB first) + N bitmask.
+//
+// HBM-bound streaming kernel: 1 B/base read, 0.375 B/base written.  Each thread converts
+// 16 bases (one 128-bit load) into one packed word with byte-SIMD (__vcmpeq4) and a pair of
+// lanes assembles one N-mask word through a shuffle, so loads and both stores are coalesced.
+#include "dig_common.cuh"
+
+namespace {
+
+// 4 ASCII bytes (little endian: lowest byte = first base) -> 8 bits of 2-bit codes, first base
+// most significant, and 4 validity bits in the same order (1 = not ACGT).
+__device__ __forceinline__ void convert4(uint32_t w, uint32_t &codes8, uint32_t &n4, uint32_t &other)
+{
+    const uint32_t up = w & 0xDFDFDFDFu;                       // upper-case
+    const uint32_t ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) |
+                        __vcmpeq4(up, 0x47474747u) | __vcmpeq4(up, 0x54545454u);
+    const uint32_t isn = __vcmpeq4(up, 0x4E4E4E4Eu);           // 'N' / 'n'
+    // A=0x41 C=0x43 G=0x47 T=0x54: ((c>>1)&3) ^ ((c>>2)&1) -> 0,1,2,3
+    uint32_t t = ((w >> 1) & 0x03030303u) ^ ((w >> 2) & 0x01010101u);
+    t &= ok;                                                   // non-ACGT stored as 0
+    codes8 = ((t & 3u) << 6) | (((t >> 8) & 3u) << 4) | (((t >> 16) & 3u) << 2) | ((t >> 24) & 3u);
+    const uint32_t bad = ~ok;
+    n4 = ((bad & 1u) << 3) | (((bad >> 8) & 1u) << 2) | (((bad >> 16) & 1u) << 1) | ((bad >> 24) & 1u);
+    other += __popc(~(ok | isn) & 0x01010101u);
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, int64_t n,
+                                                   uint32_t *__restrict__ packed2, uint32_t *__restrict__ nmask,
+                                                   unsigned long long *n_other, int64_t n_groups, int aligned)
+{
+    // n_groups is even; group gidx covers bases [16*gidx, 16*gidx+16)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t other = 0;
+    const int lane = threadIdx.x & 31;
+    // the loop condition is warp-uniform so that the pair shuffle below always sees a full warp
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n_groups; base += stride) {
+        const int64_t gidx = base + lane;
+        const bool live = gidx < n_groups;
+        const int64_t b0 = gidx << 4;
+        uint32_t w[4];
+        if (aligned && b0 + 16 <= n) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ascii + b0));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t g = b0 + q * 4 + b;
+                    const uint32_t c = g < n ? ascii[g] : (uint32_t)'N';
+                    x |= c << (8 * b);
+                }
+                w[q] = x;
+            }
+        }
+        uint32_t word = 0, n16 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t c8, n4;
+            convert4(w[q], c8, n4, other);
+            word |= c8 << (24 - 8 * q);
+            n16 |= n4 << (12 - 4 * q);
+        }
+        // positions beyond n were fed as 'N': they are flagged in the mask and do not count as "other"
+        if (live) packed2[gidx] = word;
+        const uint32_t peer = __shfl_xor_sync(0xffffffffu, n16, 1);
+        if (live && (gidx & 1) == 0) nmask[gidx >> 1] = (n16 << 16) | peer;
+    }
+    if (n_other) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) other += __shfl_xor_sync(0xffffffffu, other, o);
+        if ((threadIdx.x & 31) == 0 && other) atomicAdd(n_other, (unsigned long long)other);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t dig_packed_words(int64_t n_bases) { return ((n_bases + 31) >> 5) << 1; }
+int64_t dig_nmask_words(int64_t n_bases) { return (n_bases + 31) >> 5; }
+
+int dig_pack_genome(const uint8_t *ascii_d, int64_t n_bases, uint32_t *packed2_d, uint32_t *nmask_d,
+                    unsigned long long *n_other_d, void *stream)
+{
+    DIG_CHECK_ARG(n_bases >= 0, "negative size");
+    if (n_bases == 0) return DIG_OK;
+    DIG_CHECK_ARG(ascii_d && packed2_d && nmask_d, "null pointer");
+    const int64_t n_groups = ((n_bases + 31) >> 5) << 1;      // two 16-base groups per N-mask word
+    const int aligned = (reinterpret_cast<uintptr_t>(ascii_d) & 15u) == 0;
+    const int threads = 256;
+    int64_t blocks = (n_groups + threads - 1) / threads;
+    const int64_t cap = (int64_t)dig::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(ascii_d, n_bases, packed2_d, nmask_d,
+                                                                        n_other_d, n_groups, aligned);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+}

@@ -11,7 +11,7 @@
  * Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
  * section 4), so this oracle is pinned against outputs of the UNMODIFIED
  * reference functions executed in the build container
- * (tests/golden/make_golden.py -> tests/golden/*.npz, checked by
+ * (tests/golden/make_golden.py -> tests/golden/ npz files, checked by
  * tests/test_oracle_golden.py).
  *
  * Reference lines restated here (paths relative to /root/reference):

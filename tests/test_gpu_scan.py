@@ -1,0 +1,143 @@
+"""GPU parity tests for K1 (pack), K2 (window scan) and K4 (strand-aware block counts).
+Everything goes through the C ABI (digdriver_b200.kernels -> libdigb200.so) and is compared
+bit-exactly with the golden vectors of the unmodified reference and with the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_genome
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gold_dev_genome(dev):
+    from digdriver_b200.genome import Genome, DeviceGenome
+    z = golden("scan")
+    g = Genome(["chr1", "chr2"], [z["seq_chr1"], z["seq_chr2"]])
+    return DeviceGenome.from_genome(g, dev)
+
+
+def test_pack_matches_layout_definition(dev, oracle):
+    from digdriver_b200.genome import DeviceGenome
+    rng = np.random.default_rng(5)
+    for n in (1, 15, 16, 17, 31, 32, 33, 1000, 4097, 100003):
+        seq = rng.choice(np.frombuffer(b"ACGTacgtNnRYx-", dtype=np.uint8), size=n)
+        for shift in (0, 3):                 # aligned and unaligned device pointers
+            buf = torch.zeros(n + shift, dtype=torch.uint8, device=dev)
+            buf[shift:] = torch.from_numpy(seq).to(dev)
+            p2, nm, n_other = DeviceGenome.pack_ascii(buf[shift:])
+            want_p2, want_nm = oracle.pack_genome(seq)
+            got_p2 = p2.cpu().numpy().view(np.uint32)
+            got_nm = nm.cpu().numpy().view(np.uint32)
+            assert np.array_equal(got_p2[:len(want_p2)], want_p2), n
+            assert np.all(got_p2[len(want_p2):] == 0)
+            assert np.array_equal(got_nm[:len(want_nm)], want_nm), n
+            assert int(n_other.item()) == int(np.isin(seq, np.frombuffer(b"RYx-", dtype=np.uint8)).sum())
+
+
+def test_synth_genome_matches_oracle(dev, oracle):
+    from digdriver_b200 import _lib
+    for g0, n, seed, frac in ((0, 70001, 3, 16), (1 << 20, 1 << 21, 9, 16), (12345, 5000, 1, 0)):
+        buf = torch.empty(n, dtype=torch.uint8, device=dev)
+        _lib.call("dig_synth_genome", buf.data_ptr(), g0, n, seed, frac, torch.cuda.current_stream(dev).cuda_stream)
+        want = oracle.synth_genome(g0, n, seed, frac)
+        assert np.array_equal(buf.cpu().numpy(), want)
+    assert 0.01 < (oracle.synth_genome(0, 1 << 22, 3) == ord("N")).mean() < 0.06
+
+
+@pytest.mark.parametrize("u,d", [(1, 1), (2, 2), (0, 0), (1, 2), (2, 0)])
+def test_scan_golden_bit_exact(gold_dev_genome, u, d):
+    from digdriver_b200 import kernels
+    z = golden("scan")
+    w = z["windows"][z["rows_%d_%d" % (u, d)]]
+    counts, totals = kernels.count_contexts(gold_dev_genome, w[:, 0] - 1, w[:, 1], w[:, 2], u, d, want_totals=True)
+    got = counts.cpu().numpy().astype(np.int64)
+    want = z["counts_%d_%d" % (u, d)]
+    assert np.array_equal(got, want)
+    assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
+
+
+def test_block_counts_strand_golden(gold_dev_genome):
+    from digdriver_b200 import kernels
+    z = golden("scan")
+    counts, _ = kernels.count_contexts(gold_dev_genome, z["blk_chrom"] - 1, z["blk_start"], z["blk_end"], 1, 1,
+                                       strand=z["blk_strand"])
+    got = np.repeat(counts.cpu().numpy(), 3, axis=1).astype(np.float64)
+    assert np.array_equal(got, z["blk_L192"])
+
+
+@pytest.mark.parametrize("u,d", [(1, 1), (2, 2), (0, 0), (2, 1), (0, 3), (3, 2)])
+def test_scan_random_regions_vs_oracle(dev, oracle, u, d):
+    """Ragged, empty, chromosome-edge and both-strand regions against the C oracle."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.genome import Genome, DeviceGenome
+    rng = np.random.default_rng(100 + 10 * u + d)
+    lens = [70001, 33, 5, 40000]
+    seqs = []
+    for L in lens:
+        s = rng.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), size=L)
+        for _ in range(max(1, L // 9000)):
+            a = int(rng.integers(0, L))
+            s[a:a + int(rng.integers(1, 300))] = ord("N")
+        seqs.append(s)
+    g = Genome(["chr%d" % (i + 1) for i in range(len(lens))], seqs)
+    dg = DeviceGenome.from_genome(g, dev)
+    n = 600
+    chrom = rng.integers(0, len(lens), n)
+    L = np.array(lens)[chrom]
+    start = (rng.random(n) * (L + 5)).astype(np.int64)
+    ln = np.where(rng.random(n) < 0.2, rng.integers(0, 4, n), rng.integers(0, 9000, n))
+    end = start + ln
+    start[::17] = 0
+    start = np.where((start > 0) & (start < u), u, start)      # the reference raises inside pysam there
+    end = np.maximum(end, start)
+    strand = np.where(rng.random(n) < 0.5, -1, 1).astype(np.int8)
+    seq = np.full(dg.n_bases, ord("N"), dtype=np.uint8)
+    for o, s in zip(dg.chrom_off, seqs):
+        seq[o:o + len(s)] = s
+    for st in (None, strand):
+        counts, totals = kernels.count_contexts(dg, chrom, start, end, u, d, strand=st, want_totals=True)
+        want, _ = oracle.count_regions(seq, dg.chrom_off, dg.chrom_len, chrom, start, end, u, d, strand=st)
+        got = counts.cpu().numpy().astype(np.int64)
+        bad = np.flatnonzero((got != want).any(axis=1))
+        assert bad.size == 0, "regions %s differ (first: chrom %d %d-%d)" % (
+            bad[:5], chrom[bad[0]], start[bad[0]], end[bad[0]])
+        assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
+
+
+def test_scan_chr22_sized_vs_oracle(dev, oracle):
+    """BASELINE config 1 scale: 51 Mb synthetic chromosome, 10 kb windows, both context sizes."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.genome import DeviceGenome, tile_windows
+    lengths = np.array([51_000_000], dtype=np.int64)
+    dg = DeviceGenome.synthetic(["chr22"], lengths, seed=22, device=dev)
+    wins = tile_windows([0], lengths, 10_000)
+    assert len(wins) == 5099
+    seq = oracle.synth_genome(0, int(lengths[0]), 22)
+    for (u, d) in ((1, 1), (2, 2)):
+        counts, totals = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], u, d, want_totals=True)
+        want, n_other = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], u, d)
+        assert n_other == 0
+        assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+        assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
+
+
+def test_scan_large_windows_totals_overflow_guard(dev, oracle):
+    """1 Mb windows: per-warp register totals must be flushed before they can overflow."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.genome import DeviceGenome, tile_windows
+    lengths = np.array([9_000_001], dtype=np.int64)
+    dg = DeviceGenome.synthetic(["chr1"], lengths, seed=4, device=dev, n_frac16=0)
+    wins = tile_windows([0], lengths, 1_000_000)
+    counts, totals = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], 0, 0, want_totals=True)
+    seq = oracle.synth_genome(0, int(lengths[0]), 4, 0)
+    want, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 0, 0)
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
