@@ -26,6 +26,16 @@ SIGNATURES = {
     "dig_pack_genome": (_I, [_P, _I64, _P, _P, _P, _P]),
     "dig_count_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P]),
     "dig_synth_genome": (_I, [_P, _I64, _I64, _U64, _I, _P]),
+    "dig_mutation_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P]),
+    "dig_count_hits": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
+    "dig_tabulate_elements": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P,
+                                   _I64, _I64, _I64, _P, _P, _P]),
+    "dig_tabulate_genes": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P]),
+    "dig_element_transfer": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P,
+                                  _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dig_nb_pvalue_greater_midp": (_I, [_P, _P, _P, _I64, _P, _P]),
+    "dig_nb_burden_test": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P]),
+    "dig_fisher_combine2": (_I, [_P, _P, _I64, _P, _P]),
 }
 
 _lib = None

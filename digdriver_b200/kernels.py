@@ -47,3 +47,204 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
                   re.data_ptr(), _ptr(st), n, int(n_up), int(n_down), out.data_ptr(), _ptr(totals),
                   _stream(dev, stream))
     return out, totals
+
+
+def mutation_contexts(genome, mut_chrom, mut_start, mut_ref, n_up=1, n_down=1, stream=None):
+    """K3: context index per mutation row (-1 = dropped by the reference).  Rows grouped by chromosome."""
+    dev = genome.device
+    mc = _dev(mut_chrom, torch.int32, dev)
+    ms = _dev(mut_start, torch.int64, dev)
+    mr = _dev(mut_ref, torch.uint8, dev)
+    out = torch.empty(mc.numel(), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_mutation_contexts", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
+                  genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), mc.data_ptr(), ms.data_ptr(),
+                  mr.data_ptr(), mc.numel(), int(n_up), int(n_down), out.data_ptr(), _stream(dev, stream))
+    return out
+
+
+def nb_pvalue_greater_midp(k, alpha, p, device="cuda:0", stream=None):
+    """K7: 0.5 * nbinom.pmf(k, alpha, p) + betainc(k + 1, alpha, 1 - p) in FP64 on the GPU."""
+    dev = torch.device(device)
+    kd, ad, pd_ = (_dev(x, torch.float64, dev) for x in (k, alpha, p))
+    out = torch.empty_like(kd)
+    with torch.cuda.device(dev):
+        _lib.call("dig_nb_pvalue_greater_midp", kd.data_ptr(), ad.data_ptr(), pd_.data_ptr(), kd.numel(),
+                  out.data_ptr(), _stream(dev, stream))
+    return out
+
+
+def nb_burden_test(k, alpha, theta, pi, device="cuda:0", want_exp=True, stream=None):
+    """K7 fused: EXP = ALPHA*THETA*Pi and the mid-p p-value with p = 1/(THETA*Pi+1)."""
+    dev = torch.device(device)
+    kd, ad, td, fd = (_dev(x, torch.float64, dev) for x in (k, alpha, theta, pi))
+    pval = torch.empty_like(kd)
+    exp = torch.empty_like(kd) if want_exp else None
+    with torch.cuda.device(dev):
+        _lib.call("dig_nb_burden_test", kd.data_ptr(), ad.data_ptr(), td.data_ptr(), fd.data_ptr(), kd.numel(),
+                  _ptr(exp), pval.data_ptr(), _stream(dev, stream))
+    return exp, pval
+
+
+def fisher_combine2(p1, p2, device="cuda:0", stream=None):
+    dev = torch.device(device)
+    a, b = _dev(p1, torch.float64, dev), _dev(p2, torch.float64, dev)
+    out = torch.empty_like(a)
+    with torch.cuda.device(dev):
+        _lib.call("dig_fisher_combine2", a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream(dev, stream))
+    return out
+
+
+def _pow2_at_least(n):
+    c = 1024
+    while c < n:
+        c *= 2
+    return c
+
+
+def _check_status(status, what):
+    code = int(status.item())
+    if code == 1:
+        raise _lib.DigError("%s: hash table overflow" % what)
+    if code == 2:
+        raise KeyError("%s: an element overlaps a window that is not in region_params "
+                       "(the reference raises KeyError on the same input)" % what)
+    if code == 3:
+        raise _lib.DigError("%s: element window span exceeds the shared-memory bitmap" % what)
+    if code != 0:
+        raise _lib.DigError("%s: status %d" % (what, code))
+
+
+def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_sample, mut_isindel,
+                      n_elt, n_sample, max_muts_per_sample=10 ** 9, max_per_elt_per_sample=3 * 10 ** 9,
+                      device="cuda:0", stream=None):
+    """K5: (OBS_SAMPLES, OBS_SNV, OBS_INDEL) per element and the per-sample totals used for the
+    hypermutator black-list.  Blocks need not be sorted.  Returns (obs int64 [n_elt,3], sample_tot [n_sample])."""
+    dev = torch.device(device)
+    bks = np.asarray(blk_kstart, dtype=np.int64)
+    order = np.argsort(bks, kind="stable")
+    bks = bks[order]
+    bke = np.asarray(blk_kend, dtype=np.int64)[order]
+    belt = np.asarray(blk_elt, dtype=np.int32)[order]
+    pmax = np.maximum.accumulate(bke) if len(bke) else bke
+    t = {k: _dev(v, dt, dev) for k, v, dt in (
+        ("bks", bks, torch.int64), ("bke", bke, torch.int64), ("pmax", pmax, torch.int64), ("belt", belt, torch.int32),
+        ("mks", mut_kstart, torch.int64), ("mke", mut_kend, torch.int64), ("ms", mut_sample, torch.int32),
+        ("mi", mut_isindel, torch.uint8))}
+    n_blk, n_mut = len(bks), t["mks"].numel()
+    sptr = _stream(dev, stream)
+    with torch.cuda.device(dev):
+        n_hits = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.call("dig_count_hits", t["bks"].data_ptr(), t["bke"].data_ptr(), t["pmax"].data_ptr(),
+                  t["belt"].data_ptr(), n_blk, t["mks"].data_ptr(), t["mke"].data_ptr(), n_mut, n_hits.data_ptr(), sptr)
+        cap = _pow2_at_least(2 * int(n_hits.item()) + 16)
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        snv = torch.empty(cap, dtype=torch.int32, device=dev)
+        ind = torch.empty(cap, dtype=torch.int32, device=dev)
+        sample_tot = torch.empty(max(n_sample, 1), dtype=torch.int64, device=dev)
+        obs = torch.empty((max(n_elt, 1), 3), dtype=torch.int64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("dig_tabulate_elements", t["bks"].data_ptr(), t["bke"].data_ptr(), t["pmax"].data_ptr(),
+                  t["belt"].data_ptr(), n_blk, t["mks"].data_ptr(), t["mke"].data_ptr(), t["ms"].data_ptr(),
+                  t["mi"].data_ptr(), n_mut, keys.data_ptr(), snv.data_ptr(), ind.data_ptr(), cap, n_sample,
+                  sample_tot.data_ptr(), int(min(max_muts_per_sample, 2 ** 62)),
+                  int(min(max_per_elt_per_sample, 2 ** 62)), n_elt, obs.data_ptr(), status.data_ptr(), sptr)
+        _check_status(status, "dig_tabulate_elements")
+    return obs[:n_elt], sample_tot[:n_sample]
+
+
+def tabulate_genes(mut_gene, mut_sample, mut_class, n_gene, max_per_gene_per_sample=3 * 10 ** 9,
+                   device="cuda:0", stream=None):
+    """K5 (genes): obs int64 [n_gene,5] (SYN, MIS, NONS, SPL, INDEL) and nsamp int64 [n_gene,7]
+    (SYN, MIS, NONS, SPL, TRUNC, NONSYN, INDEL)."""
+    dev = torch.device(device)
+    mg, ms, mc = _dev(mut_gene, torch.int32, dev), _dev(mut_sample, torch.int32, dev), _dev(mut_class, torch.uint8, dev)
+    n_mut = mg.numel()
+    cap = _pow2_at_least(2 * n_mut + 16)
+    with torch.cuda.device(dev):
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        cnt = torch.empty((cap, 5), dtype=torch.int32, device=dev)
+        obs = torch.empty((max(n_gene, 1), 5), dtype=torch.int64, device=dev)
+        nsamp = torch.empty((max(n_gene, 1), 7), dtype=torch.int64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("dig_tabulate_genes", mg.data_ptr(), ms.data_ptr(), mc.data_ptr(), n_mut, keys.data_ptr(),
+                  cnt.data_ptr(), cap, int(min(max_per_gene_per_sample, 2 ** 62)), n_gene, obs.data_ptr(),
+                  nsamp.data_ptr(), status.data_ptr(), _stream(dev, stream))
+        _check_status(status, "dig_tabulate_genes")
+    return obs[:n_gene], nsamp[:n_gene]
+
+
+def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window, win_map_off, win_map,
+                     win_counts, y_pred, std, y_true, flag, d_pr, blk_counts=None, L_elt=None,
+                     device="cuda:0", stream=None):
+    """K6.  Region-parameter arrays are [n_cohort, n_win] (1-D inputs are taken as one cohort), d_pr is
+    [n_cohort, 192].  Returns a dict of device tensors (MU, SIGMA, R_OBS, FLAG: [n_cohort, n_elt];
+    R_SIZE, ELT_SIZE, N_WIN: [n_elt]; P: [n_cohort, n_elt, n_col])."""
+    dev = torch.device(device)
+    ec, es = _dev(elt_chrom, torch.int32, dev), _dev(elt_strand, torch.int8, dev)
+    bp, bs, be = (_dev(x, torch.int64, dev) for x in (blk_ptr, blk_start, blk_end))
+    wmo, wm = _dev(win_map_off, torch.int64, dev), _dev(win_map, torch.int32, dev)
+    wc = _dev(win_counts, torch.int32, dev)
+    yp, sd, yt = (_dev(x, torch.float64, dev).reshape(-1, wc.shape[0]) for x in (y_pred, std, y_true))
+    fl = _dev(np.asarray(flag).astype(np.uint8) if not isinstance(flag, torch.Tensor) else flag.to(torch.uint8),
+              torch.uint8, dev).reshape(-1, wc.shape[0])
+    dp = _dev(d_pr, torch.float64, dev).reshape(-1, 192)
+    n_cohort = dp.shape[0]
+    assert yp.shape[0] == n_cohort and sd.shape[0] == n_cohort and yt.shape[0] == n_cohort and fl.shape[0] == n_cohort
+    n_elt = ec.numel()
+    n_win = wc.shape[0]
+    if blk_counts is not None:
+        bc, Le, n_col = _dev(blk_counts, torch.int32, dev), None, 1
+    else:
+        Le = _dev(L_elt, torch.float64, dev)
+        Le = Le.reshape(n_elt, 192, -1)
+        bc, n_col = None, Le.shape[2]
+    # widest window span of any element (host side: the block tables come from the host anyway)
+    bs_h, be_h, bp_h = (x.cpu().numpy() for x in (bs, be, bp))
+    max_span = 1
+    if n_elt and len(bs_h):
+        lo = np.floor_divide(bs_h, window)
+        hi = -np.floor_divide(-be_h, window)
+        owner = np.repeat(np.arange(n_elt), np.diff(bp_h))
+        wmin = np.full(n_elt, np.iinfo(np.int64).max)
+        wmax = np.full(n_elt, np.iinfo(np.int64).min)
+        np.minimum.at(wmin, owner, lo)
+        np.maximum.at(wmax, owner, hi)
+        has = wmax > wmin
+        if has.any():
+            max_span = int((wmax[has] - wmin[has]).max())
+    out = {
+        "MU": torch.empty((n_cohort, n_elt), dtype=torch.float64, device=dev),
+        "SIGMA": torch.empty((n_cohort, n_elt), dtype=torch.float64, device=dev),
+        "R_OBS": torch.empty((n_cohort, n_elt), dtype=torch.float64, device=dev),
+        "FLAG": torch.empty((n_cohort, n_elt), dtype=torch.uint8, device=dev),
+        "R_SIZE": torch.empty(n_elt, dtype=torch.int64, device=dev),
+        "ELT_SIZE": torch.empty(n_elt, dtype=torch.int64, device=dev),
+        "P": torch.empty((n_cohort, n_elt, n_col), dtype=torch.float64, device=dev),
+        "N_WIN": torch.empty(n_elt, dtype=torch.int32, device=dev),
+    }
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_element_transfer", ec.data_ptr(), es.data_ptr(), bp.data_ptr(), bs.data_ptr(), be.data_ptr(),
+                  n_elt, int(window), wmo.data_ptr(), wm.data_ptr(), wc.data_ptr(), yp.data_ptr(), sd.data_ptr(),
+                  yt.data_ptr(), fl.data_ptr(), n_win, n_cohort, dp.data_ptr(), _ptr(bc), _ptr(Le), n_col, max_span,
+                  out["MU"].data_ptr(), out["SIGMA"].data_ptr(), out["R_OBS"].data_ptr(), out["FLAG"].data_ptr(),
+                  out["R_SIZE"].data_ptr(), out["ELT_SIZE"].data_ptr(), out["P"].data_ptr(),
+                  out["N_WIN"].data_ptr(), status.data_ptr(), _stream(dev, stream))
+        _check_status(status, "dig_element_transfer")
+    return out
+
+
+def build_window_map(win_chrom_idx, win_start, window, n_chrom):
+    """Dense (chromosome, window number) -> row map for K6.  Returns (win_map_off int64 [n_chrom+1],
+    win_map int32)."""
+    wc = np.asarray(win_chrom_idx, dtype=np.int64)
+    wn = np.asarray(win_start, dtype=np.int64) // int(window)
+    per = np.zeros(n_chrom, dtype=np.int64)
+    if len(wc):
+        np.maximum.at(per, wc, wn + 1)
+    off = np.zeros(n_chrom + 1, dtype=np.int64)
+    off[1:] = np.cumsum(per)
+    wmap = np.full(int(off[-1]), -1, dtype=np.int32)
+    wmap[off[wc] + wn] = np.arange(len(wc), dtype=np.int32)
+    return off, wmap

@@ -79,6 +79,118 @@ int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64
                        const int8_t *reg_strand_d, int64_t n_reg, int n_up, int n_down,
                        int32_t *counts_d, unsigned long long *totals_d, void *stream);
 
+
+/* ---------------------------------------------------------------------------------
+ * K3  mutation context lookup with REF check.
+ * Replaces: mutation_contexts_by_chrom (sequence_tools.py:130-178).
+ * Rows must be grouped by chromosome, in file order inside each group (what pandas
+ * groupby('CHROM') hands to the reference loop).
+ *   mut_ref_d  [n] uint8: 0..3 for a single A/C/G/T character, anything else 255
+ *   ctx_out_d  [n] int32: context index, or -1 where the reference drops the row: REF does
+ *              not match the genome (:145-148), the context contains N (:48-49), or an
+ *              earlier row of the same START run was dropped for a REF mismatch (the
+ *              cntxt_lst[-1] reuse at :150-151).  Rows whose context would leave the
+ *              chromosome are dropped as well.
+ */
+int dig_mutation_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
+                          const int64_t *chrom_off_d, const int64_t *chrom_len_d,
+                          const int32_t *mut_chrom_d, const int64_t *mut_start_d, const uint8_t *mut_ref_d,
+                          int64_t n_mut, int n_up, int n_down, int32_t *ctx_out_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * K5  observed mutation counts per element.
+ * Replaces: bedtools intersect -wa -wb + the pandas group-bys of
+ * tabulate_muts_per_sample_per_element / tabulate_mutations_in_element
+ * (data_tools/mutation_tools.py:191-230, :155-189).
+ * Coordinates are "keyed" positions (chrom_id << 32 | position) so no genome layout is needed.
+ *   blk_*_d      bed6 blocks sorted by blk_kstart; blk_pmax_d[i] = max(blk_kend[0..i]);
+ *                blk_elt_d = element id of each block
+ *   mut_*_d      mutation rows (already de-duplicated on CHROM,START,END,REF,ALT,SAMPLE when the
+ *                reference is called with drop_duplicates=True); mut_isindel_d = (ANNOT == 'INDEL')
+ * A mutation hits a block when [START,END) and [bs,be) share >= 1 base; a mutation hitting several
+ * blocks of one element counts once (drop_duplicates on (..., ELT), mutation_tools.py:208).
+ *
+ * dig_count_hits: *n_hits_d += number of (mutation, element) pairs -> size the hash table
+ * (capacity: power of two >= 2 * n_hits).
+ * dig_tabulate_elements: builds the (element, sample) table, then
+ *   sample_tot_d [n_sample] uint64: total OBS_MUT per sample over all elements (zeroed inside);
+ *                samples with sample_tot > max_muts_per_sample are black-listed (:163-165)
+ *   obs_d        [n_elt, 3] int64: OBS_SAMPLES, OBS_SNV, OBS_INDEL (zeroed inside); per
+ *                (element, sample) counts are capped at max_per_elt_per_sample (:168-169)
+ *   status_d     [1] int32: set to 1 if the hash table overflowed (results invalid)
+ */
+int dig_count_hits(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d,
+                   const int32_t *blk_elt_d, int64_t n_blk, const int64_t *mut_kstart_d,
+                   const int64_t *mut_kend_d, int64_t n_mut, unsigned long long *n_hits_d, void *stream);
+int dig_tabulate_elements(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d,
+                          const int32_t *blk_elt_d, int64_t n_blk, const int64_t *mut_kstart_d,
+                          const int64_t *mut_kend_d, const int32_t *mut_sample_d, const uint8_t *mut_isindel_d,
+                          int64_t n_mut, unsigned long long *tab_key_d, uint32_t *tab_snv_d,
+                          uint32_t *tab_indel_d, int64_t capacity, int64_t n_sample,
+                          unsigned long long *sample_tot_d, int64_t max_muts_per_sample,
+                          int64_t max_per_elt_per_sample, int64_t n_elt, int64_t *obs_d, int32_t *status_d,
+                          void *stream);
+
+/* Gene flavour: counts keyed by the file's GENE / ANNOT columns.
+ * Replaces: mutations_per_gene (mutation_tools.py:329-361) and the distinct-sample counts of
+ * transfer_gene_model (transfer_tools.py:235-265).
+ *   mut_class_d  uint8: 0 Synonymous, 1 Missense, 2 Nonsense, 3 Essential_Splice, 4 INDEL, 255 other
+ *   obs_d        [n_gene, 5] int64 OBS_SYN, OBS_MIS, OBS_NONS, OBS_SPL, OBS_INDEL (per (gene,sample,class)
+ *                counts capped at max_per_gene_per_sample)
+ *   nsamp_d      [n_gene, 7] int64 N_SAMP_SYN, MIS, NONS, SPL, TRUNC, NONSYN, INDEL (not capped)
+ *   tab_cnt_d    [capacity, 5] uint32 scratch
+ */
+int dig_tabulate_genes(const int32_t *mut_gene_d, const int32_t *mut_sample_d, const uint8_t *mut_class_d,
+                       int64_t n_mut, unsigned long long *tab_key_d, uint32_t *tab_cnt_d, int64_t capacity,
+                       int64_t max_per_gene_per_sample, int64_t n_gene, int64_t *obs_d, int64_t *nsamp_d,
+                       int32_t *status_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * K6  element transfer ("pretrain"): window-set enumeration, region parameters and the
+ * context-weighted mutability fraction.
+ * Replaces: get_ideal_overlaps + get_region_params(_direct) (genic_driver_tools.py:275-283, :235-272),
+ * the per-element loops of preprocess_nonc (sequence_tools.py:619-641), nonc_model
+ * (genic_driver_tools.py:347-390), genic_model (:86-168) and DIG_onthefly (onthefly_tools.py:109-165).
+ *   elements     CSR: element e owns blocks [blk_ptr[e], blk_ptr[e+1]); elt_chrom = index into win_map_off
+ *   windows      win_map_d[win_map_off_d[c] + ws/window] = row of window (c, ws) in the tables below, -1 if
+ *                the window is not in the map (the reference raises KeyError there; status_d is set to 2)
+ *   win_counts_d [n_win, 64] int32 trinucleotide counts of every window (K2 output)
+ *   y_pred_d, std_d, y_true_d [n_cohort, n_win] double; flag_d [n_cohort, n_win] uint8
+ *   d_pr_d       [n_cohort, 192] double, substitution order = sorted 'CTX>CTX2' names (mk_trans_idx)
+ *   L            either blk_counts_d [n_blk, 64] int32 (K4 output, strand-aware; L192 = repeat(sum, 3),
+ *                n_col = 1) or L_elt_d [n_elt, 192, n_col] double (genes: silent, mis, nons, splice)
+ *   outputs      mu, sigma, r_obs [n_cohort, n_elt] double; flag_out [n_cohort, n_elt] uint8;
+ *                r_size, elt_size [n_elt] int64 (elt_size = int(sum(L)/3) in blk_counts mode,
+ *                sum(end - start + 1) over blocks otherwise); p_out [n_cohort, n_elt, n_col] double;
+ *                n_win_out [n_elt] int32
+ *   status_d     [1] int32: 0 ok, 2 missing window, 3 window span too large for shared memory
+ */
+int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
+                         const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt, int64_t window,
+                         const int64_t *win_map_off_d, const int32_t *win_map_d, const int32_t *win_counts_d,
+                         const double *y_pred_d, const double *std_d, const double *y_true_d,
+                         const uint8_t *flag_d, int64_t n_win, int n_cohort, const double *d_pr_d,
+                         const int32_t *blk_counts_d, const double *L_elt_d, int n_col, int max_span_windows,
+                         double *mu_d, double *sigma_d, double *r_obs_d, uint8_t *flag_out_d, int64_t *r_size_d,
+                         int64_t *elt_size_d, double *p_out_d, int32_t *n_win_out_d, int32_t *status_d,
+                         void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * K7  FP64 negative-binomial burden test.
+ * dig_nb_pvalue_greater_midp replaces nb_model.nb_pvalue_greater_midp(k, alpha, p) (nb_model.py:271-278):
+ *     0.5 * nbinom.pmf(k, alpha, p) + betainc(k + 1, alpha, 1 - p)
+ * dig_nb_burden_test fuses element_expected_muts_nb + element_pvalue_burden_nb
+ * (transfer_tools.py:343-344, :473-482): EXP = ALPHA*THETA*Pi, p = 1/(THETA*Pi + 1) evaluated in the
+ * reference's operation order.  exp_out_d may be null.
+ * dig_fisher_combine2 replaces chi2.sf(-2 (ln p1 + ln p2), df=4) (transfer_tools.py:860-861, :1086-1087).
+ * Tolerance contract: |dlog10 p| <= 1e-6 against SciPy; expectations are bit-exact.
+ */
+int dig_nb_pvalue_greater_midp(const double *k_d, const double *alpha_d, const double *p_d, int64_t n,
+                               double *pval_out_d, void *stream);
+int dig_nb_burden_test(const double *k_d, const double *alpha_d, const double *theta_d, const double *pi_d,
+                       int64_t n, double *exp_out_d, double *pval_out_d, void *stream);
+int dig_fisher_combine2(const double *p1_d, const double *p2_d, int64_t n, double *out_d, void *stream);
+
 /* ---------------------------------------------------------------------------------
  * Synthetic genome generator (BASELINE.json configs are synthetic): position g is a pure
  * function of (seed, g); identical to orc_synth_genome in oracle/dig_oracle.c.
