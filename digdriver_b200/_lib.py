@@ -27,6 +27,7 @@ SIGNATURES = {
     "dig_count_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P]),
     "dig_synth_genome": (_I, [_P, _I64, _I64, _U64, _I, _P]),
     "dig_mutation_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P]),
+    "dig_substitution_counts": (_I, [_P, _P, _I64, _I, _I, _P, _P]),
     "dig_count_hits": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "dig_tabulate_elements": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P,
                                    _I64, _I64, _I64, _P, _P, _P]),
@@ -39,6 +40,15 @@ SIGNATURES = {
 }
 
 _lib = None
+
+# kernels launched per successful call (memsets not counted); summed into `launch_count` so that
+# bench.py can report how many of OUR kernels ran inside a timed region
+KERNELS_PER_CALL = {
+    "dig_pack_genome": 1, "dig_count_contexts": 1, "dig_synth_genome": 1, "dig_mutation_contexts": 1,
+    "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2,
+    "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
+}
+launch_count = 0
 
 
 class DigError(RuntimeError):
@@ -71,5 +81,7 @@ def check(rc, what=""):
 
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
+    global launch_count
     fn = getattr(load(), name)
     check(fn(*args), name)
+    launch_count += KERNELS_PER_CALL.get(name, 0)

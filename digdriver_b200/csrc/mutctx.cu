@@ -50,7 +50,50 @@ __global__ void __launch_bounds__(256) mutctx_kernel(
     }
 }
 
+// 3K-bin histogram of substitutions: bin = 3 * ctx + rank(ALT among the non-REF bases, alphabetical),
+// i.e. the sorted 'CTX>CTX2' order of mk_trans_idx (sequence_tools.py:282-289) for trinucleotides.
+__global__ void __launch_bounds__(256) subst_hist_kernel(const int32_t *__restrict__ ctx,
+                                                         const uint8_t *__restrict__ alt, int64_t n, int n_down,
+                                                         int n_bins, unsigned long long *__restrict__ counts)
+{
+    extern __shared__ unsigned int sh[];
+    for (int k = threadIdx.x; k < n_bins; k += blockDim.x) sh[k] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t c = ctx[i];
+        const uint32_t a = alt[i];
+        if (c < 0 || a > 3u) continue;
+        const uint32_t ref = ((uint32_t)c >> (2 * n_down)) & 3u;
+        if (a == ref) continue;
+        atomicAdd(sh + 3 * c + (int)(a > ref ? a - 1u : a), 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_bins; k += blockDim.x)
+        if (sh[k]) atomicAdd(counts + k, (unsigned long long)sh[k]);
+}
+
 }  // namespace
+
+extern "C" int dig_substitution_counts(const int32_t *ctx_d, const uint8_t *alt_d, int64_t n, int n_up, int n_down,
+                                       unsigned long long *counts_d, void *stream)
+{
+    DIG_CHECK_ARG(n >= 0, "negative size");
+    DIG_CHECK_ARG(n_up >= 0 && n_down >= 0 && n_up + n_down <= 5, "unsupported context size");
+    DIG_CHECK_ARG(counts_d != nullptr, "null pointer");
+    const int n_bins = 3 << (2 * (n_up + n_down + 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    DIG_CUDA(cudaMemsetAsync(counts_d, 0, (size_t)n_bins * sizeof(unsigned long long), st));
+    if (n == 0) return DIG_OK;
+    DIG_CHECK_ARG(ctx_d && alt_d, "null pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)dig::sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    subst_hist_kernel<<<(unsigned)blocks, 256, (size_t)n_bins * sizeof(unsigned int), st>>>(ctx_d, alt_d, n, n_down,
+                                                                                          n_bins, counts_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
 
 extern "C" int dig_mutation_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
                                      const int64_t *chrom_off_d, const int64_t *chrom_len_d,

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) elt_finalize_kernel(const unsigned long l
                                                            const uint32_t *__restrict__ indel, int64_t capacity,
                                                            const unsigned long long *__restrict__ sample_tot,
                                                            int64_t max_per_sample, int64_t max_per_elt_sample,
-                                                           int64_t *obs)
+                                                           int64_t n_elt, int64_t *obs)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < capacity; s += stride) {
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) elt_finalize_kernel(const unsigned long l
         if (key == 0ull) continue;
         const uint32_t sample = (uint32_t)((key - 1ull) & 0xFFFFFFFFull);
         const int64_t e = (int64_t)((key - 1ull) >> 32);
+        if (e >= n_elt) continue;
         if ((int64_t)sample_tot[sample] > max_per_sample) continue;      // hypermutator black-list
         int64_t a = snv[s], b = indel[s];
         if (a > max_per_elt_sample) a = max_per_elt_sample;
@@ -148,13 +149,15 @@ __global__ void __launch_bounds__(256) gene_insert_kernel(const int32_t *__restr
 
 __global__ void __launch_bounds__(256) gene_finalize_kernel(const unsigned long long *__restrict__ keys,
                                                             const uint32_t *__restrict__ cnt, int64_t capacity,
-                                                            int64_t cap_per, int64_t *obs, int64_t *nsamp)
+                                                            int64_t cap_per, int64_t n_gene, int64_t *obs,
+                                                            int64_t *nsamp)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < capacity; s += stride) {
         const unsigned long long key = keys[s];
         if (key == 0ull) continue;
         const int64_t g = (int64_t)((key - 1ull) >> 32);
+        if (g >= n_gene) continue;                 // a named gene that is not in the model table
         int64_t c[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) c[j] = cnt[s * 5 + j];
@@ -231,7 +234,7 @@ int dig_tabulate_elements(const int64_t *blk_kstart_d, const int64_t *blk_kend_d
                                                                  sample_tot_d);
     DIG_CHECK_LAUNCH();
     elt_finalize_kernel<<<grid_for(capacity), 256, 0, st>>>(tab_key_d, tab_snv_d, tab_indel_d, capacity, sample_tot_d,
-                                                            max_muts_per_sample, max_per_elt_per_sample, obs_d);
+                                                            max_muts_per_sample, max_per_elt_per_sample, n_elt, obs_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
@@ -258,7 +261,7 @@ int dig_tabulate_genes(const int32_t *mut_gene_d, const int32_t *mut_sample_d, c
                                                         tab_cnt_d, capacity, status_d);
     DIG_CHECK_LAUNCH();
     gene_finalize_kernel<<<grid_for(capacity), 256, 0, st>>>(tab_key_d, tab_cnt_d, capacity,
-                                                             max_per_gene_per_sample, obs_d, nsamp_d);
+                                                             max_per_gene_per_sample, n_gene, obs_d, nsamp_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

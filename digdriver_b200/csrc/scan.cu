@@ -1,16 +1,25 @@
 // K2 / K4: per-region k-mer context histograms over the 2-bit packed genome.
 //
-// Design (B200): one WARP owns one region (a 10 kb window is 313 32-base words, i.e. ten
-// fully coalesced 384-byte warp loads) and a private K-bin int32 histogram in shared memory,
-// so there is no cross-warp contention and only __syncwarp() is ever needed.  Every lane
-// takes one 32-base word per iteration (one 64-bit load of bases + one 32-bit load of the
-// N mask), gets the 2-base halo of its neighbours by shuffle, and issues 32 shared-memory
-// atomics whose k-mer indices are produced by one funnel shift + one mask each (all shift
-// amounts are compile-time constants).  Validity (window range + "k-mer contains N") is a
-// 32-bit mask built with a handful of shifts; when the whole warp is fully valid the atomics
-// run unpredicated.  The histogram is written out with 128-bit coalesced stores, re-zeroed
-// in the same pass, and folded into per-lane register totals that become the genome-wide
-// context totals (DigPreprocess.py:59) without re-reading the counts.
+// Design (B200).  One WARP owns one region (a 10 kb window is 313 32-base words, i.e. ten fully
+// coalesced 384-byte warp loads) and a private histogram in shared memory, so there is no
+// cross-warp contention and only __syncwarp() is ever needed.  Every lane takes one 32-base word
+// per iteration (one 64-bit load of bases + one 32-bit load of the N mask, prefetched one
+// iteration ahead), gets the halo of its neighbours by shuffle, and issues 32 shared-memory
+// atomics (ATOMS.POPC.INC) whose addresses are produced by ONE funnel shift and ONE LOP3 each:
+// the histogram base is aligned so that (shifted & mask) | base is the address, and all shift
+// amounts are compile-time constants.
+//
+// The kernel is bound by shared-memory atomic wavefronts (ncu: l1tex data-pipe), not by HBM, so
+// the two histogram layouts below are chosen to minimise wavefronts per base:
+//   * PRIVATE (K <= 64): every lane owns a private K-bin int32 histogram laid out so that lane l
+//     only ever touches bank l -- every atomic instruction is exactly one conflict-free wavefront.
+//     The 32 copies are summed at the end of the region with skewed, conflict-free reads.
+//   * SHARED (K = 1024): one K-bin histogram per warp (32 private copies would need 128 KB); random
+//     k-mers give ~3.4 wavefronts per instruction, which is the floor for this layout.
+// Words that are only partly valid (window edges, N runs) are handled cooperatively: the word is
+// broadcast and lane i takes position i, so the unrolled path never needs predicates.
+// Write-out uses 128-bit / 128-byte coalesced streaming stores; genome-wide context totals
+// (DigPreprocess.py:59) are accumulated per CTA in shared memory and flushed once.
 //
 // HBM traffic per base: 0.25 B bases + 0.125 B mask + 4K/W B counts.
 #include "dig_common.cuh"
@@ -19,6 +28,9 @@ namespace {
 
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
+
+// kilobases a CTA may fold into its int32 shared-memory totals before it switches to global atomics
+unsigned int g_tot_limit_kb = 1u << 20;
 
 // reverse-complement of a klen-base k-mer index (5' base most significant)
 __device__ __forceinline__ uint32_t revcomp_key(uint32_t key, int klen)
@@ -59,67 +71,114 @@ __device__ __forceinline__ RegionSpan region_span(const int64_t *__restrict__ ch
     return sp;
 }
 
-template <int U, int D, int I>
-__device__ __forceinline__ uint32_t extract_key(uint32_t a, uint32_t b0, uint32_t b1, uint32_t c)
+__device__ __forceinline__ void smem_inc(uint32_t addr)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
+}
+
+// (k-mer index of position I) << SCALE, from the four words [a|b0|b1|c] that cover bases
+// 32w-16 .. 32w+47 (MSB first).  One shift + one mask, all amounts compile-time.
+template <int U, int D, int I, int SCALE>
+__device__ __forceinline__ uint32_t scaled_key(uint32_t a, uint32_t b0, uint32_t b1, uint32_t c)
 {
     constexpr int KLEN = U + D + 1;
-    constexpr uint32_t MASK = (1u << (2 * KLEN)) - 1u;
+    constexpr uint32_t MASK = ((1u << (2 * KLEN)) - 1u) << SCALE;
     constexpr int BO = 2 * (16 + I - U);        // bit offset from the MSB of [a|b0|b1|c]
     constexpr int Q = BO >> 5;
     constexpr int R = BO & 31;
     const uint32_t hi = Q == 0 ? a : (Q == 1 ? b0 : b1);
     const uint32_t lo = Q == 0 ? b0 : (Q == 1 ? b1 : c);
     if constexpr (R + 2 * KLEN <= 32) {
-        return (hi >> (32 - R - 2 * KLEN)) & MASK;
+        constexpr int SH = 32 - R - 2 * KLEN;   // key = hi >> SH
+        if constexpr (SH >= SCALE) return (hi >> (SH - SCALE)) & MASK;
+        else return (hi << (SCALE - SH)) & MASK;
     } else {
-        return __funnelshift_r(lo, hi, 64 - R - 2 * KLEN) & MASK;
+        constexpr int S = 64 - R - 2 * KLEN;    // key = low32((hi:lo) >> S), 0 < S < 32
+        if constexpr (S >= SCALE) return __funnelshift_r(lo, hi, S - SCALE) & MASK;
+        else return (lo << (SCALE - S)) & MASK;
     }
 }
 
-template <int U, int D, int I>
+template <int U, int D, int I, int SCALE>
 struct Unroll {
-    template <bool PRED>
-    static __device__ __forceinline__ void run(int *hist, uint32_t a, uint32_t b0, uint32_t b1, uint32_t c,
-                                               uint32_t valid)
+    static __device__ __forceinline__ void run(uint32_t base, uint32_t a, uint32_t b0, uint32_t b1, uint32_t c)
     {
-        if (!PRED || (valid & (0x80000000u >> I))) atomicAdd(hist + extract_key<U, D, I>(a, b0, b1, c), 1);
-        Unroll<U, D, I + 1>::template run<PRED>(hist, a, b0, b1, c, valid);
+        smem_inc(scaled_key<U, D, I, SCALE>(a, b0, b1, c) | base);
+        Unroll<U, D, I + 1, SCALE>::run(base, a, b0, b1, c);
     }
 };
-template <int U, int D>
-struct Unroll<U, D, 32> {
-    template <bool PRED>
-    static __device__ __forceinline__ void run(int *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
+template <int U, int D, int SCALE>
+struct Unroll<U, D, 32, SCALE> {
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
 };
 
+// k-mer index of position `pos` (runtime) of the same four words
+template <int U, int D>
+__device__ __forceinline__ uint32_t runtime_key(uint32_t a, uint32_t b0, uint32_t b1, uint32_t c, int pos)
+{
+    constexpr int KLEN = U + D + 1;
+    const int bo = 2 * (16 + pos - U);
+    const int q = bo >> 5, r = bo & 31;
+    const uint32_t hi = q == 0 ? a : (q == 1 ? b0 : b1);
+    const uint32_t lo = q == 0 ? b0 : (q == 1 ? b1 : c);
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (uint32_t)(v >> (64 - r - 2 * KLEN)) & ((1u << (2 * KLEN)) - 1u);
+}
+
+struct WordLoad {
+    uint2 pw;
+    uint32_t nm;
+};
+
+// word `rel` of the current region (rel counts 32-base words from the region's first word)
+__device__ __forceinline__ WordLoad load_word(const uint2 *__restrict__ pv, const uint32_t *__restrict__ pn, int rel,
+                                              int avail)
+{
+    WordLoad x;
+    x.pw = make_uint2(0u, 0u);
+    x.nm = 0xFFFFFFFFu;
+    if (rel < avail) {
+        x.pw = __ldg(pv + rel);
+        x.nm = __ldg(pn + rel);
+    }
+    return x;
+}
+
 // ---------------------------------------------------------------------------------------
-// fast kernel: symmetric context (U == D), K = 4^(2U+1) <= 1024
+// fast kernel: symmetric context (U == D).  PRIVATE selects the lane-private layout.
 // ---------------------------------------------------------------------------------------
-template <int U>
-__global__ void __launch_bounds__(THREADS) scan_sym_kernel(
+template <int U, bool PRIVATE>
+__global__ void __launch_bounds__(THREADS, PRIVATE ? 3 : 3) scan_sym_kernel(
     const uint2 *__restrict__ p2v, const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask,
     int64_t n_words32, const int64_t *__restrict__ chrom_off, const int64_t *__restrict__ chrom_len,
     const int32_t *__restrict__ reg_chrom, const int64_t *__restrict__ reg_start,
     const int64_t *__restrict__ reg_end, const int8_t *__restrict__ reg_strand, int64_t n_reg,
-    int32_t *__restrict__ counts, unsigned long long *__restrict__ totals)
+    int32_t *__restrict__ counts, unsigned long long *__restrict__ totals, unsigned int tot_limit_kb)
 {
     constexpr int D = U;
     constexpr int KLEN = 2 * U + 1;
     constexpr int K = 1 << (2 * KLEN);
-    constexpr int K4 = K / 4;                         // int4 chunks (K >= 4)
-    constexpr int NTOT = (K4 + 31) / 32;              // int4 chunks per lane
-    extern __shared__ __align__(16) int smem[];
+    constexpr int SCALE = PRIVATE ? 7 : 2;                         // bytes per bin: 32 lanes x 4 B, or 4 B
+    constexpr uint32_t HIST_BYTES = (uint32_t)K << SCALE;          // per warp, also its alignment
+    constexpr int BPL = (K + 31) / 32;                             // bins per lane at write-out (PRIVATE)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int cta_acc_kb;     // kilobases folded into the int32 CTA totals so far
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    int *hist = smem + warp * K;
-    for (int k = lane; k < K; k += 32) hist[k] = 0;
-    __syncwarp();
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+    // layout: [CTA totals: K int32][pad to HIST_BYTES][WARPS_PER_BLOCK histograms of HIST_BYTES]
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t tot_addr = smem0;
+    const uint32_t hist0 = (smem0 + K * 4u + HIST_BYTES - 1u) & ~(HIST_BYTES - 1u);
+    const uint32_t hist = hist0 + (uint32_t)warp * HIST_BYTES;
+    const uint32_t lane_base = PRIVATE ? hist + (uint32_t)lane * 4u : hist;
+    int *hist_p = reinterpret_cast<int *>(smem_raw + (hist - smem0));
+    int *tot_p = reinterpret_cast<int *>(smem_raw);
 
-    int tot[NTOT * 4];
-#pragma unroll
-    for (int j = 0; j < NTOT * 4; ++j) tot[j] = 0;
-    int64_t tot_bases = 0;
+    for (int k = threadIdx.x; k < K; k += THREADS) tot_p[k] = 0;
+    if (threadIdx.x == 0) cta_acc_kb = 0u;
+    for (uint32_t k = lane; k < HIST_BYTES / 4u; k += 32) hist_p[k] = 0;
+    __syncthreads();
 
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
@@ -128,42 +187,51 @@ __global__ void __launch_bounds__(THREADS) scan_sym_kernel(
         const RegionSpan sp = region_span(chrom_off, chrom_len, reg_chrom, reg_start, reg_end, r, U, D, U, D);
         const bool minus = reg_strand != nullptr && __ldg(reg_strand + r) < 0;
         if (sp.ge > sp.gs) {
+            // all per-iteration arithmetic is 32-bit and relative to the region's first word; the
+            // halo words come from registers of the neighbouring iterations, so the only global
+            // loads are the prefetches issued one iteration ahead
             const int64_t w0 = sp.gs >> 5;
-            const int64_t w1 = (sp.ge - 1) >> 5;
-            for (int64_t wb = w0; wb <= w1; wb += 32) {
-                const int64_t w = wb + lane;
-                const bool loadable = w < n_words32;
-                uint2 pw = make_uint2(0u, 0u);
-                uint32_t nm = 0xFFFFFFFFu;
-                if (loadable) {
-                    pw = __ldg(p2v + w);
-                    nm = __ldg(nmask + w);
-                }
+            const int nw = (int)(((sp.ge - 1) >> 5) - w0) + 1;
+            const int lo_first = (int)(sp.gs & 31);
+            const int hi_last = (int)((sp.ge - 1) & 31) + 1;
+            const uint32_t mask_first = 0xFFFFFFFFu >> lo_first;
+            const uint32_t mask_last = hi_last >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi_last);
+            const uint2 *pv = p2v + w0;
+            const uint32_t *pn = nmask + w0;
+            const int64_t left = n_words32 - w0;
+            const int avail = left > 0x7fffffff ? 0x7fffffff : (int)left;
+            uint32_t carry_p = 0u, carry_n = 0xFFFFFFFFu;          // word w0 - 1 (for lane 0)
+            if (w0 > 0) {
+                carry_p = __ldg(p2 + 2 * w0 - 1);
+                carry_n = __ldg(nmask + w0 - 1);
+            }
+            WordLoad nxt = load_word(pv, pn, lane, avail);
+            for (int rel0 = 0; rel0 < nw; rel0 += 32) {
+                const int rel = rel0 + lane;
+                const WordLoad cur = nxt;
+                nxt = load_word(pv, pn, rel + 32, avail);           // prefetch (also feeds lane 31's halo)
+                const uint2 pw = cur.pw;
+                const uint32_t nm = cur.nm;
                 uint32_t prev_p = __shfl_up_sync(0xffffffffu, pw.y, 1);
                 uint32_t next_p = __shfl_down_sync(0xffffffffu, pw.x, 1);
                 uint32_t prev_n = __shfl_up_sync(0xffffffffu, nm, 1);
                 uint32_t next_n = __shfl_down_sync(0xffffffffu, nm, 1);
+                const uint32_t n0_p = __shfl_sync(0xffffffffu, nxt.pw.x, 0);
+                const uint32_t n0_n = __shfl_sync(0xffffffffu, nxt.nm, 0);
                 if (lane == 0) {
-                    prev_p = w > 0 ? __ldg(p2 + 2 * w - 1) : 0u;
-                    prev_n = w > 0 ? __ldg(nmask + w - 1) : 0xFFFFFFFFu;
+                    prev_p = carry_p;
+                    prev_n = carry_n;
                 }
                 if (lane == 31) {
-                    const bool ok = w + 1 < n_words32;
-                    next_p = ok ? __ldg(p2 + 2 * w + 2) : 0u;
-                    next_n = ok ? __ldg(nmask + w + 1) : 0xFFFFFFFFu;
+                    next_p = n0_p;
+                    next_n = n0_n;
                 }
+                carry_p = __shfl_sync(0xffffffffu, pw.y, 31);
+                carry_n = __shfl_sync(0xffffffffu, nm, 31);
                 // positions of this word that are centres of the region
-                const int64_t base_g = w << 5;
-                const int64_t lo64 = sp.gs - base_g;
-                const int64_t hi64 = sp.ge - base_g;
-                const int lo = lo64 < 0 ? 0 : (lo64 > 32 ? 32 : (int)lo64);
-                const int hi = hi64 < 0 ? 0 : (hi64 > 32 ? 32 : (int)hi64);
-                uint32_t valid = 0u;
-                if (hi > lo) {
-                    const uint32_t from_lo = lo >= 32 ? 0u : (0xFFFFFFFFu >> lo);
-                    const uint32_t below_hi = hi >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
-                    valid = from_lo & below_hi;
-                }
+                uint32_t valid = rel < nw ? 0xFFFFFFFFu : 0u;
+                if (rel == 0) valid &= mask_first;
+                if (rel == nw - 1) valid &= mask_last;
                 // k-mers touching a non-ACGT base are skipped
                 uint32_t bad = nm;
 #pragma unroll
@@ -172,81 +240,118 @@ __global__ void __launch_bounds__(THREADS) scan_sym_kernel(
                 for (int t = 1; t <= U; ++t) bad |= (nm >> t) | (prev_n << (32 - t));
                 valid &= ~bad;
 
-                if (__all_sync(0xffffffffu, valid == 0xFFFFFFFFu)) {
-                    Unroll<U, D, 0>::template run<false>(hist, prev_p, pw.x, pw.y, next_p, valid);
-                } else if (__any_sync(0xffffffffu, valid != 0u)) {
-                    Unroll<U, D, 0>::template run<true>(hist, prev_p, pw.x, pw.y, next_p, valid);
+                const bool full = valid == 0xFFFFFFFFu;
+                if (full) Unroll<U, D, 0, SCALE>::run(lane_base, prev_p, pw.x, pw.y, next_p);
+                // partly valid words: broadcast the word, lane i takes position i
+                uint32_t pm = __ballot_sync(0xffffffffu, !full && valid != 0u);
+                while (pm) {
+                    const int j = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const uint32_t a = __shfl_sync(0xffffffffu, prev_p, j);
+                    const uint32_t b0 = __shfl_sync(0xffffffffu, pw.x, j);
+                    const uint32_t b1 = __shfl_sync(0xffffffffu, pw.y, j);
+                    const uint32_t c = __shfl_sync(0xffffffffu, next_p, j);
+                    const uint32_t v = __shfl_sync(0xffffffffu, valid, j);
+                    if (v & (0x80000000u >> lane))
+                        smem_inc((runtime_key<U, D>(a, b0, b1, c, lane) << SCALE) | lane_base);
                 }
             }
         }
         __syncwarp();
-        // write-out: counts row r, re-zero the histogram, fold into the register totals
+        // ---- write-out: counts row r, re-zero the histogram, fold into the CTA totals
         int32_t *out = counts + r * (int64_t)K;
-        if (!minus) {
-            int4 *hist4 = reinterpret_cast<int4 *>(hist);
-            int4 *out4 = reinterpret_cast<int4 *>(out);
+        // the CTA totals are int32: once 2^30 bases have been folded in, later regions of this CTA add
+        // straight to the global uint64 totals instead (never reached by window-sized workloads)
+        bool tot_smem = totals != nullptr, tot_glob = false;
+        if (totals != nullptr) {
+            const unsigned int kb = (unsigned int)((sp.ge - sp.gs) >> 10) + 1u;
+            unsigned int old = 0u;
+            if (lane == 0) old = atomicAdd(&cta_acc_kb, kb);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old + kb > tot_limit_kb || old + kb < old) {
+                tot_smem = false;
+                tot_glob = true;
+            }
+        }
+        if constexpr (PRIVATE) {
+            int bins[BPL];
 #pragma unroll
-            for (int j = 0; j < NTOT; ++j) {
-                const int cidx = j * 32 + lane;
-                if (K4 >= 32 || cidx < K4) {
-                    const int4 v = hist4[cidx];
-                    hist4[cidx] = make_int4(0, 0, 0, 0);
-                    __stcs(out4 + cidx, v);
-                    tot[4 * j + 0] += v.x;
-                    tot[4 * j + 1] += v.y;
-                    tot[4 * j + 2] += v.z;
-                    tot[4 * j + 3] += v.w;
+            for (int q = 0; q < BPL; ++q) {
+                const int b = q * 32 + lane;
+                int acc = 0;
+                if (K >= 32 || b < K) {
+                    // sum the 32 lane-private copies of bin b with eight 128-bit reads; chunk
+                    // (s + lane) & 7 keeps every quarter-warp on 8 distinct 16-byte bank groups
+                    int4 *row4 = reinterpret_cast<int4 *>(hist_p + b * 32);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int ch = (s + lane) & 7;
+                        const int4 v = row4[ch];
+                        row4[ch] = make_int4(0, 0, 0, 0);
+                        acc += (v.x + v.y) + (v.z + v.w);
+                    }
+                }
+                bins[q] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < BPL; ++q) {
+                const int b = q * 32 + lane;
+                if (K >= 32 || b < K) {
+                    const int ob = minus ? (int)revcomp_key((uint32_t)b, KLEN) : b;
+                    __stcs(out + ob, bins[q]);
+                    if (tot_smem && bins[q]) atomicAdd(tot_p + ob, bins[q]);
+                    if (tot_glob && bins[q]) atomicAdd(totals + ob, (unsigned long long)bins[q]);
                 }
             }
         } else {
-            // minus strand: the reverse-complemented string has the reverse-complemented k-mers
-            for (int k = lane; k < K; k += 32) {
-                const int v = hist[k];
-                hist[k] = 0;
-                const uint32_t rk = revcomp_key((uint32_t)k, KLEN);
-                out[rk] = v;
-                if (totals != nullptr && v) atomicAdd(totals + rk, (unsigned long long)v);
+            constexpr int K4 = K / 4;
+            if (!minus) {
+                int4 *hist4 = reinterpret_cast<int4 *>(hist_p);
+                int4 *out4 = reinterpret_cast<int4 *>(out);
+#pragma unroll
+                for (int j = 0; j < K4 / 32; ++j) {
+                    const int cidx = j * 32 + lane;
+                    const int4 v = hist4[cidx];
+                    hist4[cidx] = make_int4(0, 0, 0, 0);
+                    __stcs(out4 + cidx, v);
+                    if (tot_smem) {
+                        // CTA totals are kept in 4 planes (plane q = bins 4c+q) so that these
+                        // atomics touch 32 consecutive words
+                        atomicAdd(tot_p + 0 * K4 + cidx, v.x);
+                        atomicAdd(tot_p + 1 * K4 + cidx, v.y);
+                        atomicAdd(tot_p + 2 * K4 + cidx, v.z);
+                        atomicAdd(tot_p + 3 * K4 + cidx, v.w);
+                    }
+                    if (tot_glob) {
+                        if (v.x) atomicAdd(totals + 4 * cidx + 0, (unsigned long long)v.x);
+                        if (v.y) atomicAdd(totals + 4 * cidx + 1, (unsigned long long)v.y);
+                        if (v.z) atomicAdd(totals + 4 * cidx + 2, (unsigned long long)v.z);
+                        if (v.w) atomicAdd(totals + 4 * cidx + 3, (unsigned long long)v.w);
+                    }
+                }
+            } else {
+                for (int k = lane; k < K; k += 32) {
+                    const int v = hist_p[k];
+                    hist_p[k] = 0;
+                    const uint32_t rk = revcomp_key((uint32_t)k, KLEN);
+                    out[rk] = v;
+                    if (tot_smem && v) atomicAdd(tot_p + (rk & 3u) * K4 + (rk >> 2), v);
+                    if (tot_glob && v) atomicAdd(totals + rk, (unsigned long long)v);
+                }
             }
         }
         __syncwarp();
-        tot_bases += sp.ge - sp.gs;
-        if (tot_bases > (int64_t)1 << 30) {          // keep the int32 register totals from overflowing
-            if (totals != nullptr) {
-#pragma unroll
-                for (int j = 0; j < NTOT; ++j) {
-                    const int cidx = j * 32 + lane;
-                    if (K4 >= 32 || cidx < K4) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (tot[4 * j + q]) atomicAdd(totals + 4 * cidx + q, (unsigned long long)tot[4 * j + q]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NTOT * 4; ++j) tot[j] = 0;
-            tot_bases = 0;
-        }
     }
 
     if (totals == nullptr) return;                  // uniform across the grid
-    // block-level reduction of the totals in shared memory (aliases the now all-zero histograms)
     __syncthreads();
-    unsigned long long *ctot = reinterpret_cast<unsigned long long *>(smem);
-    static_assert(WARPS_PER_BLOCK * 4 >= 8, "ctot must fit in the histogram area");
-    for (int k = threadIdx.x; k < K; k += THREADS) ctot[k] = 0ull;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < NTOT; ++j) {
-        const int cidx = j * 32 + lane;
-        if (K4 >= 32 || cidx < K4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (tot[4 * j + q]) atomicAdd(ctot + 4 * cidx + q, (unsigned long long)tot[4 * j + q]);
+    for (int k = threadIdx.x; k < K; k += THREADS) {
+        const int v = tot_p[k];
+        if (v) {
+            const int bin = PRIVATE ? k : ((k % (K / 4)) * 4 + k / (K / 4));
+            atomicAdd(totals + bin, (unsigned long long)v);
         }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += THREADS)
-        if (ctot[k]) atomicAdd(totals + k, ctot[k]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -304,18 +409,20 @@ __global__ void __launch_bounds__(THREADS) scan_generic_kernel(
     }
 }
 
-template <int U>
+template <int U, bool PRIVATE>
 int launch_sym(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start,
                const int64_t *reg_end, const int8_t *reg_strand, int64_t n_reg, int32_t *counts,
                unsigned long long *totals, cudaStream_t stream)
 {
     constexpr int K = 1 << (2 * (2 * U + 1));
-    const size_t smem = (size_t)WARPS_PER_BLOCK * K * sizeof(int) < 2048 ? 2048 : (size_t)WARPS_PER_BLOCK * K * sizeof(int);
-    auto kern = scan_sym_kernel<U>;
+    constexpr size_t HIST_BYTES = (size_t)K << (PRIVATE ? 7 : 2);
+    // totals + alignment slack + one histogram per warp
+    const size_t smem = (size_t)K * 4 + HIST_BYTES + (size_t)WARPS_PER_BLOCK * HIST_BYTES;
+    auto kern = scan_sym_kernel<U, PRIVATE>;
     static thread_local int blocks_per_sm = 0;
+    DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (blocks_per_sm == 0) {
-        DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
@@ -324,12 +431,16 @@ int launch_sym(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const in
     if (blocks > need) blocks = need;
     kern<<<(unsigned)blocks, THREADS, smem, stream>>>(reinterpret_cast<const uint2 *>(p2), p2, nm,
                                                       (n_bases + 31) >> 5, chrom_off, chrom_len, reg_chrom,
-                                                      reg_start, reg_end, reg_strand, n_reg, counts, totals);
+                                                      reg_start, reg_end, reg_strand, n_reg, counts, totals,
+                                                      g_tot_limit_kb);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
 
 }  // namespace
+
+// test hook (not part of the public header): lowers the int32-totals guard so tests can reach it
+extern "C" void dig_debug_set_totals_limit_kb(unsigned int kb) { g_tot_limit_kb = kb; }
 
 extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
                                   const int64_t *chrom_off_d, const int64_t *chrom_len_d,
@@ -349,24 +460,20 @@ extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nma
     if (n_up == n_down && n_up <= 2) {
         switch (n_up) {
         case 0:
-            return launch_sym<0>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d,
-                                 reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
+            return launch_sym<0, true>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d,
+                                       reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
         case 1:
-            return launch_sym<1>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d,
-                                 reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
+            return launch_sym<1, true>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d,
+                                       reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
         default:
-            return launch_sym<2>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d,
-                                 reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
+            return launch_sym<2, false>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d,
+                                        reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
         }
     }
     const int K = 1 << (2 * (n_up + n_down + 1));
     const size_t smem = (size_t)WARPS_PER_BLOCK * K * sizeof(int);
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        DIG_CUDA(cudaFuncSetAttribute(scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      WARPS_PER_BLOCK * 4096 * (int)sizeof(int)));
-        attr_set = true;
-    }
+    DIG_CUDA(cudaFuncSetAttribute(scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  WARPS_PER_BLOCK * 4096 * (int)sizeof(int)));
     int64_t blocks = (int64_t)dig::sm_count() * 4;
     const int64_t need = (n_reg + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (blocks > need) blocks = need;

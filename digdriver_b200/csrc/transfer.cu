@@ -235,7 +235,7 @@ extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *el
                       win_map_d && win_counts_d && y_pred_d && std_d && y_true_d && flag_d && d_pr_d && mu_d &&
                       sigma_d && r_obs_d && flag_out_d && r_size_d && elt_size_d && p_out_d && n_win_out_d,
                   "null pointer");
-    const int span_words = (max_span_windows + 31) / 32;
+    const int span_words = ((max_span_windows + 31) / 32 + 3) & ~3;      // keeps every warp's slice 16-byte aligned
     const size_t smem = (size_t)TW * (128 * sizeof(double) + (size_t)span_words * sizeof(uint32_t));
     if (smem > 200 * 1024) {
         dig::set_error("dig_element_transfer: window span of %d windows needs %zu B of shared memory",

@@ -176,7 +176,7 @@ def tabulate_genes(mut_gene, mut_sample, mut_class, n_gene, max_per_gene_per_sam
 
 def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window, win_map_off, win_map,
                      win_counts, y_pred, std, y_true, flag, d_pr, blk_counts=None, L_elt=None,
-                     device="cuda:0", stream=None):
+                     device="cuda:0", stream=None, max_span=None):
     """K6.  Region-parameter arrays are [n_cohort, n_win] (1-D inputs are taken as one cohort), d_pr is
     [n_cohort, 192].  Returns a dict of device tensors (MU, SIGMA, R_OBS, FLAG: [n_cohort, n_elt];
     R_SIZE, ELT_SIZE, N_WIN: [n_elt]; P: [n_cohort, n_elt, n_col])."""
@@ -199,20 +199,8 @@ def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window,
         Le = _dev(L_elt, torch.float64, dev)
         Le = Le.reshape(n_elt, 192, -1)
         bc, n_col = None, Le.shape[2]
-    # widest window span of any element (host side: the block tables come from the host anyway)
-    bs_h, be_h, bp_h = (x.cpu().numpy() for x in (bs, be, bp))
-    max_span = 1
-    if n_elt and len(bs_h):
-        lo = np.floor_divide(bs_h, window)
-        hi = -np.floor_divide(-be_h, window)
-        owner = np.repeat(np.arange(n_elt), np.diff(bp_h))
-        wmin = np.full(n_elt, np.iinfo(np.int64).max)
-        wmax = np.full(n_elt, np.iinfo(np.int64).min)
-        np.minimum.at(wmin, owner, lo)
-        np.maximum.at(wmax, owner, hi)
-        has = wmax > wmin
-        if has.any():
-            max_span = int((wmax[has] - wmin[has]).max())
+    if max_span is None:
+        max_span = element_max_span(bp, bs, be, window)
     out = {
         "MU": torch.empty((n_cohort, n_elt), dtype=torch.float64, device=dev),
         "SIGMA": torch.empty((n_cohort, n_elt), dtype=torch.float64, device=dev),
@@ -235,6 +223,28 @@ def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window,
     return out
 
 
+def element_max_span(blk_ptr, blk_start, blk_end, window):
+    """Widest window span (in windows) of any element: sizes K6's shared-memory bitmap.  Host-side; cache it
+    when the same annotation is used repeatedly."""
+    def host(x):
+        return x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    bp_h, bs_h, be_h = host(blk_ptr).astype(np.int64), host(blk_start).astype(np.int64), host(blk_end).astype(np.int64)
+    n_elt = len(bp_h) - 1
+    max_span = 1
+    if n_elt > 0 and len(bs_h):
+        lo = np.floor_divide(bs_h, window)
+        hi = -np.floor_divide(-be_h, window)
+        owner = np.repeat(np.arange(n_elt), np.diff(bp_h))
+        wmin = np.full(n_elt, np.iinfo(np.int64).max)
+        wmax = np.full(n_elt, np.iinfo(np.int64).min)
+        np.minimum.at(wmin, owner, lo)
+        np.maximum.at(wmax, owner, hi)
+        has = wmax > wmin
+        if has.any():
+            max_span = int((wmax[has] - wmin[has]).max())
+    return max_span
+
+
 def build_window_map(win_chrom_idx, win_start, window, n_chrom):
     """Dense (chromosome, window number) -> row map for K6.  Returns (win_map_off int64 [n_chrom+1],
     win_map int32)."""
@@ -248,3 +258,14 @@ def build_window_map(win_chrom_idx, win_start, window, n_chrom):
     wmap = np.full(int(off[-1]), -1, dtype=np.int32)
     wmap[off[wc] + wn] = np.arange(len(wc), dtype=np.int32)
     return off, wmap
+
+
+def substitution_counts(ctx, alt, n_up=1, n_down=1, stream=None):
+    """Histogram of substitutions in sorted 'CTX>CTX2' order: int64 [3K] on the device of ``ctx``."""
+    dev = ctx.device
+    al = _dev(alt, torch.uint8, dev)
+    out = torch.empty(3 * 4 ** (n_up + n_down + 1), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_substitution_counts", ctx.data_ptr(), al.data_ptr(), ctx.numel(), int(n_up), int(n_down),
+                  out.data_ptr(), _stream(dev, stream))
+    return out

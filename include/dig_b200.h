@@ -97,6 +97,14 @@ int dig_mutation_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, in
                           const int32_t *mut_chrom_d, const int64_t *mut_start_d, const uint8_t *mut_ref_d,
                           int64_t n_mut, int n_up, int n_down, int32_t *ctx_out_d, void *stream);
 
+/* Substitution histogram behind train_sequence_model (sequence_tools.py:336-339): counts_d [3K] uint64
+ * (overwritten), bin = 3 * ctx + rank(ALT among the non-REF bases in alphabetical order) -- for
+ * trinucleotides this is the sorted 'CTX>CTX2' order of mk_trans_idx (:282-289).  Rows with ctx < 0,
+ * alt > 3 or ALT == REF are skipped.
+ */
+int dig_substitution_counts(const int32_t *ctx_d, const uint8_t *alt_d, int64_t n, int n_up, int n_down,
+                            unsigned long long *counts_d, void *stream);
+
 /* ---------------------------------------------------------------------------------
  * K5  observed mutation counts per element.
  * Replaces: bedtools intersect -wa -wb + the pandas group-bys of

@@ -129,15 +129,24 @@ def test_scan_chr22_sized_vs_oracle(dev, oracle):
         assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
 
 
-def test_scan_large_windows_totals_overflow_guard(dev, oracle):
-    """1 Mb windows: per-warp register totals must be flushed before they can overflow."""
-    from digdriver_b200 import kernels
+@pytest.mark.parametrize("u", [0, 1, 2])
+def test_scan_large_windows_totals_overflow_guard(dev, oracle, u):
+    """1 Mb windows, and the guard that moves a CTA from int32 shared-memory totals to global
+    uint64 atomics (forced here by lowering its threshold through the test hook)."""
+    import ctypes
+    from digdriver_b200 import kernels, _lib
     from digdriver_b200.genome import DeviceGenome, tile_windows
     lengths = np.array([9_000_001], dtype=np.int64)
     dg = DeviceGenome.synthetic(["chr1"], lengths, seed=4, device=dev, n_frac16=0)
-    wins = tile_windows([0], lengths, 1_000_000)
-    counts, totals = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], 0, 0, want_totals=True)
+    wins = np.concatenate([tile_windows([0], lengths, 1_000_000)] * 40)      # 320 regions > one wave of warps
     seq = oracle.synth_genome(0, int(lengths[0]), 4, 0)
-    want, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 0, 0)
-    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
-    assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
+    want, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], u, u)
+    hook = ctypes.CDLL(_lib.LIB_PATH).dig_debug_set_totals_limit_kb
+    try:
+        for limit in (1 << 20, 1500):
+            hook(ctypes.c_uint(limit))
+            counts, totals = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], u, u, want_totals=True)
+            assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+            assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
+    finally:
+        hook(ctypes.c_uint(1 << 20))
