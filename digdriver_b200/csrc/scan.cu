@@ -205,11 +205,15 @@ __global__ void __launch_bounds__(THREADS, PRIVATE ? 3 : 3) scan_sym_kernel(
                 carry_p = __ldg(p2 + 2 * w0 - 1);
                 carry_n = __ldg(nmask + w0 - 1);
             }
+            // two words in flight per lane: `nxt` (issued one iteration ago) also feeds lane 31's halo,
+            // `nx2` is issued now and not touched until the next iteration
             WordLoad nxt = load_word(pv, pn, lane, avail);
+            WordLoad nx2 = load_word(pv, pn, lane + 32, avail);
             for (int rel0 = 0; rel0 < nw; rel0 += 32) {
                 const int rel = rel0 + lane;
                 const WordLoad cur = nxt;
-                nxt = load_word(pv, pn, rel + 32, avail);           // prefetch (also feeds lane 31's halo)
+                nxt = nx2;
+                nx2 = load_word(pv, pn, rel + 64, avail);
                 const uint2 pw = cur.pw;
                 const uint32_t nm = cur.nm;
                 uint32_t prev_p = __shfl_up_sync(0xffffffffu, pw.y, 1);

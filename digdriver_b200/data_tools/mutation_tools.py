@@ -1,0 +1,224 @@
+"""Drop-in for DIGDriver/data_tools/mutation_tools.py: mutation-file reader and observed-count
+tabulation.  The bedtools subprocess + pandas group-bys of the reference are replaced by K5
+(interval stabbing + hash-table aggregation on the GPU); file parsing stays pandas.
+"""
+import csv
+import gzip
+
+import numpy as np
+import pandas as pd
+
+from .. import kernels
+
+AUTOSOMES = [str(i) for i in range(1, 23)]
+
+
+def read_mutation_file(path, drop_sex=True, drop_duplicates=False, unique_indels=True):
+    """Reference :45-104: headerless TSV whose column count (5-11) selects the schema."""
+    try:
+        with open(path) as f:
+            first_row = next(csv.reader(f, delimiter='\t', skipinitialspace=True))
+    except UnicodeDecodeError:
+        with gzip.open(path, 'rt') as f:
+            first_row = next(csv.reader(f, delimiter='\t', skipinitialspace=True))
+    schemas = {
+        5: ['CHROM', 'POS', 'REF', 'ALT', 'SAMPLE'],
+        6: ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE'],
+        7: ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'ANNOT'],
+        8: ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'GENE', 'ANNOT'],
+        9: ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'ANNOT', 'MUT_TYPE', 'CONTEXT'],
+        10: ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'GENE', 'ANNOT', 'MUT_TYPE', 'CONTEXT'],
+        11: ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'GENE', 'ANNOT', 'MUT_TYPE', 'CONTEXT', 'STRAND'],
+    }
+    cols = schemas[len(first_row)]
+    dtype = {c: (int if c in ('POS', 'START', 'END') else str) for c in cols}
+    df = pd.read_csv(path, sep="\t", low_memory=False, names=cols, dtype=dtype)
+    if drop_sex:
+        if set(df.CHROM.unique()) - set(AUTOSOMES):
+            print('Restricting to autosomes')
+            df = df[df.CHROM.isin(AUTOSOMES)]
+        df = df.assign(CHROM=df.CHROM.astype(int))
+    if drop_duplicates:
+        df = drop_duplicate_mutations(df)
+    if unique_indels and 'ANNOT' in df.columns:
+        df = get_unique_indels(df)
+    return df
+
+
+def drop_duplicate_mutations(df_mut):
+    return df_mut.drop_duplicates(['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE'])
+
+
+def get_unique_indels(df_mut):
+    df_indel = df_mut[df_mut.ANNOT == 'INDEL']
+    df_snv = df_mut[df_mut.ANNOT != 'INDEL']
+    subset = [c for c in ['CHROM', 'START', 'END', 'REF', 'ALT', 'GENE'] if c in df_mut.columns]
+    return pd.concat([df_snv, df_indel.drop_duplicates(subset=subset)])
+
+
+def filter_hypermut_samples(df_mut, max_muts_per_sample, return_blacklist=False):
+    """Remove samples that have more mutations than the threshold (reference :293-304)."""
+    sample_cnt = df_mut.SAMPLE.value_counts()
+    samples_blacklist = sample_cnt[sample_cnt > max_muts_per_sample].index.to_list()
+    df_whitelist = df_mut[~df_mut.SAMPLE.isin(samples_blacklist)]
+    if return_blacklist:
+        return df_whitelist, samples_blacklist
+    return df_whitelist
+
+
+def bed12_boundaries(f_bed):
+    """Reference :383-414: CHROM (int, autosomes), ELT, STRAND, BLOCK_STARTS, BLOCK_ENDS per bed12 row."""
+    names = ['CHROM', 'START', 'END', "ELT", "SCORE", "STRAND", 'thickStart', 'thickEnd', 'rgb', 'blockCount',
+             'blockSizes', 'blockStarts']
+    df = pd.read_table(f_bed, names=names, low_memory=False)
+    df['CHROM'] = df.CHROM.astype(str).map(lambda x: x[3:] if x.startswith('chr') else x)
+    df = df[df.CHROM.isin(AUTOSOMES)].copy()
+    df['CHROM'] = df.CHROM.astype(int)
+    starts, ends = [], []
+    for s0, bs, bz in zip(df.START.values, df.blockStarts.astype(str).values, df.blockSizes.astype(str).values):
+        st = [int(x) + int(s0) for x in bs.strip(',').split(',')]
+        sz = [int(x) for x in bz.strip(',').split(',')]
+        starts.append(st)
+        ends.append([a + b for a, b in zip(st, sz)])
+    df['BLOCK_STARTS'] = starts
+    df['BLOCK_ENDS'] = ends
+    return df[['CHROM', 'ELT', 'STRAND', 'BLOCK_STARTS', 'BLOCK_ENDS']]
+
+
+def _chrom_codes(*series):
+    """Shared integer code per chromosome label across several columns ('chr' prefix kept as written,
+    exactly like bedtools' string comparison)."""
+    labels = pd.unique(np.concatenate([np.asarray(s).astype(str) for s in series]))
+    code = {c: i for i, c in enumerate(labels)}
+    return [np.array([code[str(v)] for v in s], dtype=np.int64) for s in series]
+
+
+def _read_bed_blocks(f_elt_bed, bed12):
+    bed = pd.read_table(f_elt_bed, header=None, low_memory=False)
+    if not bed12:
+        return pd.DataFrame({'CHROM': bed[0].astype(str), 'START': bed[1].astype(np.int64),
+                             'END': bed[2].astype(np.int64), 'ELT': bed[3].astype(str)})
+    rows = []
+    for r in bed.itertuples(index=False):
+        sizes = [int(x) for x in str(r[10]).strip(',').split(',')]
+        starts = [int(x) for x in str(r[11]).strip(',').split(',')]
+        for sz, st in zip(sizes, starts):
+            rows.append((str(r[0]), int(r[1]) + st, int(r[1]) + st + sz, str(r[3])))
+    return pd.DataFrame(rows, columns=['CHROM', 'START', 'END', 'ELT'])
+
+
+def _read_raw_mutations(f_mut):
+    """The mutation file as bedtools sees it: every row, CHROM as written."""
+    try:
+        df = pd.read_table(f_mut, header=None, low_memory=False, dtype={0: str})
+    except UnicodeDecodeError:
+        df = pd.read_table(f_mut, header=None, low_memory=False, dtype={0: str}, compression='gzip')
+    return df
+
+
+def _tabulate(f_mut, f_elt_bed, bed12, drop_duplicates, max_muts_per_sample, max_muts_per_elt_per_sample):
+    """K5 behind tabulate_muts_per_sample_per_element (:191-230) + tabulate_mutations_in_element (:155-189)."""
+    mut = _read_raw_mutations(f_mut)
+    blocks = _read_bed_blocks(f_elt_bed, bed12)
+    if drop_duplicates:
+        # drop_duplicates([0..5, 13]) after the intersect == de-duplicate mutation rows first (:208)
+        mut = mut.drop_duplicates([0, 1, 2, 3, 4, 5])
+    elts, elt_id = np.unique(blocks.ELT.values, return_inverse=True)
+    samples, sample_id = np.unique(mut[5].astype(str).values, return_inverse=True)
+    mc, bc = _chrom_codes(mut[0].values, blocks.CHROM.values)
+    is_indel = (mut[7].values == 'INDEL') if mut.shape[1] > 7 else np.zeros(len(mut), dtype=bool)
+    obs, stot = kernels.tabulate_elements(
+        (bc << 32) | blocks.START.values.astype(np.int64), (bc << 32) | blocks.END.values.astype(np.int64), elt_id,
+        (mc << 32) | mut[1].values.astype(np.int64), (mc << 32) | mut[2].values.astype(np.int64), sample_id, is_indel,
+        len(elts), len(samples), max_muts_per_sample=int(min(max_muts_per_sample, 2 ** 62)),
+        max_per_elt_per_sample=int(min(max_muts_per_elt_per_sample, 2 ** 62)))
+    obs = obs.cpu().numpy()
+    stot = stot.cpu().numpy()
+    blacklist = list(samples[stot > max_muts_per_sample])
+    df = pd.DataFrame(obs.astype(np.float64), index=pd.Index(elts, name='ELT'),
+                      columns=['OBS_SAMPLES', 'OBS_SNV', 'OBS_INDEL'])
+    return df[df.OBS_SAMPLES > 0], blacklist
+
+
+def tabulate_mutations_in_element(f_mut, f_elt_bed, bed12=False, drop_duplicates=False, all_elements=False,
+                                  max_muts_per_sample=1e9, max_muts_per_elt_per_sample=3e9, return_blacklist=False):
+    """Reference :155-189: OBS_SAMPLES, OBS_SNV, OBS_INDEL per element (index ELT)."""
+    df_summary, blacklist = _tabulate(f_mut, f_elt_bed, bed12, drop_duplicates, max_muts_per_sample,
+                                      max_muts_per_elt_per_sample)
+    if all_elements:
+        df_bed = pd.read_csv(f_elt_bed, sep="\t", header=None).set_index(3)
+        df_bed.index.rename('ELT', inplace=True)
+        df_summary = df_bed.merge(df_summary, left_index=True, right_index=True, how='left')
+        for c in ('OBS_SNV', 'OBS_INDEL', 'OBS_SAMPLES'):
+            df_summary[c] = df_summary[c].fillna(0)
+    out = df_summary[['OBS_SAMPLES', 'OBS_SNV', 'OBS_INDEL']]
+    if return_blacklist:
+        return out, blacklist
+    return out
+
+
+def mutations_per_gene(df_mut_cds, max_muts_per_gene_per_sample=3e9, return_sample_counts=False):
+    """Reference :329-361: OBS_{MIS,NONS,SYN,SPL,INDEL} per gene (index GENE), per-(gene,sample,class) counts
+    capped.  With return_sample_counts also the distinct-sample counts of transfer_gene_model
+    (transfer_tools.py:243-265)."""
+    genes, gid = np.unique(df_mut_cds.GENE.values.astype(str), return_inverse=True)
+    samples, sid = np.unique(df_mut_cds.SAMPLE.values.astype(str), return_inverse=True)
+    cls_map = {"Synonymous": 0, "Missense": 1, "Nonsense": 2, "Essential_Splice": 3, "INDEL": 4}
+    cls = np.array([cls_map.get(a, 255) for a in df_mut_cds.ANNOT.values], dtype=np.uint8)
+    obs, nsamp = kernels.tabulate_genes(gid, sid, cls, len(genes),
+                                        max_per_gene_per_sample=int(min(max_muts_per_gene_per_sample, 2 ** 62)))
+    obs, nsamp = obs.cpu().numpy(), nsamp.cpu().numpy()
+    idx = pd.Index(genes, name='GENE')
+    df_counts = pd.DataFrame({'OBS_SPL': obs[:, 3], 'OBS_INDEL': obs[:, 4], 'OBS_MIS': obs[:, 1],
+                              'OBS_NONS': obs[:, 2], 'OBS_SYN': obs[:, 0]}, index=idx)
+    if return_sample_counts:
+        df_ns = pd.DataFrame(nsamp, index=idx, columns=['N_SAMP_SYN', 'N_SAMP_MIS', 'N_SAMP_NONS', 'N_SAMP_SPL',
+                                                        'N_SAMP_TRUNC', 'N_SAMP_NONSYN', 'N_SAMP_INDEL'])
+        return df_counts, df_ns
+    return df_counts
+
+
+def tabulate_nonc_mutations_at_sites(f_sites, f_mut, return_sites=False):
+    """Reference :233-275: mutations matching a site exactly on (CHROM, START, END, REF, ALT, GENE, ANNOT,
+    MUT_TYPE, CONTEXT); OBS_SNV = matched rows, OBS_SAMPLES = distinct samples, per site-set (ELT)."""
+    df_sites = read_mutation_file(f_sites)
+    df_sites = df_sites.rename({"SAMPLE": "ELT"}, axis=1)
+    assert ('GENE' in df_sites.columns and 'ANNOT' in df_sites.columns and 'MUT_TYPE' in df_sites.columns)
+    if 'STRAND' not in df_sites.columns:
+        print("WARNING: strand column not detected in sites file. Defaulting all sites to + strand.")
+        df_sites['STRAND'] = "+"
+    df_mut = read_mutation_file(f_mut, drop_duplicates=False)
+    assert ('GENE' in df_mut.columns and 'ANNOT' in df_mut.columns and 'MUT_TYPE' in df_mut.columns)
+    if len(df_mut[df_mut.ANNOT == 'INDEL']):
+        print('WARNING: INDELS found in mutation file. Dig sites model is only applicable to SNVs. '
+              'INDELS will be dropped.')
+    df_mut = df_mut[df_mut.ANNOT != 'INDEL']
+    on = ['CHROM', 'START', 'END', 'REF', 'ALT', 'GENE', 'ANNOT', 'MUT_TYPE', 'CONTEXT']
+    # exact match == zero-length-interval stabbing on a key; the (ELT, SAMPLE) aggregation is K5's table
+    key_s = df_sites[on].astype(str).agg('|'.join, axis=1)
+    key_m = df_mut[on].astype(str).agg('|'.join, axis=1)
+    ukeys, inv = np.unique(np.concatenate([key_s.values, key_m.values]), return_inverse=True)
+    ks, km = inv[:len(key_s)].astype(np.int64), inv[len(key_s):].astype(np.int64)
+    elts, elt_id = np.unique(df_sites.ELT.values.astype(str), return_inverse=True)
+    samples, sid = np.unique(df_mut.SAMPLE.values.astype(str), return_inverse=True)
+    obs, _ = kernels.tabulate_elements(ks, ks + 1, elt_id, km, km + 1, sid, np.zeros(len(km), dtype=bool),
+                                       len(elts), len(samples))
+    obs = obs.cpu().numpy()
+    # K5 counts a mutation once per site-set; the reference's merge counts it once per matching site ROW
+    # (:259-261), so site rows repeated inside one set add their mutation count again (integer glue)
+    pair, mult = np.unique(np.stack([ks, elt_id.astype(np.int64)]), axis=1, return_counts=True)
+    if np.any(mult > 1):
+        per_key = np.bincount(km, minlength=len(ukeys))
+        extra = (mult - 1) * per_key[pair[0]]
+        np.add.at(obs[:, 1], pair[1], extra)
+    keep = obs[:, 0] > 0
+    counts = pd.DataFrame({'ELT': elts[keep], 'OBS_SAMPLES': obs[keep, 0], 'OBS_SNV': obs[keep, 1]})
+    if return_sites:
+        df_sites = df_sites.drop(columns=['GENE', 'ANNOT', 'REF', 'ALT']).rename(columns={'ELT': 'GENE'}).set_index('GENE')
+        return counts, df_sites
+    return counts
+
+
+def tabulate_sites_in_element(f_sites, f_mut):
+    df_res = tabulate_nonc_mutations_at_sites(f_sites, f_mut).set_index('ELT')
+    return df_res[['OBS_SAMPLES', 'OBS_SNV']]

@@ -1,0 +1,197 @@
+"""Drop-in for DIGDriver/sequence_model/genic_driver_tools.py: element / gene "pretrain" -- the set of
+windows an element overlaps, the sums of the region model over those windows and the context-weighted
+mutability fraction.  The per-element Python loops (h5py row reads + pandas .loc lookups) are replaced
+by kernel K6 (one warp per element); see csrc/transfer.cu.
+"""
+import math
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import kernels, storage
+from . import sequence_tools
+
+
+def reverse_complement(seq):
+    return sequence_tools.reverse_complement(seq)
+
+
+def trip_to_str(trip):
+    return 'chr{}:{}-{}'.format(trip[0], trip[1], trip[2])
+
+
+def get_ideal_overlaps(chrom, intervals, window):
+    """Windows overlapped by a set of intervals (reference :275-283).  The reference returns list(set(...)) in
+    hash order; the same set is returned here in ascending order."""
+    region = set()
+    for i in np.asarray(intervals).T:
+        low = math.floor(i[0].min() / window) * window
+        high = math.ceil(i[1].max() / window) * window
+        borders = np.arange(low, high + window, window)
+        for j in range(len(borders) - 1):
+            region.add((chrom, int(borders[j]), int(borders[j + 1])))
+    return sorted(region)
+
+
+def get_elt_ideal_overlaps(chrom, start, end, window):
+    return [(int(c), s, e) for c, s, e in get_ideal_overlaps(chrom, np.array([[start], [end]]), window)]
+
+
+class RegionModel:
+    """region_params (reference: region_model_tools.py:93-126) held as device-ready arrays + the dense
+    (chromosome, window number) -> row map used by K6."""
+
+    def __init__(self, df):
+        self.df = df
+        self.window = int(df.iloc[0]['END'] - df.iloc[0]['START'])
+        chrom = df.CHROM.values.astype(np.int64)
+        self.n_chrom = int(chrom.max()) + 1 if len(chrom) else 1        # index by chromosome number itself
+        self.win_map_off, self.win_map = kernels.build_window_map(chrom, df.START.values, self.window, self.n_chrom)
+        self.y_pred = df.Y_PRED.values.astype(np.float64)
+        self.std = df.STD.values.astype(np.float64)
+        self.y_true = df.Y_TRUE.values.astype(np.float64)
+        self.flag = df.FLAG.values.astype(bool) if 'FLAG' in df.columns else np.zeros(len(df), dtype=bool)
+
+
+def _one_cohort(out):
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    return {"MU": o["MU"][0], "SIGMA": o["SIGMA"][0], "R_OBS": o["R_OBS"][0], "FLAG": o["FLAG"][0].astype(bool),
+            "R_SIZE": o["R_SIZE"], "ELT_SIZE": o["ELT_SIZE"], "P": o["P"][0], "N_WIN": o["N_WIN"]}
+
+
+def transfer_elements(region_model, win_counts64, d_pr, elt_chrom, elt_strand, blk_ptr, blk_start, blk_end,
+                      blk_counts=None, L_elt=None):
+    """K6 for a batch of elements against one region model.  elt_chrom holds chromosome NUMBERS (1..22).
+    Returns a dict of host arrays (MU, SIGMA, R_OBS, FLAG, R_SIZE, ELT_SIZE, P [E, n_col], N_WIN)."""
+    rm = region_model
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = kernels.element_transfer(np.asarray(elt_chrom, dtype=np.int32), np.asarray(elt_strand, dtype=np.int8),
+                                   blk_ptr, blk_start, blk_end, rm.window, rm.win_map_off, rm.win_map, win_counts64,
+                                   rm.y_pred, rm.std, rm.y_true, rm.flag, d_pr, blk_counts=blk_counts, L_elt=L_elt,
+                                   device=dev)
+    return _one_cohort(out)
+
+
+def get_region_params_direct(df, overlaps, window):
+    """mu, sigma, R_obs, FLAG over a list of (chrom, start, end) windows (reference :258-272), via K6."""
+    rm = df if isinstance(df, RegionModel) else RegionModel(df)
+    ov = sorted(overlaps)
+    if len(ov) == 0:
+        return 0, 0.0, 0, False
+    chrom = int(ov[0][0])
+    starts = np.array([o[1] for o in ov], dtype=np.int64)
+    n = len(df) if not isinstance(df, RegionModel) else len(rm.df)
+    res = transfer_elements(rm, np.zeros((n, 64), dtype=np.int32), np.ones(192), [chrom], [1],
+                            [0, len(ov)], starts, starts + 1, L_elt=np.zeros((1, 192, 1)))
+    return res["MU"][0], res["SIGMA"][0], res["R_OBS"][0], bool(res["FLAG"][0])
+
+
+def get_region_params(df, chrom, intervals, window):
+    """Reference :235-250."""
+    return get_region_params_direct(df, get_ideal_overlaps(chrom, intervals, window), window)
+
+
+def _strand_code(values):
+    return np.array([-1 if (s == '-' or s == '-1' or s == -1) else 1 for s in values], dtype=np.int8)
+
+
+def nonc_model_arrays(df_elts, L_contexts, region_model, win_counts64, d_pr, f_fasta=None):
+    """Element pretrain on in-memory inputs: preprocess_nonc (sequence_tools.py:596-644) + nonc_model
+    (reference :300-431) == the loop body of DIG_onthefly (onthefly_tools.py:109-165).
+
+    df_elts: bed12_boundaries() frame.  L_contexts: precount_region_contexts_parallel() frame (index
+    'chr{c}:{s}-{e}', 192 columns).  Returns the pretrain DataFrame of reference :404-417."""
+    E = len(df_elts)
+    ptr = np.zeros(E + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(b) for b in df_elts.BLOCK_STARTS])
+    bs = np.array([x for b in df_elts.BLOCK_STARTS for x in b], dtype=np.int64)
+    be = np.array([x for b in df_elts.BLOCK_ENDS for x in b], dtype=np.int64)
+    owner = np.repeat(np.arange(E), np.diff(ptr))
+    chrom = df_elts.CHROM.values.astype(np.int64)
+    keys = ['chr{}:{}-{}'.format(c, s, e) for c, s, e in zip(chrom[owner], bs, be)]
+    Lb = L_contexts.loc[keys].values                          # raises KeyError like the reference (:637)
+    L = np.zeros((E, 192), dtype=np.float64)
+    np.add.at(L, owner, Lb)
+    res = transfer_elements(region_model, win_counts64, d_pr, chrom, _strand_code(df_elts.STRAND.values), ptr, bs, be,
+                            L_elt=L.reshape(E, 192, 1))
+    elt_size = (L.sum(axis=1) / 3).astype(np.int64)           # int(np.sum(L) / 3)  (:380)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_indel = elt_size / res["R_SIZE"].astype(np.float64)
+    return pd.DataFrame({
+        'ELT': df_elts.ELT.values, 'ELT_SIZE': elt_size, 'FLAG': res["FLAG"], 'R_SIZE': res["R_SIZE"],
+        'R_OBS': res["R_OBS"], 'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"],
+        'MU_INDEL': res["MU"], 'SIGMA_INDEL': res["SIGMA"], 'P_SUM': res["P"][:, 0], 'P_INDEL': p_indel})
+
+
+def _window_counts_for(region_model, f_fasta):
+    """Trinucleotide counts of every window of the region model (K2)."""
+    df = region_model.df
+    g = sequence_tools.get_device_genome(f_fasta)
+    cidx = g.chrom_indices(df.CHROM.values)
+    counts, _ = kernels.count_contexts(g, cidx, df.START.values, df.END.values, 1, 1)
+    return counts
+
+
+def nonc_model_parallel(f_pretrained, f_nonc_data, nonc_L_key, N_procs=1, indels_direct=False):
+    """Reference :434-461 on the directory/HDF5 store written by preprocess_element_model."""
+    pre = storage.Store(f_pretrained, "r")
+    rm = RegionModel(pre.read_table('region_params'))
+    d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
+    data = storage.Store(f_nonc_data, "r")
+    wkey = 'window_{}'.format(rm.window)
+    df_elts = data.read_table('{}/{}/elements'.format(wkey, nonc_L_key))
+    df_elts['BLOCK_STARTS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_STARTS]
+    df_elts['BLOCK_ENDS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_ENDS]
+    L_contexts = data.read_table('{}/{}/L_contexts'.format(wkey, nonc_L_key))
+    win_idx = data.read_array('{}/full_window_si_index'.format(wkey))
+    win_vals = data.read_array('{}/full_window_si_values'.format(wkey))
+    # align the stored window counts to the region model's rows
+    key = {tuple(r): i for i, r in enumerate(map(tuple, win_idx))}
+    rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
+    return nonc_model_arrays(df_elts, L_contexts, rm, win_vals[rows].astype(np.int32), d_pr)
+
+
+def genic_model_arrays(genes, region_model, win_counts64, d_pr):
+    """genic_model (reference :31-203) on in-memory inputs.  ``genes``: pipeline.GeneTable with chromosome
+    NUMBERS in chrom_idx.  Returns the genic pretrain DataFrame (reference :170-201)."""
+    res = transfer_elements(region_model, win_counts64, d_pr, genes.chrom_idx, genes.strand, genes.blk_ptr,
+                            genes.blk_start, genes.blk_end, L_elt=genes.L)
+    P = res["P"]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_indel = res["ELT_SIZE"] / res["R_SIZE"].astype(np.float64)
+    df = pd.DataFrame({'CHROM': [str(c) for c in genes.chrom_idx], 'GENE': genes.names,
+                       'GENE_LENGTH': res["ELT_SIZE"], 'R_SIZE': res["R_SIZE"], 'R_OBS': res["R_OBS"],
+                       'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"], 'MU_INDEL': res["MU"],
+                       'SIGMA_INDEL': res["SIGMA"], 'FLAG': res["FLAG"], 'P_MIS': P[:, 1], 'P_NONS': P[:, 2],
+                       'P_SILENT': P[:, 0], 'P_SPLICE': P[:, 3], 'P_TRUNC': P[:, 2] + P[:, 3], 'P_INDEL': p_indel})
+    return df
+
+
+def genic_model_parallel(f_pretrained_str, f_genic_str, N_procs=1, counts_key="window_10kb/counts",
+                         indels_direct=False, f_fasta=None):
+    """Reference :206-226.  f_genic is a store with the f_genic layout flattened to arrays: 'genes' table
+    (GENE, CHROM, STRAND), 'cds_ptr', 'cds_start', 'cds_end' (inclusive intervals) and 'L_data' [E,192,4];
+    the window trinucleotide counts come from f_pretrained's 'window_counts_64' (written by
+    DigPretrain.py genicModel from the genome-count file) or are scanned from f_fasta."""
+    from ..pipeline import GeneTable
+    pre = storage.Store(f_pretrained_str, "r")
+    rm = RegionModel(pre.read_table('region_params'))
+    d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
+    gs = storage.Store(f_genic_str, "r")
+    meta = gs.read_table('genes')
+    keep = ~meta.CHROM.astype(str).isin(['X', 'Y']).values            # reference :89-90
+    ptr = gs.read_array('cds_ptr')
+    sel = np.flatnonzero(keep)
+    lens = np.diff(ptr)[sel]
+    new_ptr = np.zeros(len(sel) + 1, dtype=np.int64)
+    new_ptr[1:] = np.cumsum(lens)
+    take = np.concatenate([np.arange(ptr[i], ptr[i + 1]) for i in sel]) if len(sel) else np.zeros(0, dtype=np.int64)
+    genes = GeneTable(chrom_idx=meta.CHROM.values[sel].astype(np.int32), strand=_strand_code(meta.STRAND.values[sel]),
+                      blk_ptr=new_ptr, blk_start=gs.read_array('cds_start')[take], blk_end=gs.read_array('cds_end')[take],
+                      L=gs.read_array('L_data')[sel], names=list(meta.GENE.values[sel]))
+    if pre.has('window_counts_64'):
+        wc = pre.read_array('window_counts_64').astype(np.int32)
+    else:
+        wc = _window_counts_for(rm, f_fasta)
+    return genic_model_arrays(genes, rm, wc, d_pr)

@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""CLI shim with the sub-commands and arguments of the reference's scripts/DigPreprocess.py that lie on the
+hot path: countGenomeContext (the genome scan), addMutationContext, preprocess_element_model,
+initialize_f_data.  Output files are directory stores (or HDF5 when h5py + PyTables exist), see
+digdriver_b200/storage.py."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from digdriver_b200 import kernels, storage  # noqa: E402
+from digdriver_b200.data_tools import mutation_tools  # noqa: E402
+from digdriver_b200.sequence_model import sequence_tools  # noqa: E402
+
+
+def get_cpus():
+    """Kept for CLI compatibility (reference auxilaries/utils.py:3-8); the GPU path ignores it."""
+    return min(max(1, (os.cpu_count() or 3) - 2), 20)
+
+
+def countGenomeContext(args):
+    """Reference DigPreprocess.py:19-73: per-window context counts, genome totals, idx, attrs."""
+    assert (args.h5 or args.bed), "One of --h5 or --bed must be supplied."
+    assert not (args.h5 and args.bed), "At most one of --h5 or --bed can be supplied."
+    if args.h5:
+        df_bed = pd.DataFrame(storage.Store(args.h5, "r").read_array('idx'))
+    else:
+        df_bed = pd.read_table(args.bed, header=None, low_memory=False)
+        df_bed[0] = df_bed[0].astype(str)
+        df_bed = df_bed[df_bed[0].isin([str(i) for i in range(1, 23)])].copy()      # restrict to autosomes
+        df_bed[0] = df_bed[0].astype(int)
+    df_bed = df_bed.sort_values(by=[0, 1])
+    print('Counting nucleotide contexts in {} regions'.format(len(df_bed)))
+    g = sequence_tools.get_device_genome(args.fasta)
+    cidx = g.chrom_indices(df_bed.iloc[:, 0].values)
+    counts, totals = kernels.count_contexts(g, cidx, df_bed.iloc[:, 1].values, df_bed.iloc[:, 2].values,
+                                            args.up, args.down, want_totals=True)
+    cols = list(sequence_tools.mk_context_sequences(args.up, args.down))
+    index = ['chr{}:{}-{}'.format(c, s, e) for c, s, e in df_bed.iloc[:, 0:3].values]
+    df = pd.DataFrame(counts.cpu().numpy().astype(np.int64), index=index, columns=cols)
+    S_count = pd.Series(totals.cpu().numpy(), index=cols)              # == df.sum(axis=0), fused into the scan
+    idx = df_bed.iloc[:, 0:3].values
+    print('Saving context counts to {}'.format(args.fout))
+    st = storage.Store(args.fout, "w")
+    st.write_table('genome_counts', S_count)
+    st.write_table('all_window_genome_counts', df)
+    st.write_array('idx', idx, dtype=np.int32)
+    st.set_attrs(n_up=args.up, n_down=args.down, collapse=0)
+    if args.map_file:
+        mapp = np.loadtxt(args.map_file) if not args.map_file.endswith('.npy') else np.load(args.map_file)
+        assert len(mapp) == len(idx), "--map-file must hold one mappability value per window"
+        st.write_array('mappability', mapp, dtype=float)
+
+
+def addMutationContext(args):
+    """Reference DigPreprocess.py:75-100."""
+    print('Reading in mutation file')
+    df_mut = mutation_tools.read_mutation_file(args.fmut, drop_duplicates=False)
+    print('Extracting mutation contexts')
+    df_mut2 = sequence_tools.add_context_to_mutations(args.fasta, df_mut, n_up=args.up, n_down=args.down,
+                                                      N_proc=args.n_procs, collapse=False)
+    print('Saving annotated mutation file: {}'.format(args.fout))
+    if args.fout.endswith('.gz'):
+        args.fout = args.fout[:-3]
+    df_mut2.to_csv(args.fout, sep="\t", index=False, header=False)
+
+
+def initialize_data(args):
+    """Reference DigPreprocess.py:147-153 + sequence_tools.initialize_nonc_data (:451-478)."""
+    src = storage.Store(args.f_genome_counts, "r")
+    assert src.has('idx') and src.has('all_window_genome_counts'), \
+        "f_genome_counts file does not contain necessary groups. Please check that the correct file is passed"
+    idx = src.read_array('idx')
+    window = int(idx[0, 2] - idx[0, 1])
+    dst = storage.Store(args.f_annot_data, "a")
+    wkey = 'window_{}'.format(window)
+    if not dst.has('substitution_idx'):
+        dst.write_array('substitution_idx', np.array(sequence_tools.mk_trans_idx(1, 1)))
+    if not (dst.has(wkey + '/full_window_si_index') and dst.has(wkey + '/full_window_si_values')):
+        genome_df = src.read_table('all_window_genome_counts')
+        assert int(str(genome_df.index[0]).split('-')[-1]) - int(str(genome_df.index[0]).split(':')[1].split('-')[0]) == window
+        dst.write_array(wkey + '/full_window_si_values', genome_df.values, dtype=np.int64)
+        dst.write_array(wkey + '/full_window_si_index', idx)
+
+
+def preprocess_nonc_contexts(args):
+    """Reference DigPreprocess.py:129-144 for --f-bed: block context counts (K4) + element block tables."""
+    assert args.f_sites or args.f_element_bed, \
+        "ERROR: need to pass in a f_sites file or a elements file for preprocessing"
+    if args.f_sites:
+        raise NotImplementedError("sites preprocessing is driven through transfer_tools.run_sites_region_model")
+    print("Preprocessing elements")
+    L = sequence_tools.precount_region_contexts_parallel(args.f_element_bed, args.f_fasta, args.N_procs, args.window,
+                                                         args.use_sub_elts)
+    df_elts = mutation_tools.bed12_boundaries(args.f_element_bed)
+    df_elts['BLOCK_STARTS'] = [','.join(map(str, b)) for b in df_elts.BLOCK_STARTS]
+    df_elts['BLOCK_ENDS'] = [','.join(map(str, b)) for b in df_elts.BLOCK_ENDS]
+    st = storage.Store(args.f_element_data, "a")
+    wkey = 'window_{}'.format(args.window)
+    st.write_table('{}/{}/elements'.format(wkey, args.save_key), df_elts.reset_index(drop=True))
+    st.write_table('{}/{}/L_contexts'.format(wkey, args.save_key), L)
+
+
+def parse_args(text=None):
+    parser = argparse.ArgumentParser(description='Preprocess genome and mutation files for use with Dig (B200).')
+    sub = parser.add_subparsers()
+    a = sub.add_parser('countGenomeContext', help='count nucleotide contexts in genome windows')
+    a.add_argument('fasta', type=str)
+    a.add_argument('fout', type=str)
+    a.add_argument('--h5', type=str, default='')
+    a.add_argument('--bed', type=str, default='')
+    a.add_argument('--up', type=int, default=1)
+    a.add_argument('--down', type=int, default=1)
+    a.add_argument('--n-procs', type=int, default=get_cpus())
+    a.add_argument('--map-file', type=str, default='')
+    a.add_argument('--map-thresh', type=float, default=0.5)
+    a.set_defaults(func=countGenomeContext)
+    b = sub.add_parser('addMutationContext', help='annotate mutations with their sequence context')
+    b.add_argument('fmut', type=str)
+    b.add_argument('fasta', type=str)
+    b.add_argument('fout', type=str)
+    b.add_argument('--up', type=int, default=1)
+    b.add_argument('--down', type=int, default=1)
+    b.add_argument('--n-procs', type=int, default=get_cpus())
+    b.set_defaults(func=addMutationContext)
+    e = sub.add_parser('preprocess_element_model', help='precount element contexts')
+    e.add_argument('f_element_data')
+    e.add_argument('f_pretrained')
+    e.add_argument('f_fasta')
+    e.add_argument('save_key')
+    e.add_argument('--f-bed', dest='f_element_bed')
+    e.add_argument('--f-sites', type=str, default=None)
+    e.add_argument('--ignore-sub_elts', dest='use_sub_elts', action='store_false', default=True)
+    e.add_argument('--n-procs', default=get_cpus(), type=int, dest='N_procs')
+    e.add_argument('--window', type=int, default=10000)
+    e.set_defaults(func=preprocess_nonc_contexts)
+    f = sub.add_parser('initialize_f_data', help='copy window counts into the element data store')
+    f.add_argument('f_annot_data')
+    f.add_argument('f_genome_counts')
+    f.set_defaults(func=initialize_data)
+    return parser.parse_args(text.split()) if text else parser.parse_args()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    args.func(args)

@@ -1,0 +1,136 @@
+"""CPU-only tests of the host-side logic (no kernel launches): loaders, storage, index tables, window maps."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import golden
+
+
+def test_index_tables_match_reference_on_cpu():
+    from digdriver_b200.sequence_model import sequence_tools as st
+    z = golden("tables")
+    assert st.mk_trans_idx() == list(z["trans_idx"])
+    df = st.mk_mutation_context(return_df=True)
+    assert list(df.MUT_TYPE) == list(z["mutctx_mut"]) and list(df.CONTEXT) == list(z["mutctx_ctx"])
+    assert list(st.mk_context_sequences(2, 2)) == list(golden("scan")["columns_2_2"])
+    assert len(st.mk_context_sequences(1, 1, collapse=True)) == 32
+    assert st.reverse_complement("AACGN") == "NCGTT"
+    assert st.seq_to_context("ANA") == "" and st.type_mutation("G", "A", collapse=True) == "C>T"
+
+
+def test_get_ideal_overlaps_golden():
+    from digdriver_b200.sequence_model.genic_driver_tools import get_ideal_overlaps, trip_to_str
+    z = golden("overlaps")
+    for i in range(8):
+        for W in (10000, 1000):
+            got = get_ideal_overlaps(3, z["case%d_w%d_in" % (i, W)], W)
+            assert [list(t) for t in got] == z["case%d_w%d_out" % (i, W)].tolist()
+    assert trip_to_str((1, 0, 10)) == "chr1:0-10"
+
+
+def test_storage_roundtrip(tmp_path):
+    from digdriver_b200 import storage
+    st = storage.Store(str(tmp_path / "s"), "w")
+    df = pd.DataFrame({"MUT_TYPE": ["A>C", "C>T"], "FREQ": [1e-6, 2.5e-7], "FLAG": [True, False]},
+                      index=["chr1:0-10", "chr1:10-20"])
+    st.write_table("window_10000/K/elements", df)
+    got = storage.read_hdf(str(tmp_path / "s"), "window_10000/K/elements")
+    assert list(got.columns) == list(df.columns) and list(got.index) == list(df.index)
+    assert np.array_equal(got.FREQ.values, df.FREQ.values) and got.FLAG.dtype == bool
+    s = pd.Series([3, 4], index=["AAA", "AAC"])
+    st.write_table("genome_counts", s)
+    assert st.read_table("genome_counts").to_dict() == {"AAA": 3, "AAC": 4}
+    st.write_array("idx", np.arange(6).reshape(2, 3), dtype=np.int32)
+    assert st.read_array("idx").dtype == np.int32 and st.has("idx") and not st.has("nope")
+    st.set_attrs(n_up=1, n_down=np.int64(2))
+    assert st.get_attrs() == {"n_up": 1, "n_down": 2}
+    assert st.keys("window_10000") == ["K"]
+    with pytest.raises(FileNotFoundError):
+        storage.Store(str(tmp_path / "missing"), "r")
+
+
+def test_read_mutation_file_schemas(tmp_path):
+    from digdriver_b200.data_tools import mutation_tools as mt
+    rows = [("1", 100, 101, "A", "C", "S1", "G1", "Missense", "A>C", "TAG"),
+            ("1", 100, 101, "A", "C", "S1", "G1", "Missense", "A>C", "TAG"),
+            ("X", 5, 6, "A", "C", "S1", ".", "Noncoding", "A>C", "TAG"),
+            ("2", 7, 9, "AT", "A", "S2", "G2", "INDEL", "cds_INDEL", "."),
+            ("2", 7, 9, "AT", "A", "S3", "G2", "INDEL", "cds_INDEL", ".")]
+    f = tmp_path / "m.tsv"
+    pd.DataFrame(rows).to_csv(f, sep="\t", header=False, index=False)
+    df = mt.read_mutation_file(str(f))
+    assert list(df.columns) == ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'GENE', 'ANNOT', 'MUT_TYPE', 'CONTEXT']
+    assert df.CHROM.dtype.kind == "i" and set(df.CHROM) == {1, 2}         # sex chromosomes dropped
+    assert (df.ANNOT == "INDEL").sum() == 1                               # indels unique on (..., GENE)
+    assert len(mt.read_mutation_file(str(f), drop_duplicates=True)) == 2
+    assert len(mt.read_mutation_file(str(f), drop_sex=False)) == 4
+    pd.DataFrame([r[:6] for r in rows]).to_csv(f, sep="\t", header=False, index=False)
+    assert list(mt.read_mutation_file(str(f), unique_indels=False).columns) == ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE']
+    wl, bl = mt.filter_hypermut_samples(df, 1, return_blacklist=True)
+    assert bl == ["S1"] and set(wl.SAMPLE) == {"S2"}
+
+
+def test_bed12_boundaries(tmp_path):
+    from digdriver_b200.data_tools import mutation_tools as mt
+    f = tmp_path / "e.bed"
+    f.write_text("chr1\t100\t500\tE1\t0\t-\t100\t500\t0\t2\t50,20,\t0,380,\n"
+                 "X\t1\t9\tEX\t0\t+\t1\t9\t0\t1\t8\t0\n"
+                 "2\t10\t40\tE2\t0\t+\t10\t40\t0\t1\t30\t0\n")
+    df = mt.bed12_boundaries(str(f))
+    assert list(df.ELT) == ["E1", "E2"] and list(df.CHROM) == [1, 2]
+    assert df.BLOCK_STARTS.iloc[0] == [100, 480] and df.BLOCK_ENDS.iloc[0] == [150, 500]
+    blocks = mt._read_bed_blocks(str(f), bed12=True)
+    assert len(blocks) == 4 and list(blocks.CHROM) == ["chr1", "chr1", "X", "2"]
+
+
+def test_window_tiling_and_map():
+    from digdriver_b200 import genome as G, kernels
+    w = G.tile_windows([1, 2], [40123, 2000], 1000)
+    assert len(w) == 40 + 1 and w[-1].tolist() == [2, 0, 1000] and w[39].tolist() == [1, 39000, 40000]
+    off, wmap = kernels.build_window_map(w[:, 0], w[:, 1], 1000, 3)
+    assert off.tolist() == [0, 0, 40, 41] and wmap[39] == 39 and wmap[40] == 40
+    keep = np.r_[0:10, 12:41]
+    off, wmap = kernels.build_window_map(w[keep, 0], w[keep, 1], 1000, 3)
+    assert wmap[10] == -1 and wmap[11] == -1 and wmap[12] == 10
+    assert kernels.element_max_span([0, 2, 3], [100, 25000, 7], [900, 25100, 9], 1000) == 26
+    assert G.hg19_like_lengths().sum() == 3_100_000_000
+
+
+def test_fasta_reader(tmp_path):
+    from digdriver_b200.genome import Genome
+    f = tmp_path / "g.fa"
+    f.write_text(">chr1 desc\nACGT\nacgN\n>chr2\nTT\n")
+    g = Genome.from_fasta(str(f))
+    assert g.names == ["chr1", "chr2"] and g.fetch("chr1") == "ACGTacgN" and g.fetch("chr2", 1, 2) == "T"
+    assert g.lengths.tolist() == [8, 2]
+
+
+def test_restrict_mutations_to_regions_and_qvals():
+    from digdriver_b200.sequence_model import sequence_tools as st
+    from digdriver_b200.sequence_model.nb_model import get_q_vals
+    mut = pd.DataFrame({"CHROM": [1, 1, 1, 2, 2], "START": [5, 10, 19, 5, 30], "END": [6, 11, 25, 6, 31],
+                        "REF": list("AAAAA"), "ALT": list("CCCCC")})
+    got = st.restrict_mutations_to_regions(mut, np.array([[1, 10, 20], [2, 0, 10]]))
+    assert got.START.tolist() == [10, 19, 5]
+    q = get_q_vals([0.01, 0.04, 0.03, 0.5])
+    np.testing.assert_allclose(q, [0.04, 0.04 * 4 / 3, 0.04 * 4 / 3, 0.5])
+
+
+def test_cli_parsers_accept_the_reference_arguments():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mods = {}
+    for name in ("DigPreprocess", "DigPretrain", "DigDriver"):
+        spec = importlib.util.spec_from_file_location("cli_" + name, os.path.join(root, "scripts", name + ".py"))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    a = mods["DigPreprocess"].parse_args("countGenomeContext g.fa out --bed w.bed --up 2 --down 2 --n-procs 4")
+    assert a.up == 2 and a.bed == "w.bed" and a.func.__name__ == "countGenomeContext"
+    a = mods["DigPretrain"].parse_args("elementModel pre.h5 data.h5 KEY --n-procs 3")
+    assert a.save_key == "KEY" and a.N_procs == 3
+    a = mods["DigDriver"].parse_args("elementDriver m.txt model.h5 KEY --f-bed e.bed --outpfx x --outdir o --scale-type genome")
+    assert a.f_bed == "e.bed" and a.scale_type == "genome" and a.max_muts_per_sample == 3e9
+    a = mods["DigDriver"].parse_args("geneDriver m.txt model.h5 --outpfx x --outdir o --scale-by-mutations")
+    assert a.scale_by_expectation is False
