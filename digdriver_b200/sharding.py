@@ -1,0 +1,93 @@
+"""Range sharding of the hot path over the GPUs of one node.
+
+Windows are independent given a halo of max(n_up, n_down) bases, elements are independent given the window
+count table, p-values are independent per row.  So the genome is cut into contiguous genomic ranges on
+window boundaries, one per rank; the only exchanges are
+  * all-reduce(sum) of the genome-wide context totals (replaces df.sum(axis=0), DigPreprocess.py:59),
+  * all-reduce(sum) of substitution counts / scale-factor sums,
+  * gather of per-window / per-element result rows on rank 0 (replaces pd.concat, sequence_tools.py:125).
+All of them go through torch.distributed (NCCL on GPUs, gloo in the CPU tests); payloads are KB-sized.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .genome import Genome
+
+
+def partition_windows(win_start, win_end, world):
+    """Cut the window list (sorted by chromosome, start) into `world` contiguous slices of nearly equal
+    base count.  Returns a list of (lo, hi) index pairs."""
+    size = (np.asarray(win_end, dtype=np.int64) - np.asarray(win_start, dtype=np.int64)).clip(min=0)
+    cum = np.concatenate([[0], np.cumsum(size)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(len(size))
+    cuts = np.maximum.accumulate(np.minimum(cuts, len(size)))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+def slice_genome(genome, win_chrom, win_start, win_end, halo):
+    """The part of `genome` one rank needs for its windows: for every chromosome touched, the segment from
+    (first window start - halo) to (last window end + halo), clipped to the chromosome.  Returns
+    (Genome of segments, chrom index per window into it, re-based starts, re-based ends).
+
+    The halo keeps the reference's edge rules intact after re-basing: a re-based START is 0 only when the true
+    START is 0 (sequence_tools.py:25-26), and a segment ends before its window's END + n_down only at the true
+    chromosome end (the faidx clipping of :28)."""
+    win_chrom = np.asarray(win_chrom)
+    ws = np.asarray(win_start, dtype=np.int64)
+    we = np.asarray(win_end, dtype=np.int64)
+    names, seqs, seg_of = [], [], {}
+    new_chrom = np.empty(len(ws), dtype=np.int32)
+    new_s, new_e = ws.copy(), we.copy()
+    for c in dict.fromkeys(win_chrom.tolist()):
+        m = win_chrom == c
+        L = len(genome.seqs[c])
+        a = max(int(ws[m].min()) - halo, 0)
+        b = min(int(we[m].max()) + halo, L)
+        seg_of[c] = len(names)
+        names.append(genome.names[c])
+        seqs.append(genome.seqs[c][a:max(b, a)])
+        new_chrom[m] = seg_of[c]
+        new_s[m] -= a
+        new_e[m] -= a
+    return Genome(names, seqs), new_chrom, new_s, new_e
+
+
+class Collectives:
+    """Thin wrapper so the same sharded driver runs on NCCL (GPU) and gloo (CPU tests)."""
+
+    def __init__(self):
+        self.on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank() if self.on else 0
+        self.world = dist.get_world_size() if self.on else 1
+
+    def all_reduce_sum(self, t):
+        if self.on and self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    def all_reduce_max(self, t):
+        if self.on and self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
+    def gather_rows(self, t):
+        """Concatenate per-rank row blocks (possibly of different length) on rank 0; None elsewhere."""
+        if not self.on or self.world == 1:
+            return t
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(sizes)
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+        if self.rank != 0:
+            return None
+        return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
