@@ -227,36 +227,24 @@ def hot_path_step(dg, di, d, dist_ctx, ev=None):
     sub = kernels.substitution_counts(ctx, di.m_alt, 1, 1)
     if dist_ctx is not None:
         buf = torch.cat([di.totals5, di.totals3, sub])
-        dist_ctx.all_reduce(buf)
+        dist_ctx.all_reduce_sum(buf)
         tot3, sub = buf[1024:1088], buf[1088:]
     else:
         tot3 = di.totals3
-    d_pr = sub.to(torch.float64) / tot3.to(torch.float64).repeat_interleave(3)
+    d_pr = kernels.sequence_freq(sub.contiguous(), tot3.contiguous())
     # 3. gene pretrain (K6), observed counts (K5), burden test (K7)
     pre = kernels.element_transfer(di.g_chrom, di.g_strand, di.g_ptr, di.g_bs, di.g_be, WINDOW, di.wmap_off,
                                    di.wmap, di.counts3, di.y_pred, di.std, di.y_true, di.flag, d_pr,
                                    L_elt=di.L, device=dev, max_span=di.max_span)
     obs, nsamp = kernels.tabulate_genes(di.m_gene, di.m_sample, di.m_cls, N_GENES, device=dev)
     n_syn = d["n_syn"]
-    res = pipeline.gene_burden_test(pre, obs, nsamp, n_syn)
+    res = pipeline.gene_burden_test(pre, obs, nsamp, n_syn, collectives=dist_ctx)
     return res
 
 
-class DistCtx:
-    def __init__(self):
-        import torch.distributed as dist
-        self.dist = dist
-        self.rank = dist.get_rank()
-        self.world = dist.get_world_size()
-
-    def all_reduce(self, t):
-        self.dist.all_reduce(t)
-
-    def gather_results(self, t):
-        import torch
-        out = [torch.empty_like(t) for _ in range(self.world)] if self.rank == 0 else None
-        self.dist.gather(t, out, dst=0)
-        return out
+def gather_results(coll, t):
+    """Per-gene results of every shard on rank 0 (the reference's pd.concat of chunk results)."""
+    return coll.gather_rows(t.unsqueeze(1))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -454,7 +442,8 @@ def main():
     dist_ctx = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-        dist_ctx = DistCtx()
+        from digdriver_b200.sharding import Collectives
+        dist_ctx = Collectives()
 
     clocks = ClockSampler(local_rank)
     clocks.start()                       # nvidia-smi takes a while to start: launch it before the set-up
@@ -473,7 +462,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         res = hot_path_step(dg, di, d, dist_ctx)
         if dist_ctx is not None:
-            dist_ctx.gather_results(res["PVAL_MUT_BURDEN"])
+            gather_results(dist_ctx, res["PVAL_MUT_BURDEN"])
     barrier()
     ev_all = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -483,7 +472,7 @@ def main():
     for i in range(args.steps):
         res = hot_path_step(dg, di, d, dist_ctx, ev=ev_all[i])
         if dist_ctx is not None:
-            dist_ctx.gather_results(res["PVAL_MUT_BURDEN"])
+            gather_results(dist_ctx, res["PVAL_MUT_BURDEN"])
     end.record()
     barrier()
     launches = _lib.launch_count - launches0

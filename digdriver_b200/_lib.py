@@ -37,6 +37,9 @@ SIGNATURES = {
     "dig_nb_pvalue_greater_midp": (_I, [_P, _P, _P, _I64, _P, _P]),
     "dig_nb_burden_test": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "dig_fisher_combine2": (_I, [_P, _P, _I64, _P, _P]),
+    "dig_sequence_freq": (_I, [_P, _P, _I, _P, _P]),
+    "dig_gene_scale_sums": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P]),
+    "dig_gene_burden_test": (_I, [_P, _P, _P, _P, _P, _P, _I64, _P, _D, _D, _P, _P]),
 }
 
 _lib = None
@@ -47,6 +50,7 @@ KERNELS_PER_CALL = {
     "dig_pack_genome": 1, "dig_count_contexts": 1, "dig_synth_genome": 1, "dig_mutation_contexts": 1,
     "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2,
     "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
+    "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
 }
 launch_count = 0
 

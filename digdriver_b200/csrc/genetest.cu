@@ -1,0 +1,167 @@
+// Gene-level burden stage fused on the device: scale-factor sums, then all 13 NB tests + Fisher per gene.
+//
+// Replaces the table arithmetic of run_gene_model (transfer_tools.py:809-861): load_pretrained_model's
+// ALPHA/THETA (:17-19, nb_model.py:237-241), Pi_TRUNC/Pi_NONSYN (genic_driver_tools.py:123, transfer_tools.py:34),
+// the synonymous scale factor cj (:813-815), gene_expected_muts_nb (:331-341), gene_pvalue_burden_nb (:394-456),
+// gene_pvalue_burden_nb_by_sample (:484-592), gene_pvalue_indel (:709-729) and the Fisher combine (:860-861).
+#include "nb_math.cuh"
+
+namespace {
+
+using namespace dig_nb;
+
+// sums[0] = sum_{g != TP53} MU * Pi_SYN          sums[1] = sum_{g not CGC} Pi_INDEL * ALPHA * THETA
+// sums[2] = sum_{g not CGC} OBS_INDEL            (fixed summation order: one block, strided + tree)
+__global__ void __launch_bounds__(1024) gene_scale_sums_kernel(
+    const double *__restrict__ mu, const double *__restrict__ sigma, const double *__restrict__ P,
+    const double *__restrict__ pi_indel, const int64_t *__restrict__ obs, const uint8_t *__restrict__ cgc,
+    int64_t tp53, int64_t n, double *__restrict__ sums)
+{
+    __shared__ double sh[3][1024];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int64_t g = threadIdx.x; g < n; g += 1024) {
+        const double m = mu[g], s = sigma[g];
+        if (g != tp53) a0 += m * P[g * 4 + 0];
+        if (cgc == nullptr || !cgc[g]) {
+            const double alpha = (m * m) / (s * s);
+            const double theta = (s * s) / m;
+            a1 += pi_indel[g] * alpha * theta;
+            a2 += (double)obs[g * 5 + 4];
+        }
+    }
+    sh[0][threadIdx.x] = a0;
+    sh[1][threadIdx.x] = a1;
+    sh[2][threadIdx.x] = a2;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) sums[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// test t of gene g: t in 0..5 count burden (SYN, MIS, NONS, SPL, TRUNC, NONSYN), 6..11 sample burden, 12 indel
+__global__ void __launch_bounds__(128) gene_test_kernel(
+    const double *__restrict__ mu, const double *__restrict__ sigma, const double *__restrict__ P,
+    const double *__restrict__ pi_indel, const int64_t *__restrict__ obs, const int64_t *__restrict__ nsamp,
+    int64_t n, const double *__restrict__ sums, double n_syn,
+    double scale_factor, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double cj = isnan(scale_factor) ? n_syn / sums[0] : scale_factor;
+    const double t_indel = sums[2] / sums[1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 13; i += stride) {
+        const int64_t g = i / 13;
+        const int t = (int)(i - g * 13);
+        const double m = mu[g], s = sigma[g];
+        const double alpha = (m * m) / (s * s);
+        const double theta0 = (s * s) / m;
+        const double p_syn = P[g * 4 + 0], p_mis = P[g * 4 + 1], p_nons = P[g * 4 + 2], p_spl = P[g * 4 + 3];
+        const double p_trunc = p_nons + p_spl;
+        const double p_nonsyn = p_mis + p_trunc;
+        double pi, k, theta;
+        if (t == 12) {
+            pi = pi_indel[g];
+            k = (double)obs[g * 5 + 4];
+            theta = theta0 * t_indel;
+        } else {
+            const int c = t % 6;
+            pi = c == 0 ? p_syn : c == 1 ? p_mis : c == 2 ? p_nons : c == 3 ? p_spl : c == 4 ? p_trunc : p_nonsyn;
+            theta = theta0 * cj;
+            if (t < 6) {
+                const double o0 = (double)obs[g * 5 + 0], o1 = (double)obs[g * 5 + 1], o2 = (double)obs[g * 5 + 2],
+                             o3 = (double)obs[g * 5 + 3];
+                k = c == 0 ? o0 : c == 1 ? o1 : c == 2 ? o2 : c == 3 ? o3 : c == 4 ? o2 + o3 : o1 + (o2 + o3);
+            } else {
+                k = (double)nsamp[g * 7 + (c < 4 ? c : c)];      // nsamp columns: SYN MIS NONS SPL TRUNC NONSYN INDEL
+            }
+        }
+        const double expv = __dmul_rn(__dmul_rn(alpha, theta), pi);
+        const double p = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(theta, pi), 1.0));
+        const double pval = nb_midp(k, alpha, p);
+        // rows: 0-5 EXP_*, 6-11 PVAL_*_BURDEN, 12-17 PVAL_*_BURDEN_SAMPLE, 18 EXP_INDEL, 19 PVAL_INDEL_BURDEN
+        if (t < 6) {
+            out[(int64_t)t * n + g] = expv;
+            out[(int64_t)(6 + t) * n + g] = pval;
+        } else if (t < 12) {
+            out[(int64_t)(6 + t) * n + g] = pval;
+        } else {
+            out[18 * n + g] = expv;
+            out[19 * n + g] = pval;
+        }
+        if (t == 0) {
+            out[21 * n + g] = alpha;
+            out[22 * n + g] = theta;
+            out[23 * n + g] = theta0 * t_indel;
+            out[24 * n + g] = pi_indel[g];
+            out[25 * n + g] = p_trunc;
+            out[26 * n + g] = p_nonsyn;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gene_fisher_kernel(int64_t n, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride)
+        out[20 * n + g] = fisher2(out[(6 + 4) * n + g], out[19 * n + g]);     // PVAL_TRUNC_BURDEN x PVAL_INDEL_BURDEN
+}
+
+__global__ void __launch_bounds__(256) seq_freq_kernel(const unsigned long long *__restrict__ counts,
+                                                       const unsigned long long *__restrict__ totals, int n_sub,
+                                                       double *__restrict__ freq)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_sub) freq[j] = (double)counts[j] / (double)totals[j / 3];
+}
+
+}  // namespace
+
+extern "C" {
+
+int dig_sequence_freq(const unsigned long long *subst_counts_d, const unsigned long long *ctx_totals_d, int n_ctx,
+                      double *freq_d, void *stream)
+{
+    DIG_CHECK_ARG(n_ctx > 0 && subst_counts_d && ctx_totals_d && freq_d, "bad arguments");
+    const int n_sub = 3 * n_ctx;
+    seq_freq_kernel<<<(n_sub + 255) / 256, 256, 0, (cudaStream_t)stream>>>(subst_counts_d, ctx_totals_d, n_sub, freq_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_gene_scale_sums(const double *mu_d, const double *sigma_d, const double *p_d, const double *pi_indel_d,
+                        const int64_t *obs_d, const uint8_t *cgc_mask_d, int64_t tp53, int64_t n_gene,
+                        double *sums_d, void *stream)
+{
+    DIG_CHECK_ARG(n_gene >= 0 && sums_d, "bad arguments");
+    DIG_CHECK_ARG(n_gene == 0 || (mu_d && sigma_d && p_d && pi_indel_d && obs_d), "null pointer");
+    gene_scale_sums_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mu_d, sigma_d, p_d, pi_indel_d, obs_d, cgc_mask_d,
+                                                                 tp53, n_gene, sums_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_gene_burden_test(const double *mu_d, const double *sigma_d, const double *p_d, const double *pi_indel_d,
+                         const int64_t *obs_d, const int64_t *nsamp_d, int64_t n_gene, const double *sums_d,
+                         double n_syn, double scale_factor, double *out_d, void *stream)
+{
+    DIG_CHECK_ARG(n_gene >= 0, "negative size");
+    if (n_gene == 0) return DIG_OK;
+    DIG_CHECK_ARG(mu_d && sigma_d && p_d && pi_indel_d && obs_d && nsamp_d && sums_d && out_d, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (n_gene * 13 + 127) / 128;
+    const int64_t cap = (int64_t)dig::sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    gene_test_kernel<<<(unsigned)blocks, 128, 0, st>>>(mu_d, sigma_d, p_d, pi_indel_d, obs_d, nsamp_d, n_gene, sums_d,
+                                                       n_syn, scale_factor, out_d);
+    DIG_CHECK_LAUNCH();
+    gene_fisher_kernel<<<(unsigned)((n_gene + 255) / 256), 256, 0, st>>>(n_gene, out_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+}

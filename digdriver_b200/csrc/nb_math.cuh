@@ -1,0 +1,145 @@
+// FP64 negative-binomial mid-p arithmetic shared by nbtest.cu and genetest.cu (see nbtest.cu for the method).
+#pragma once
+#include "dig_common.cuh"
+
+namespace dig_nb {
+
+__device__ const double c_sfe[31] = {
+    0.0, 0.1534264097200273452913848, 0.0810614667953272582196702, 0.0548141210519176538961390,
+    0.0413406959554092940938221, 0.03316287351993628748511048, 0.02767792568499833914878929,
+    0.02374616365629749597132920, 0.02079067210376509311152277, 0.01848845053267318523077934,
+    0.01664469118982119216319487, 0.01513497322191737887351255, 0.01387612882307074799874573,
+    0.01281046524292022692424986, 0.01189670994589177009505572, 0.01110455975820691732662991,
+    0.010411265261972096497478567, 0.009799416126158803298389475, 0.009255462182712732917728637,
+    0.008768700134139385462952823, 0.008330563433362871256469318, 0.007934114564314020547248100,
+    0.007573675487951840794972024, 0.007244554301320383179543912, 0.006942840107209529865664152,
+    0.006665247032707682442354394, 0.006408994188004207068439631, 0.006171712263039457647532867,
+    0.005951370112758847735624416, 0.005746216513010115682023589, 0.005554733551962801371038690};
+
+constexpr double LN_SQRT_2PI = 0.918938533204672741780329736406;
+constexpr double LN_2PI = 1.837877066409345483560659472811;
+
+// log(n!) - log(sqrt(2 pi n) (n/e)^n)
+__device__ inline double stirlerr(double n)
+{
+    if (n <= 15.0) {
+        const double nn = n + n;
+        if (nn == floor(nn)) return c_sfe[(int)nn];
+        return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - LN_SQRT_2PI;
+    }
+    const double S0 = 1.0 / 12.0, S1 = 1.0 / 360.0, S2 = 1.0 / 1260.0, S3 = 1.0 / 1680.0, S4 = 1.0 / 1188.0;
+    const double nn = n * n;
+    if (n > 500.0) return (S0 - S1 / nn) / n;
+    if (n > 80.0) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35.0) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+// deviance term x log(x/np) + np - x without cancellation when x ~ np
+__device__ inline double bd0(double x, double np)
+{
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * v;
+        if (fabs(s) < 2.2250738585072014e-308) return s;
+        double ej = 2.0 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; ++j) {
+            ej *= v;
+            const double s1 = s + ej / (double)((j << 1) + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+// log of the binomial-type kernel of Loader's algorithm (x, n real)
+__device__ inline double log_dbinom_raw(double x, double n, double p, double q)
+{
+    if (x == 0.0) {
+        if (n == 0.0) return 0.0;
+        return p < 0.1 ? -bd0(n, n * q) - n * p : n * log(q);
+    }
+    if (x == n) return q < 0.1 ? -bd0(n, n * p) - n * q : n * log(p);
+    const double lc = stirlerr(n) - stirlerr(x) - stirlerr(n - x) - bd0(x, n * p) - bd0(n - x, n * q);
+    const double lf = LN_2PI + log(x) + log1p(-x / n);
+    return lc - 0.5 * lf;
+}
+
+// log of Gamma(k+a)/(Gamma(a) Gamma(k+1)) p^a q^k for real k >= 0, a > 0, 0 < p,q < 1
+__device__ inline double log_nb_density(double k, double a, double p, double q)
+{
+    if (k == 0.0) return p > 0.5 ? a * log1p(-q) : a * log(p);
+    if (k < 1e-10 * a)
+        return a * log(p) + k * (log(a) + log(q)) - lgamma(k + 1.0) + log1p(k * (k - 1.0) / (2.0 * a));
+    return log_dbinom_raw(a, k + a, p, q) + log(a / (a + k));
+}
+
+// continued fraction of I_x(a,b) (modified Lentz); converges fast for x < (a+1)/(a+b+2)
+__device__ inline double beta_cf(double a, double b, double x)
+{
+    const double FPMIN = 1e-300, EPS = 1e-15;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0;
+    double d = 1.0 - qab * x / qap;
+    if (fabs(d) < FPMIN) d = FPMIN;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m < 2000000; ++m) {
+        const double dm = (double)m, m2 = 2.0 * dm;
+        double aa = dm * (b - dm) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < FPMIN) d = FPMIN;
+        c = 1.0 + aa / c;
+        if (fabs(c) < FPMIN) c = FPMIN;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + dm) * (qab + dm) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < FPMIN) d = FPMIN;
+        c = 1.0 + aa / c;
+        if (fabs(c) < FPMIN) c = FPMIN;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < EPS) break;
+    }
+    return h;
+}
+
+__device__ inline double nb_midp(double k, double alpha, double p)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (isnan(k) || isnan(alpha) || isnan(p)) return nan;
+    if (!(alpha > 0.0) || isinf(alpha) || k < 0.0 || isinf(k) || p < 0.0 || p > 1.0) return nan;
+    const double q = 1.0 - p;
+    const bool isint = (k == floor(k));
+    if (q <= 0.0) return k == 0.0 ? 0.5 : 0.0;   // p == 1: all mass at 0
+    if (p <= 0.0) return 1.0;
+    const double lg = log_nb_density(k, alpha, p, q);
+    const double a = k + 1.0;
+    double sf;
+    if (q < (a + 1.0) / (a + alpha + 2.0)) {
+        const double cf = beta_cf(a, alpha, q);
+        sf = exp(lg + log(q * (k + alpha) / a * cf));
+    } else {
+        const double cf = beta_cf(alpha, a, p);
+        sf = 1.0 - exp(lg + log(q * (k + alpha) / alpha * cf));
+    }
+    return (isint ? 0.5 * exp(lg) : 0.0) + sf;
+}
+
+
+// chi2.sf(-2 (ln p1 + ln p2), df=4) = exp(-y) (1 + y), y = -(ln p1 + ln p2)  (transfer_tools.py:860-861)
+__device__ inline double fisher2(double a, double b)
+{
+    if (isnan(a) || isnan(b)) return __longlong_as_double(0x7ff8000000000000LL);
+    const double y = -(log(a) + log(b));     // log(0) = -inf -> y = +inf -> 0
+    if (isnan(y)) return y;
+    if (y <= 0.0) return 1.0;
+    if (isinf(y)) return 0.0;
+    return exp(-y) * (1.0 + y);
+}
+
+}  // namespace dig_nb

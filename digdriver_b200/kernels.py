@@ -269,3 +269,44 @@ def substitution_counts(ctx, alt, n_up=1, n_down=1, stream=None):
         _lib.call("dig_substitution_counts", ctx.data_ptr(), al.data_ptr(), ctx.numel(), int(n_up), int(n_down),
                   out.data_ptr(), _stream(dev, stream))
     return out
+
+
+def sequence_freq(subst_counts, ctx_totals, stream=None):
+    """FREQ of every substitution = COUNT / S_genome[context] (float64 [3K], sorted substitution order)."""
+    dev = subst_counts.device
+    n_ctx = ctx_totals.numel()
+    out = torch.empty(3 * n_ctx, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_sequence_freq", subst_counts.data_ptr(), ctx_totals.data_ptr(), n_ctx, out.data_ptr(),
+                  _stream(dev, stream))
+    return out
+
+
+GENE_OUT_ROWS = (["EXP_" + c for c in ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")] +
+                 ["PVAL_%s_BURDEN" % c for c in ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")] +
+                 ["PVAL_%s_BURDEN_SAMPLE" % c for c in ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")] +
+                 ["EXP_INDEL", "PVAL_INDEL_BURDEN", "PVAL_MUT_BURDEN", "ALPHA", "THETA", "THETA_INDEL", "Pi_INDEL",
+                  "Pi_TRUNC", "Pi_NONSYN"])
+
+
+def gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc_mask=None, tp53=-1, stream=None):
+    """[sum_{g != TP53} MU*Pi_SYN, sum_{non-CGC} Pi_INDEL*ALPHA*THETA, sum_{non-CGC} OBS_INDEL] on the device."""
+    dev = mu.device
+    sums = torch.empty(3, dtype=torch.float64, device=dev)
+    cg = _dev(cgc_mask, torch.uint8, dev) if cgc_mask is not None else None
+    with torch.cuda.device(dev):
+        _lib.call("dig_gene_scale_sums", mu.data_ptr(), sigma.data_ptr(), P.data_ptr(), pi_indel.data_ptr(),
+                  obs.data_ptr(), _ptr(cg), int(tp53), mu.numel(), sums.data_ptr(), _stream(dev, stream))
+    return sums
+
+
+def gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, n_syn, scale_factor=None, stream=None):
+    """All 13 NB tests + Fisher per gene in one launch pair.  Returns float64 [27, E] (rows: GENE_OUT_ROWS)."""
+    dev = mu.device
+    E = mu.numel()
+    out = torch.empty((len(GENE_OUT_ROWS), E), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_gene_burden_test", mu.data_ptr(), sigma.data_ptr(), P.data_ptr(), pi_indel.data_ptr(),
+                  obs.data_ptr(), nsamp.data_ptr(), E, sums.data_ptr(), float(n_syn),
+                  float("nan") if scale_factor is None else float(scale_factor), out.data_ptr(), _stream(dev, stream))
+    return out

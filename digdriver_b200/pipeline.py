@@ -60,63 +60,30 @@ def gene_pretrain(genes, window, win_map_off, win_map, win_counts64, y_pred, std
     return out
 
 
-def gene_burden_test(pre, obs, nsamp, n_syn_non_tp53, tp53=-1, cgc_mask=None, scale_factor=None, cohort=0):
-    """run_gene_model's arithmetic (transfer_tools.py:809-861) on device tensors.
+def gene_burden_test(pre, obs, nsamp, n_syn_non_tp53, tp53=-1, cgc_mask=None, scale_factor=None, cohort=0,
+                     collectives=None):
+    """run_gene_model's arithmetic (transfer_tools.py:809-861) fused on the device: one reduction kernel for the
+    scale-factor sums, one kernel for the 13 NB tests of every gene, one for the Fisher combine.
 
-    pre: output of gene_pretrain; obs [E,5] / nsamp [E,7] from kernels.tabulate_genes.
+    pre: output of gene_pretrain; obs [E,5] / nsamp [E,7] from kernels.tabulate_genes.  With `collectives`
+    (sharding.Collectives) the sums and n_syn are all-reduced so every shard uses the cohort-wide scale factors.
     Returns a dict of [E] float64 device tensors with the reference's column names."""
-    dev = obs.device
-    E = obs.shape[0]
-    mu, sigma = pre["MU"][cohort], pre["SIGMA"][cohort]
-    P = pre["P"][cohort]                                     # silent, mis, nons, splice
-    pi = {"SYN": P[:, 0], "MIS": P[:, 1], "NONS": P[:, 2], "SPL": P[:, 3]}
-    pi["TRUNC"] = pi["NONS"] + pi["SPL"]                      # genic_driver_tools.py:123
-    pi["NONSYN"] = pi["MIS"] + pi["TRUNC"]                    # transfer_tools.py:34
-    alpha = mu ** 2 / sigma ** 2                              # nb_model.py:237-241
-    theta = sigma ** 2 / mu
-    keep = torch.ones(E, dtype=torch.bool, device=dev)
-    if tp53 >= 0:
-        keep[tp53] = False
-    if scale_factor is None:                                  # transfer_tools.py:813-815
-        exp_syn = (mu[keep] * pi["SYN"][keep]).sum()
-        cj = float(n_syn_non_tp53) / exp_syn
-    else:
-        cj = torch.tensor(float(scale_factor), dtype=torch.float64, device=dev)
-    theta_c = theta * cj                                      # transfer_tools.py:268
+    mu, sigma = pre["MU"][cohort].contiguous(), pre["SIGMA"][cohort].contiguous()
+    P = pre["P"][cohort].contiguous()                        # silent, mis, nons, splice
+    pi_indel = pre["ELT_SIZE"].to(torch.float64) / pre["R_SIZE"].to(torch.float64)   # genic_driver_tools.py:158-159
+    sums = kernels.gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc_mask, tp53)
+    n_syn = float(n_syn_non_tp53)
+    if collectives is not None and collectives.world > 1:
+        buf = torch.cat([sums, torch.tensor([n_syn], dtype=torch.float64, device=sums.device)])
+        collectives.all_reduce_sum(buf)
+        sums, n_syn_t = buf[:3].contiguous(), buf[3]
+        n_syn = float(n_syn_t)                                # one scalar read; only on the multi-GPU path
+    out = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, n_syn, scale_factor)
+    res = {name: out[i] for i, name in enumerate(kernels.GENE_OUT_ROWS)}
     o = obs.to(torch.float64)
-    ns = nsamp.to(torch.float64)
-    k = {"SYN": o[:, 0], "MIS": o[:, 1], "NONS": o[:, 2], "SPL": o[:, 3]}
-    k["TRUNC"] = k["NONS"] + k["SPL"]                         # transfer_tools.py:231-232
-    k["NONSYN"] = k["MIS"] + k["TRUNC"]
-    ks = {"SYN": ns[:, 0], "MIS": ns[:, 1], "NONS": ns[:, 2], "SPL": ns[:, 3], "TRUNC": ns[:, 4], "NONSYN": ns[:, 5]}
-    # indel model (gene_pvalue_indel, transfer_tools.py:709-729)
-    r_size = pre["R_SIZE"].to(torch.float64)
-    pi_indel = pre["ELT_SIZE"].to(torch.float64) / r_size     # genic_driver_tools.py:158-159
-    null = torch.ones(E, dtype=torch.bool, device=dev) if cgc_mask is None else ~torch.as_tensor(cgc_mask, device=dev)
-    exp_unif = (pi_indel[null] * alpha[null] * theta[null]).sum()
-    t_indel = o[:, 4][null].sum() / exp_unif
-    theta_indel = theta * t_indel
-    # one fused launch for all 13 NB tests of every gene
-    kk = torch.stack([k[c] for c in GENE_CLASSES] + [ks[c] for c in GENE_CLASSES] + [o[:, 4]])
-    pp = torch.stack([pi[c] for c in GENE_CLASSES] * 2 + [pi_indel])
-    tt = torch.cat([theta_c.expand(12, E), theta_indel.unsqueeze(0)])
-    aa = alpha.expand(13, E)
-    exp, pval = kernels.nb_burden_test(kk.reshape(-1), aa.reshape(-1), tt.reshape(-1), pp.reshape(-1), dev)
-    exp, pval = exp.reshape(13, E), pval.reshape(13, E)
-    res = {"MU": mu, "SIGMA": sigma, "ALPHA": alpha, "THETA": theta_c, "THETA_INDEL": theta_indel,
-           "Pi_INDEL": pi_indel, "CJ": cj, "T_INDEL": t_indel}
-    for i, c in enumerate(GENE_CLASSES):
-        res["Pi_" + c] = pi[c]
-        res["OBS_" + c] = k[c]
-        res["N_SAMP_" + c] = ks[c]
-        res["EXP_" + c] = exp[i]
-        res["PVAL_%s_BURDEN" % c] = pval[i]
-        res["PVAL_%s_BURDEN_SAMPLE" % c] = pval[6 + i]
-    res["OBS_INDEL"] = o[:, 4]
-    res["N_SAMP_INDEL"] = ns[:, 6]
-    res["EXP_INDEL"] = exp[12]
-    res["PVAL_INDEL_BURDEN"] = pval[12]
-    res["PVAL_MUT_BURDEN"] = kernels.fisher_combine2(res["PVAL_TRUNC_BURDEN"], pval[12], dev)
+    res.update({"MU": mu, "SIGMA": sigma, "Pi_SYN": P[:, 0], "Pi_MIS": P[:, 1], "Pi_NONS": P[:, 2], "Pi_SPL": P[:, 3],
+                "OBS_SYN": o[:, 0], "OBS_MIS": o[:, 1], "OBS_NONS": o[:, 2], "OBS_SPL": o[:, 3], "OBS_INDEL": o[:, 4],
+                "SUMS": sums})
     return res
 
 

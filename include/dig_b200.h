@@ -200,6 +200,29 @@ int dig_nb_burden_test(const double *k_d, const double *alpha_d, const double *t
 int dig_fisher_combine2(const double *p1_d, const double *p2_d, int64_t n, double *out_d, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * Gene-level burden stage fused on the device (run_gene_model's table arithmetic, transfer_tools.py:809-861).
+ * dig_sequence_freq: FREQ[j] = COUNT[j] / S_genome[j / 3] (mutation_freq_conditional, sequence_tools.py:356-373)
+ *   for the 3*n_ctx substitutions in sorted 'CTX>CTX2' order; inputs are the uint64 outputs of
+ *   dig_substitution_counts and the totals of dig_count_contexts.
+ * dig_gene_scale_sums: sums_d[0] = sum_{g != tp53} MU*Pi_SYN (:814), sums_d[1] = sum_{g not CGC}
+ *   Pi_INDEL*ALPHA*THETA (:716), sums_d[2] = sum_{g not CGC} OBS_INDEL (:717).  One block, fixed summation
+ *   order.  Multi-GPU callers all-reduce sums_d (and n_syn) between the two calls.
+ * dig_gene_burden_test: cj = n_syn / sums[0] (or scale_factor when it is not NaN), t_indel = sums[2] / sums[1];
+ *   out_d [27, n_gene] rows: 0-5 EXP_{SYN,MIS,NONS,SPL,TRUNC,NONSYN}, 6-11 PVAL_*_BURDEN, 12-17
+ *   PVAL_*_BURDEN_SAMPLE, 18 EXP_INDEL, 19 PVAL_INDEL_BURDEN, 20 PVAL_MUT_BURDEN (Fisher of TRUNC and INDEL),
+ *   21 ALPHA, 22 THETA (scaled by cj), 23 THETA_INDEL, 24 Pi_INDEL, 25 Pi_TRUNC, 26 Pi_NONSYN.
+ *   p_d [n_gene, 4] = Pi_SYN, Pi_MIS, Pi_NONS, Pi_SPL; obs_d [n_gene, 5], nsamp_d [n_gene, 7] from dig_tabulate_genes.
+ */
+int dig_sequence_freq(const unsigned long long *subst_counts_d, const unsigned long long *ctx_totals_d, int n_ctx,
+                      double *freq_d, void *stream);
+int dig_gene_scale_sums(const double *mu_d, const double *sigma_d, const double *p_d, const double *pi_indel_d,
+                        const int64_t *obs_d, const uint8_t *cgc_mask_d, int64_t tp53, int64_t n_gene,
+                        double *sums_d, void *stream);
+int dig_gene_burden_test(const double *mu_d, const double *sigma_d, const double *p_d, const double *pi_indel_d,
+                         const int64_t *obs_d, const int64_t *nsamp_d, int64_t n_gene, const double *sums_d,
+                         double n_syn, double scale_factor, double *out_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Synthetic genome generator (BASELINE.json configs are synthetic): position g is a pure
  * function of (seed, g); identical to orc_synth_genome in oracle/dig_oracle.c.
  */

@@ -300,3 +300,42 @@ def test_gene_transfer_multi_cohort_vs_oracle(gold_dev_genome, oracle):
     assert np.array_equal(o["R_SIZE"], want["R_SIZE"])
     assert np.array_equal(o["ELT_SIZE"], want["GENE_LENGTH"])
     assert np.array_equal(o["N_WIN"], want["N_WIN"])
+
+
+def test_fused_gene_test_kernels_golden():
+    """dig_gene_scale_sums + dig_gene_burden_test (13 NB tests + Fisher per gene in one launch) against the
+    reference's transfer_tools functions run on the same table (tests/golden/genes.npz)."""
+    import torch
+    from digdriver_b200 import kernels
+    z = golden("genes")
+    genes = list(z["pre_genes"])
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dtype=dt)
+    mu, sigma = t(z["pre_MU"]), t(z["pre_SIGMA"])
+    P = t(np.stack([z["pre_Pi_SYN"], z["pre_Pi_MIS"], z["pre_Pi_NONS"], z["pre_Pi_SPL"]], axis=1))
+    pi_indel = t(z["pre_Pi_INDEL"])
+    obs = t(np.stack([z["out_OBS_" + c] for c in ("SYN", "MIS", "NONS", "SPL", "INDEL")], axis=1), torch.int64)
+    nsamp = t(np.stack([z["out_N_SAMP_" + c] for c in ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN", "INDEL")], axis=1),
+              torch.int64)
+    cgc = np.array([g in ("TP53", "KRAS", "PIK3CA", "BRAF", "PTEN") for g in genes])
+    sums = kernels.gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc, genes.index("TP53"))
+    s = sums.cpu().numpy()
+    keep = np.array([g != "TP53" for g in genes])
+    np.testing.assert_allclose(s[0], (z["pre_MU"][keep] * z["pre_Pi_SYN"][keep]).sum(), rtol=1e-13)
+    np.testing.assert_allclose(s[1], (z["pre_Pi_INDEL"] * z["pre_ALPHA_INDEL"] * z["pre_THETA_INDEL"])[~cgc].sum(), rtol=1e-13)
+    assert s[2] == z["out_OBS_INDEL"][~cgc].sum()
+    out = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, 0.0, scale_factor=float(z["cj"])).cpu().numpy()
+    res = dict(zip(kernels.GENE_OUT_ROWS, out))
+    for name, got in res.items():
+        key = "out_" + name
+        if key not in z.files:
+            continue
+        if name.startswith("PVAL_"):
+            assert_pvals_close(got, z[key])
+        else:
+            np.testing.assert_allclose(got, z[key], rtol=1e-12, err_msg=name)
+    np.testing.assert_allclose(res["ALPHA"], z["pre_ALPHA"], rtol=0)
+    np.testing.assert_allclose(res["Pi_TRUNC"], z["pre_Pi_TRUNC"], rtol=0)
+    np.testing.assert_allclose(res["Pi_NONSYN"], z["pre_Pi_NONSYN"], rtol=1e-15)
+    # scale by expectation: cj = n_syn / sums[0]
+    out2 = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, 1234.0).cpu().numpy()
+    np.testing.assert_allclose(out2[22], z["pre_THETA"] * (1234.0 / s[0]), rtol=1e-14)
