@@ -209,37 +209,49 @@ class DeviceInputs:
         self.totals3 = torch.zeros(64, dtype=torch.int64, device=device)
 
 
-def hot_path_step(dg, di, d, dist_ctx, ev=None):
-    """One pass of the whole path on device-resident inputs.  Returns the per-gene result dict."""
-    import torch
-    from digdriver_b200 import kernels, pipeline
-    from digdriver_b200.pipeline import GeneTable
-    dev = dg.device
-    # 1. context maps + genome totals (K2)
+def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
+    """Context maps + genome totals (K2) for windows [lo, hi): pentanucleotide then trinucleotide."""
+    from digdriver_b200 import kernels
+    hi = di.win_chrom.numel() if hi is None else hi
+    if zero:
+        di.totals5.zero_()
+        di.totals3.zero_()
     if ev is not None:
         ev[0].record()
-    pipeline.scan_windows(dg, di.win_chrom, di.win_start, di.win_end, 2, 2, out=di.counts5, totals=di.totals5)
+    kernels.count_contexts(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi], 2, 2,
+                           out=di.counts5[lo:hi], totals=di.totals5)
     if ev is not None:
         ev[1].record()
-    pipeline.scan_windows(dg, di.win_chrom, di.win_start, di.win_end, 1, 1, out=di.counts3, totals=di.totals3)
-    # 2. sequence model (K3 + substitution histogram); totals and counts are all-reduced across shards
+    kernels.count_contexts(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi], 1, 1,
+                           out=di.counts3[lo:hi], totals=di.totals3)
+
+
+def test_stage(dg, di, d, dist_ctx):
+    """Sequence model (K3), gene pretrain (K6), observed counts (K5), burden test (K7)."""
+    import torch
+    from digdriver_b200 import kernels, pipeline
+    dev = dg.device
     ctx = kernels.mutation_contexts(dg, di.m_chrom, di.m_pos, di.m_ref, 1, 1)
     sub = kernels.substitution_counts(ctx, di.m_alt, 1, 1)
     if dist_ctx is not None:
+        # genome-wide totals and substitution counts are cohort-wide quantities: all-reduce across shards
         buf = torch.cat([di.totals5, di.totals3, sub])
         dist_ctx.all_reduce_sum(buf)
         tot3, sub = buf[1024:1088], buf[1088:]
     else:
         tot3 = di.totals3
     d_pr = kernels.sequence_freq(sub.contiguous(), tot3.contiguous())
-    # 3. gene pretrain (K6), observed counts (K5), burden test (K7)
     pre = kernels.element_transfer(di.g_chrom, di.g_strand, di.g_ptr, di.g_bs, di.g_be, WINDOW, di.wmap_off,
                                    di.wmap, di.counts3, di.y_pred, di.std, di.y_true, di.flag, d_pr,
                                    L_elt=di.L, device=dev, max_span=di.max_span)
     obs, nsamp = kernels.tabulate_genes(di.m_gene, di.m_sample, di.m_cls, N_GENES, device=dev)
-    n_syn = d["n_syn"]
-    res = pipeline.gene_burden_test(pre, obs, nsamp, n_syn, collectives=dist_ctx)
-    return res
+    return pipeline.gene_burden_test(pre, obs, nsamp, d["n_syn"], collectives=dist_ctx)
+
+
+def hot_path_step(dg, di, d, dist_ctx, ev=None):
+    """One pass of the whole path on device-resident inputs.  Returns the per-gene result dict."""
+    scan_stage(dg, di, ev)
+    return test_stage(dg, di, d, dist_ctx)
 
 
 def gather_results(coll, t):
@@ -274,51 +286,67 @@ class HostPath:
         self.host_in["flag"] = pin(d["flag"].astype(np.uint8))
         self.host_in["wins"] = pin(d["wins"])
         self.host_out = torch.empty((14, N_GENES), dtype=torch.float64, pin_memory=True)
+        self.host_tot = torch.empty(1024 + 64, dtype=torch.int64, pin_memory=True)
         self.copy_stream = torch.cuda.Stream(device)
+        self.out_stream = torch.cuda.Stream(device)
         self.h2d_bytes = n + sum(v.numel() * v.element_size() for v in self.host_in.values())
         self.d2h_bytes = (self.host_counts5.numel() + self.host_counts3.numel()) * 4 + self.host_out.numel() * 8 + \
             (1024 + 64) * 8
 
     def step(self, di):
+        """H2D, pack, scan and D2H are pipelined per chromosome on three streams: while chromosome c is being
+        scanned, chromosome c+1 is on its way in and the count rows of chromosome c-1 are on their way out."""
         import torch
-        from digdriver_b200 import _lib, kernels, pipeline
+        from digdriver_b200 import _lib, pipeline
         dg, dev, d = self.dg, self.device, self.d
         main = torch.cuda.current_stream(dev)
-        # genome: chromosome by chromosome on the copy stream, packed on the main stream as it lands
         bounds = list(dg.chrom_off) + [dg.n_bases]
+        wins = d["wins"]
+        wlo = np.searchsorted(wins[:, 0], np.arange(len(dg.chrom_off)), side="left")
+        whi = np.searchsorted(wins[:, 0], np.arange(len(dg.chrom_off)), side="right")
+        self.copy_stream.wait_stream(main)
+        self.out_stream.wait_stream(main)
+        # small tables first (they are needed only by the test stage)
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_stream(main)
-            evs = []
-            for a, b in zip(bounds[:-1], bounds[1:]):
+            t = {k: v.to(dev, non_blocking=True) for k, v in self.host_in.items()}
+            ev_tables = torch.cuda.Event()
+            ev_tables.record(self.copy_stream)
+        main.wait_event(ev_tables)
+        w = t["wins"]
+        di.win_chrom, di.win_start, di.win_end = w[:, 0].to(torch.int32), w[:, 1].contiguous(), w[:, 2].contiguous()
+        di.totals5.zero_()
+        di.totals3.zero_()
+        for c, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            with torch.cuda.stream(self.copy_stream):
                 self.dev_ascii[a:b].copy_(self.host_ascii[a:b], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(self.copy_stream)
-                evs.append(e)
-        for (a, b), e in zip(zip(bounds[:-1], bounds[1:]), evs):
-            main.wait_event(e)
+                e_in = torch.cuda.Event()
+                e_in.record(self.copy_stream)
+            main.wait_event(e_in)
             _lib.call("dig_pack_genome", self.dev_ascii.data_ptr() + int(a), int(b - a),
                       dg.packed2.data_ptr() + int(a) // 16 * 4, dg.nmask.data_ptr() + int(a) // 32 * 4, None,
                       main.cuda_stream)
-        # small tables
-        t = {k: v.to(dev, non_blocking=True) for k, v in self.host_in.items()}
-        wins = t["wins"]
-        di.win_chrom, di.win_start, di.win_end = wins[:, 0].to(torch.int32), wins[:, 1].contiguous(), wins[:, 2].contiguous()
+            lo, hi = int(wlo[c]), int(whi[c])
+            if hi > lo:
+                scan_stage(dg, di, None, lo, hi, zero=False)
+                e_scan = torch.cuda.Event()
+                e_scan.record(main)
+                with torch.cuda.stream(self.out_stream):
+                    self.out_stream.wait_event(e_scan)
+                    self.host_counts5[lo:hi].copy_(di.counts5[lo:hi], non_blocking=True)
+                    self.host_counts3[lo:hi].copy_(di.counts3[lo:hi], non_blocking=True)
         di.y_pred, di.std, di.y_true, di.flag = t["y_pred"], t["std"], t["y_true"], t["flag"]
         di.g_chrom, di.g_strand, di.g_ptr, di.g_bs, di.g_be, di.L = (t[k] for k in ("g_chrom", "g_strand", "g_ptr",
                                                                                     "g_bs", "g_be", "L"))
         di.m_chrom, di.m_pos, di.m_ref, di.m_alt, di.m_gene, di.m_cls, di.m_sample = (
             t[k] for k in ("m_chrom", "m_pos", "m_ref", "m_alt", "m_gene", "m_cls", "m_sample"))
-        res = hot_path_step(dg, di, d, None)
-        # results back to the host
-        self.host_counts5.copy_(di.counts5, non_blocking=True)
-        self.host_counts3.copy_(di.counts3, non_blocking=True)
+        res = test_stage(dg, di, d, None)
         cols = [res["PVAL_%s_BURDEN" % c] for c in pipeline.GENE_CLASSES] + \
                [res["PVAL_%s_BURDEN_SAMPLE" % c] for c in pipeline.GENE_CLASSES] + \
                [res["PVAL_INDEL_BURDEN"], res["PVAL_MUT_BURDEN"]]
         self.host_out.copy_(torch.stack(cols), non_blocking=True)
-        tot = torch.cat([di.totals5, di.totals3]).cpu()
+        self.host_tot.copy_(torch.cat([di.totals5, di.totals3]), non_blocking=True)
         torch.cuda.synchronize(dev)
-        return tot
+        return self.host_tot
 
 
 # ------------------------------------------------------------------------------------------------

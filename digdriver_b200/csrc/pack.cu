@@ -24,53 +24,66 @@ __device__ __forceinline__ void convert4(uint32_t w, uint32_t &codes8, uint32_t 
     other += __popc(~(ok | isn) & 0x01010101u);
 }
 
+constexpr int PACK_UNROLL = 4;     // independent 128-bit loads in flight per thread
+
+__device__ __forceinline__ void load_group(const uint8_t *__restrict__ ascii, int64_t n, int64_t gidx, int aligned,
+                                           uint32_t (&w)[4])
+{
+    const int64_t b0 = gidx << 4;
+    if (aligned && b0 + 16 <= n) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(ascii + b0));      // streaming: read once
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int64_t g = b0 + q * 4 + b;
+                const uint32_t c = g < n ? ascii[g] : (uint32_t)'N';
+                x |= c << (8 * b);
+            }
+            w[q] = x;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, int64_t n,
                                                    uint32_t *__restrict__ packed2, uint32_t *__restrict__ nmask,
                                                    unsigned long long *n_other, int64_t n_groups, int aligned)
 {
-    // n_groups is even; group gidx covers bases [16*gidx, 16*gidx+16)
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    uint32_t other = 0;
+    // n_groups is even; group gidx covers bases [16*gidx, 16*gidx+16).  A warp takes PACK_UNROLL runs of 32
+    // consecutive groups per iteration; the loop condition is warp-uniform so the pair shuffle sees a full warp.
     const int lane = threadIdx.x & 31;
-    // the loop condition is warp-uniform so that the pair shuffle below always sees a full warp
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n_groups; base += stride) {
-        const int64_t gidx = base + lane;
-        const bool live = gidx < n_groups;
-        const int64_t b0 = gidx << 4;
-        uint32_t w[4];
-        if (aligned && b0 + 16 <= n) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ascii + b0));
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else {
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t other = 0;
+    for (int64_t base = warp_id * (32 * PACK_UNROLL); base < n_groups; base += n_warps * (32 * PACK_UNROLL)) {
+        uint32_t w[PACK_UNROLL][4];
+#pragma unroll
+        for (int j = 0; j < PACK_UNROLL; ++j) load_group(ascii, n, base + j * 32 + lane, aligned, w[j]);
+#pragma unroll
+        for (int j = 0; j < PACK_UNROLL; ++j) {
+            const int64_t gidx = base + j * 32 + lane;
+            const bool live = gidx < n_groups;
+            uint32_t word = 0, n16 = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                uint32_t x = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int64_t g = b0 + q * 4 + b;
-                    const uint32_t c = g < n ? ascii[g] : (uint32_t)'N';
-                    x |= c << (8 * b);
-                }
-                w[q] = x;
+                uint32_t c8, n4;
+                convert4(w[j][q], c8, n4, other);
+                word |= c8 << (24 - 8 * q);
+                n16 |= n4 << (12 - 4 * q);
             }
+            // positions beyond n were fed as 'N': they are flagged in the mask and do not count as "other"
+            if (live) __stcs(packed2 + gidx, word);
+            const uint32_t peer = __shfl_xor_sync(0xffffffffu, n16, 1);
+            if (live && (gidx & 1) == 0) __stcs(nmask + (gidx >> 1), (n16 << 16) | peer);
         }
-        uint32_t word = 0, n16 = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t c8, n4;
-            convert4(w[q], c8, n4, other);
-            word |= c8 << (24 - 8 * q);
-            n16 |= n4 << (12 - 4 * q);
-        }
-        // positions beyond n were fed as 'N': they are flagged in the mask and do not count as "other"
-        if (live) packed2[gidx] = word;
-        const uint32_t peer = __shfl_xor_sync(0xffffffffu, n16, 1);
-        if (live && (gidx & 1) == 0) nmask[gidx >> 1] = (n16 << 16) | peer;
     }
     if (n_other) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) other += __shfl_xor_sync(0xffffffffu, other, o);
-        if ((threadIdx.x & 31) == 0 && other) atomicAdd(n_other, (unsigned long long)other);
+        if (lane == 0 && other) atomicAdd(n_other, (unsigned long long)other);
     }
 }
 
@@ -90,8 +103,8 @@ int dig_pack_genome(const uint8_t *ascii_d, int64_t n_bases, uint32_t *packed2_d
     const int64_t n_groups = ((n_bases + 31) >> 5) << 1;      // two 16-base groups per N-mask word
     const int aligned = (reinterpret_cast<uintptr_t>(ascii_d) & 15u) == 0;
     const int threads = 256;
-    int64_t blocks = (n_groups + threads - 1) / threads;
-    const int64_t cap = (int64_t)dig::sm_count() * 16;
+    int64_t blocks = (n_groups + threads * PACK_UNROLL - 1) / (threads * PACK_UNROLL);
+    const int64_t cap = (int64_t)dig::sm_count() * 8;
     if (blocks > cap) blocks = cap;
     pack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(ascii_d, n_bases, packed2_d, nmask_d,
                                                                         n_other_d, n_groups, aligned);
