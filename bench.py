@@ -39,6 +39,7 @@ N_GENES = 20_000
 N_MUT = 1_000_000
 N_SAMPLES = 200
 B_PER_BASE_K1024 = 0.25 + 0.125 + 4.0 * 1024 / WINDOW      # 0.7846 B/base
+B_PER_BASE_FUSED = 0.25 + 0.125 + 4.0 * (1024 + 64) / WINDOW  # both tables written by one pass: 0.8102
 B_PER_BASE_K64 = 0.25 + 0.125 + 4.0 * 64 / WINDOW
 
 
@@ -210,7 +211,8 @@ class DeviceInputs:
 
 
 def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
-    """Context maps + genome totals (K2) for windows [lo, hi): pentanucleotide then trinucleotide."""
+    """Context maps + genome totals (K2) for windows [lo, hi): pentanucleotide and trinucleotide tables in one
+    fused pass (dig_count_contexts_fused53)."""
     from digdriver_b200 import kernels
     hi = di.win_chrom.numel() if hi is None else hi
     if zero:
@@ -218,12 +220,11 @@ def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
         di.totals3.zero_()
     if ev is not None:
         ev[0].record()
-    kernels.count_contexts(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi], 2, 2,
-                           out=di.counts5[lo:hi], totals=di.totals5)
+    kernels.count_contexts_fused53(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi],
+                                   out5=di.counts5[lo:hi], out3=di.counts3[lo:hi], totals5=di.totals5,
+                                   totals3=di.totals3)
     if ev is not None:
         ev[1].record()
-    kernels.count_contexts(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi], 1, 1,
-                           out=di.counts3[lo:hi], totals=di.totals3)
 
 
 def test_stage(dg, di, d, dist_ctx):
@@ -544,11 +545,14 @@ def main():
         peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = n_scanned * B_PER_BASE_K1024 / (k5_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "scan_sym_kernel<2> (pentanucleotide window scan, K=1024)",
+    achieved = n_scanned * B_PER_BASE_FUSED / (k5_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "scan_fused53_kernel (pentanucleotide K=1024 + trinucleotide K=64 window "
+                                          "tables and genome totals in one pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": which, "kernel_ms": k5_ms,
-                "algorithmic_bytes_per_base": B_PER_BASE_K1024, "share_of_step": k5_ms / ms_per_step}
+                "algorithmic_bytes_per_base": B_PER_BASE_FUSED,
+                "note": "HBM is the roofline the contract asks for; ncu shows the kernel is bound by the shared-memory "
+                        "atomic data pipe (96 % busy), see DESIGN.md section 4", "share_of_step": k5_ms / ms_per_step}
 
     if rank != 0:
         if dist_ctx is not None:

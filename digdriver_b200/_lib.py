@@ -25,6 +25,7 @@ SIGNATURES = {
     "dig_nmask_words": (_I64, [_I64]),
     "dig_pack_genome": (_I, [_P, _I64, _P, _P, _P, _P]),
     "dig_count_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P]),
+    "dig_count_contexts_fused53": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "dig_synth_genome": (_I, [_P, _I64, _I64, _U64, _I, _P]),
     "dig_mutation_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P]),
     "dig_substitution_counts": (_I, [_P, _P, _I64, _I, _I, _P, _P]),
@@ -47,7 +48,7 @@ _lib = None
 # kernels launched per successful call (memsets not counted); summed into `launch_count` so that
 # bench.py can report how many of OUR kernels ran inside a timed region
 KERNELS_PER_CALL = {
-    "dig_pack_genome": 1, "dig_count_contexts": 1, "dig_synth_genome": 1, "dig_mutation_contexts": 1,
+    "dig_pack_genome": 1, "dig_count_contexts": 1, "dig_count_contexts_fused53": 1, "dig_synth_genome": 1, "dig_mutation_contexts": 1,
     "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2,
     "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
     "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,

@@ -49,6 +49,30 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
     return out, totals
 
 
+def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=False, out5=None, out3=None,
+                           totals5=None, totals3=None, stream=None):
+    """K2 fused: pentanucleotide and trinucleotide tables (+ totals) of the same regions in one pass.
+    Returns (counts5 [n,1024], counts3 [n,64], totals5, totals3)."""
+    dev = genome.device
+    rc = _dev(reg_chrom, torch.int32, dev)
+    rs = _dev(reg_start, torch.int64, dev)
+    re = _dev(reg_end, torch.int64, dev)
+    n = rc.numel()
+    if out5 is None:
+        out5 = torch.empty((n, 1024), dtype=torch.int32, device=dev)
+    if out3 is None:
+        out3 = torch.empty((n, 64), dtype=torch.int32, device=dev)
+    if want_totals and totals5 is None:
+        totals5 = torch.zeros(1024, dtype=torch.int64, device=dev)
+        totals3 = torch.zeros(64, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_count_contexts_fused53", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
+                  genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),
+                  re.data_ptr(), n, out5.data_ptr(), out3.data_ptr(), _ptr(totals5), _ptr(totals3),
+                  _stream(dev, stream))
+    return out5, out3, totals5, totals3
+
+
 def mutation_contexts(genome, mut_chrom, mut_start, mut_ref, n_up=1, n_down=1, stream=None):
     """K3: context index per mutation row (-1 = dropped by the reference).  Rows grouped by chromosome."""
     dev = genome.device

@@ -79,6 +79,17 @@ int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64
                        const int8_t *reg_strand_d, int64_t n_reg, int n_up, int n_down,
                        int32_t *counts_d, unsigned long long *totals_d, void *stream);
 
+/* Pentanucleotide (n_up = n_down = 2) AND trinucleotide (1, 1) tables of the same regions in ONE pass: what
+ * two countGenomeContext runs of the reference produce (DigPreprocess.py:19-73 with --up/--down 2 and 1).  The
+ * trinucleotide row is the marginal of the pentanucleotide row plus the centres whose 3-mer is valid while
+ * their 5-mer is not; results are bit-identical to two dig_count_contexts calls.  counts5_d [n_reg, 1024],
+ * counts3_d [n_reg, 64] int32; totals5_d [1024] / totals3_d [64] uint64 are added to (both or neither).
+ */
+int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
+                               const int64_t *chrom_off_d, const int64_t *chrom_len_d,
+                               const int32_t *reg_chrom_d, const int64_t *reg_start_d, const int64_t *reg_end_d,
+                               int64_t n_reg, int32_t *counts5_d, int32_t *counts3_d,
+                               unsigned long long *totals5_d, unsigned long long *totals3_d, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * K3  mutation context lookup with REF check.

@@ -150,3 +150,55 @@ def test_scan_large_windows_totals_overflow_guard(dev, oracle, u):
             assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
     finally:
         hook(ctypes.c_uint(1 << 20))
+
+
+def test_fused_penta_tri_scan_matches_two_scans(dev, oracle, gold_dev_genome):
+    """dig_count_contexts_fused53: one pass giving both tables must equal the two separate scans bit for bit
+    (golden windows incl. START == 0 / chromosome-end / tiny windows, random ragged regions with N runs,
+    and a 51 Mb chromosome)."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.genome import Genome, DeviceGenome, tile_windows
+    z = golden("scan")
+    w = z["windows"][z["rows_2_2"]]
+    c5, c3, t5, t3 = kernels.count_contexts_fused53(gold_dev_genome, w[:, 0] - 1, w[:, 1], w[:, 2], want_totals=True)
+    assert np.array_equal(c5.cpu().numpy(), z["counts_2_2"])
+    rows3 = {tuple(r): i for i, r in enumerate(z["windows"][z["rows_1_1"]])}
+    want3 = z["counts_1_1"][[rows3[tuple(r)] for r in w]]
+    assert np.array_equal(c3.cpu().numpy(), want3)
+    assert np.array_equal(t5.cpu().numpy(), z["counts_2_2"].sum(axis=0)) and np.array_equal(t3.cpu().numpy(), want3.sum(axis=0))
+    # random regions on a genome with many short N runs and N exactly two bases from valid centres
+    rng = np.random.default_rng(99)
+    lens = [50_001, 64, 7, 33_000]
+    seqs = []
+    for L in lens:
+        s = rng.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), size=L)
+        for _ in range(max(1, L // 400)):
+            a = int(rng.integers(0, L))
+            s[a:a + int(rng.integers(1, 4))] = ord("N")
+        seqs.append(s)
+    dg = DeviceGenome.from_genome(Genome(["c%d" % i for i in range(len(lens))], seqs), dev)
+    n = 800
+    chrom = rng.integers(0, len(lens), n)
+    Lc = np.array(lens)[chrom]
+    start = (rng.random(n) * (Lc + 3)).astype(np.int64)
+    end = start + np.where(rng.random(n) < 0.3, rng.integers(0, 5, n), rng.integers(0, 4000, n))
+    start[::13] = 0
+    start = np.where((start > 0) & (start < 2), 2, start)
+    end = np.maximum(end, start)
+    c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, chrom, start, end, want_totals=True)
+    w5, _ = kernels.count_contexts(dg, chrom, start, end, 2, 2)
+    w3, _ = kernels.count_contexts(dg, chrom, start, end, 1, 1)
+    assert np.array_equal(c5.cpu().numpy(), w5.cpu().numpy())
+    bad = np.flatnonzero((c3.cpu().numpy() != w3.cpu().numpy()).any(axis=1))
+    assert bad.size == 0, (bad[:5], chrom[bad[:5]], start[bad[:5]], end[bad[:5]])
+    assert np.array_equal(t3.cpu().numpy(), w3.cpu().numpy().astype(np.int64).sum(axis=0))
+    # chr22-sized
+    lengths = np.array([51_000_000], dtype=np.int64)
+    dg = DeviceGenome.synthetic(["chr22"], lengths, seed=22, device=dev)
+    wins = tile_windows([0], lengths, 10_000)
+    c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, wins[:, 0], wins[:, 1], wins[:, 2], want_totals=True)
+    seq = oracle.synth_genome(0, int(lengths[0]), 22)
+    want5, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 2, 2)
+    want3, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 1, 1)
+    assert np.array_equal(c5.cpu().numpy(), want5) and np.array_equal(c3.cpu().numpy(), want3)
+    assert np.array_equal(t5.cpu().numpy(), want5.sum(axis=0)) and np.array_equal(t3.cpu().numpy(), want3.sum(axis=0))
