@@ -32,6 +32,7 @@ SIGNATURES = {
     "dig_count_hits": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "dig_tabulate_elements": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P,
                                    _I64, _I64, _I64, _P, _P, _P]),
+    "dig_site_counts": (_I, [_P, _P, _I64, _I64, _I, _P, _P]),
     "dig_tabulate_genes": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P]),
     "dig_element_transfer": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P,
                                   _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -49,7 +50,7 @@ _lib = None
 # bench.py can report how many of OUR kernels ran inside a timed region
 KERNELS_PER_CALL = {
     "dig_pack_genome": 1, "dig_count_contexts": 1, "dig_count_contexts_fused53": 1, "dig_synth_genome": 1, "dig_mutation_contexts": 1,
-    "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2,
+    "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2, "dig_site_counts": 1,
     "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
     "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
 }

@@ -174,6 +174,18 @@ __global__ void __launch_bounds__(256) gene_finalize_kernel(const unsigned long 
     }
 }
 
+// L[elt, sub] += 1 per site (preprocess_sites, sequence_tools.py:698-703)
+__global__ void __launch_bounds__(256) site_counts_kernel(const int32_t *__restrict__ elt, const int32_t *__restrict__ sub,
+                                                          int64_t n, int64_t n_elt, int n_sub,
+                                                          unsigned long long *__restrict__ L)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t e = elt[i], j = sub[i];
+        if (e >= 0 && e < n_elt && j >= 0 && j < n_sub) atomicAdd(L + (int64_t)e * n_sub + j, 1ull);
+    }
+}
+
 inline unsigned grid_for(int64_t n)
 {
     int64_t blocks = (n + 255) / 256;
@@ -262,6 +274,20 @@ int dig_tabulate_genes(const int32_t *mut_gene_d, const int32_t *mut_sample_d, c
     DIG_CHECK_LAUNCH();
     gene_finalize_kernel<<<grid_for(capacity), 256, 0, st>>>(tab_key_d, tab_cnt_d, capacity,
                                                              max_per_gene_per_sample, n_gene, obs_d, nsamp_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_site_counts(const int32_t *site_elt_d, const int32_t *site_sub_d, int64_t n_site, int64_t n_elt, int n_sub,
+                    unsigned long long *L_d, void *stream)
+{
+    DIG_CHECK_ARG(n_site >= 0 && n_elt >= 0 && n_sub > 0, "bad sizes");
+    DIG_CHECK_ARG(n_elt == 0 || L_d, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_elt) DIG_CUDA(cudaMemsetAsync(L_d, 0, (size_t)n_elt * n_sub * sizeof(unsigned long long), st));
+    if (n_site == 0 || n_elt == 0) return DIG_OK;
+    DIG_CHECK_ARG(site_elt_d && site_sub_d, "null pointer");
+    site_counts_kernel<<<grid_for(n_site), 256, 0, st>>>(site_elt_d, site_sub_d, n_site, n_elt, n_sub, L_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

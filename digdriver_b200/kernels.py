@@ -334,3 +334,14 @@ def gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, n_syn, scale_fact
                   obs.data_ptr(), nsamp.data_ptr(), E, sums.data_ptr(), float(n_syn),
                   float("nan") if scale_factor is None else float(scale_factor), out.data_ptr(), _stream(dev, stream))
     return out
+
+
+def site_counts(site_elt, site_sub, n_elt, n_sub=192, device="cuda:0", stream=None):
+    """L[elt, sub] = number of sites per (site-set, substitution): int64 [n_elt, n_sub] on the device."""
+    dev = torch.device(device)
+    se, ss = _dev(site_elt, torch.int32, dev), _dev(site_sub, torch.int32, dev)
+    out = torch.empty((max(n_elt, 1), n_sub), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_site_counts", se.data_ptr(), ss.data_ptr(), se.numel(), n_elt, n_sub, out.data_ptr(),
+                  _stream(dev, stream))
+    return out[:n_elt]

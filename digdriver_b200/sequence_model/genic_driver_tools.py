@@ -140,16 +140,20 @@ def nonc_model_parallel(f_pretrained, f_nonc_data, nonc_L_key, N_procs=1, indels
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     wkey = 'window_{}'.format(rm.window)
-    df_elts = data.read_table('{}/{}/elements'.format(wkey, nonc_L_key))
-    df_elts['BLOCK_STARTS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_STARTS]
-    df_elts['BLOCK_ENDS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_ENDS]
-    L_contexts = data.read_table('{}/{}/L_contexts'.format(wkey, nonc_L_key))
     win_idx = data.read_array('{}/full_window_si_index'.format(wkey))
     win_vals = data.read_array('{}/full_window_si_values'.format(wkey))
     # align the stored window counts to the region model's rows
     key = {tuple(r): i for i, r in enumerate(map(tuple, win_idx))}
     rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
-    return nonc_model_arrays(df_elts, L_contexts, rm, win_vals[rows].astype(np.int32), d_pr)
+    win_counts = win_vals[rows].astype(np.int32)
+    if data.has('{}/{}/sites'.format(wkey, nonc_L_key)):               # preprocess_element_model --f-sites
+        df_sites = data.read_table('{}/{}/sites'.format(wkey, nonc_L_key))
+        return sites_model_arrays(df_sites.reset_index(drop=True), rm, win_counts, d_pr)
+    df_elts = data.read_table('{}/{}/elements'.format(wkey, nonc_L_key))
+    df_elts['BLOCK_STARTS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_STARTS]
+    df_elts['BLOCK_ENDS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_ENDS]
+    L_contexts = data.read_table('{}/{}/L_contexts'.format(wkey, nonc_L_key))
+    return nonc_model_arrays(df_elts, L_contexts, rm, win_counts, d_pr)
 
 
 def genic_model_arrays(genes, region_model, win_counts64, d_pr):
@@ -195,3 +199,48 @@ def genic_model_parallel(f_pretrained_str, f_genic_str, N_procs=1, counts_key="w
     else:
         wc = _window_counts_for(rm, f_fasta)
     return genic_model_arrays(genes, rm, wc, d_pr)
+
+
+def sites_model_arrays(df_sites, region_model, win_counts64, d_pr):
+    """preprocess_sites (sequence_tools.py:647-711) + nonc_model (reference :300-431) for site sets.
+
+    df_sites: a sites file read with mutation_tools.read_mutation_file -- its SAMPLE column holds the site-set
+    name (ELT), MUT_TYPE / CONTEXT give each site's substitution, STRAND (optional) flips it.  Per set:
+    L[j] = number of sites with substitution j (K5's dig_site_counts), windows = overlaps of the sites' own
+    (START, END) intervals, strand = the set's first STRAND value.  Returns the pretrain DataFrame."""
+    from .sequence_tools import mk_trans_idx
+    df = df_sites.rename(columns={'SAMPLE': 'ELT'}) if 'ELT' not in df_sites.columns else df_sites
+    if 'STRAND' not in df.columns:
+        df = df.assign(STRAND='.')
+    sub_pos = {n: i for i, n in enumerate(mk_trans_idx(1, 1))}
+    elts, elt_id = np.unique(df.ELT.values.astype(str), return_inverse=True)
+    order = np.argsort(elt_id, kind="stable")
+    df = df.iloc[order]
+    elt_id = elt_id[order]
+    first = np.concatenate([[0], np.flatnonzero(np.diff(elt_id)) + 1])
+    strand = _strand_code(df.STRAND.values[first])                       # list(group['STRAND'])[0]  (:679)
+    minus = strand[elt_id] < 0
+    ctx = df.CONTEXT.astype(str).values
+    mut = df.MUT_TYPE.astype(str).values
+    sub = np.full(len(df), -1, dtype=np.int32)
+    for i, (m, c, neg) in enumerate(zip(mut, ctx, minus)):
+        if 'nan' in c or len(c) != 3 or len(m) != 3:
+            continue                                                      # 'nan' contexts are skipped (:700-701)
+        name = c + '>' + c[0] + m[2] + c[2]
+        if neg:                                                           # strand flips the substitution (:681-683)
+            name = reverse_complement(c) + '>' + reverse_complement(c[0] + m[2] + c[2])
+        sub[i] = sub_pos.get(name, -1)
+    E = len(elts)
+    L = kernels.site_counts(elt_id, sub, E, 192, device=torch.device("cuda", torch.cuda.current_device()))
+    ptr = np.concatenate([first, [len(df)]]).astype(np.int64)
+    chrom = df.CHROM.values[first].astype(np.int64)
+    res = transfer_elements(region_model, win_counts64, d_pr, chrom, strand, ptr, df.START.values.astype(np.int64),
+                            df.END.values.astype(np.int64), L_elt=L.to(torch.float64).reshape(E, 192, 1))
+    Lh = L.cpu().numpy()
+    elt_size = (Lh.sum(axis=1) / 3).astype(np.int64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_indel = elt_size / res["R_SIZE"].astype(np.float64)
+    return pd.DataFrame({
+        'ELT': elts, 'ELT_SIZE': elt_size, 'FLAG': res["FLAG"], 'R_SIZE': res["R_SIZE"], 'R_OBS': res["R_OBS"],
+        'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"], 'MU_INDEL': res["MU"],
+        'SIGMA_INDEL': res["SIGMA"], 'P_SUM': res["P"][:, 0], 'P_INDEL': p_indel})

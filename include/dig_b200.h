@@ -150,6 +150,13 @@ int dig_tabulate_elements(const int64_t *blk_kstart_d, const int64_t *blk_kend_d
                           int64_t max_per_elt_per_sample, int64_t n_elt, int64_t *obs_d, int32_t *status_d,
                           void *stream);
 
+/* Site sets (preprocess_sites, sequence_tools.py:692-703): L_d [n_elt, n_sub] uint64 (overwritten),
+ * L[elt, sub] = number of sites of site-set `elt` whose substitution index is `sub` (negative / out-of-range
+ * ids are skipped, e.g. sites whose context is 'nan').
+ */
+int dig_site_counts(const int32_t *site_elt_d, const int32_t *site_sub_d, int64_t n_site, int64_t n_elt, int n_sub,
+                    unsigned long long *L_d, void *stream);
+
 /* Gene flavour: counts keyed by the file's GENE / ANNOT columns.
  * Replaces: mutations_per_gene (mutation_tools.py:329-361) and the distinct-sample counts of
  * transfer_gene_model (transfer_tools.py:235-265).

@@ -91,16 +91,18 @@ def preprocess_nonc_contexts(args):
     """Reference DigPreprocess.py:129-144 for --f-bed: block context counts (K4) + element block tables."""
     assert args.f_sites or args.f_element_bed, \
         "ERROR: need to pass in a f_sites file or a elements file for preprocessing"
+    st = storage.Store(args.f_element_data, "a")
+    wkey = 'window_{}'.format(args.window)
     if args.f_sites:
-        raise NotImplementedError("sites preprocessing is driven through transfer_tools.run_sites_region_model")
+        print("preprocessing sites data")
+        st.write_table('{}/{}/sites'.format(wkey, args.save_key), mutation_tools.read_mutation_file(args.f_sites))
+        return
     print("Preprocessing elements")
     L = sequence_tools.precount_region_contexts_parallel(args.f_element_bed, args.f_fasta, args.N_procs, args.window,
                                                          args.use_sub_elts)
     df_elts = mutation_tools.bed12_boundaries(args.f_element_bed)
     df_elts['BLOCK_STARTS'] = [','.join(map(str, b)) for b in df_elts.BLOCK_STARTS]
     df_elts['BLOCK_ENDS'] = [','.join(map(str, b)) for b in df_elts.BLOCK_ENDS]
-    st = storage.Store(args.f_element_data, "a")
-    wkey = 'window_{}'.format(args.window)
     st.write_table('{}/{}/elements'.format(wkey, args.save_key), df_elts.reset_index(drop=True))
     st.write_table('{}/{}/L_contexts'.format(wkey, args.save_key), L)
 
