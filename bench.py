@@ -549,7 +549,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": "scan_fused53_kernel (pentanucleotide K=1024 + trinucleotide K=64 window "
                                           "tables and genome totals in one pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": which, "kernel_ms": k5_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default size, from the committed
+                # ncu --set full capture (profiles/r01_scan_fused53_summary.txt): 1.178 GB + 1.298 GB
+                "traffic": 2.4755e9 if abs(args.bases - 3.1e9) < 1 else None,
+                "algorithmic_bytes": n_scanned * B_PER_BASE_FUSED,
+                "peak_source": which, "kernel_ms": k5_ms,
                 "algorithmic_bytes_per_base": B_PER_BASE_FUSED,
                 "note": "HBM is the roofline the contract asks for; ncu shows the kernel is bound by the shared-memory "
                         "atomic data pipe (96 % busy), see DESIGN.md section 4", "share_of_step": k5_ms / ms_per_step}
