@@ -22,127 +22,14 @@
 // (DigPreprocess.py:59) are accumulated per CTA in shared memory and flushed once.
 //
 // HBM traffic per base: 0.25 B bases + 0.125 B mask + 4K/W B counts.
-#include "dig_common.cuh"
+#include "scan_common.cuh"
+
+using namespace digscan;
 
 namespace {
 
-constexpr int WARPS_PER_BLOCK = 8;
-constexpr int THREADS = WARPS_PER_BLOCK * 32;
-
-// kilobases a CTA may fold into its int32 shared-memory totals before it switches to global atomics
-unsigned int g_tot_limit_kb = 1u << 20;
-
-// reverse-complement of a klen-base k-mer index (5' base most significant)
-__device__ __forceinline__ uint32_t revcomp_key(uint32_t key, int klen)
-{
-    uint32_t x = __brev(key);                                    // reverses pairs AND bits inside pairs
-    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);     // undo the swap inside each pair
-    x >>= (32 - 2 * klen);
-    return x ^ ((1u << (2 * klen)) - 1u);                        // complement: b -> 3 - b
-}
-
-struct RegionSpan {
-    int64_t gs, ge;   // global centre range [gs, ge)
-};
-
-// Centre range of region r exactly as the reference walks it (see dig_b200.h); u/d are the
-// number of bases taken to the left/right of the centre on the PLUS strand.
-__device__ __forceinline__ RegionSpan region_span(const int64_t *__restrict__ chrom_off,
-                                                  const int64_t *__restrict__ chrom_len,
-                                                  const int32_t *__restrict__ reg_chrom,
-                                                  const int64_t *__restrict__ reg_start,
-                                                  const int64_t *__restrict__ reg_end, int64_t r, int n_up,
-                                                  int n_down, int u, int d)
-{
-    const int32_t c = __ldg(reg_chrom + r);
-    const int64_t L = __ldg(chrom_len + c);
-    const int64_t off = __ldg(chrom_off + c);
-    int64_t s = __ldg(reg_start + r);
-    const int64_t e = __ldg(reg_end + r);
-    if (s < n_up) s = n_up;                 // START == 0 -> n_up (sequence_tools.py:25-26)
-    int64_t f0 = s - n_up;                  // fetched string [f0, f1)
-    int64_t f1 = e + n_down;
-    if (f1 > L) f1 = L;                     // faidx clips at the chromosome end
-    if (f0 > L) f0 = L;
-    RegionSpan sp;
-    sp.gs = off + f0 + u;
-    sp.ge = off + f1 - d;
-    if (sp.ge < sp.gs) sp.ge = sp.gs;
-    return sp;
-}
-
-__device__ __forceinline__ void smem_inc(uint32_t addr)
-{
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
-}
-
-// (k-mer index of position I) << SCALE, from the four words [a|b0|b1|c] that cover bases
-// 32w-16 .. 32w+47 (MSB first).  One shift + one mask, all amounts compile-time.
-template <int U, int D, int I, int SCALE>
-__device__ __forceinline__ uint32_t scaled_key(uint32_t a, uint32_t b0, uint32_t b1, uint32_t c)
-{
-    constexpr int KLEN = U + D + 1;
-    constexpr uint32_t MASK = ((1u << (2 * KLEN)) - 1u) << SCALE;
-    constexpr int BO = 2 * (16 + I - U);        // bit offset from the MSB of [a|b0|b1|c]
-    constexpr int Q = BO >> 5;
-    constexpr int R = BO & 31;
-    const uint32_t hi = Q == 0 ? a : (Q == 1 ? b0 : b1);
-    const uint32_t lo = Q == 0 ? b0 : (Q == 1 ? b1 : c);
-    if constexpr (R + 2 * KLEN <= 32) {
-        constexpr int SH = 32 - R - 2 * KLEN;   // key = hi >> SH
-        if constexpr (SH >= SCALE) return (hi >> (SH - SCALE)) & MASK;
-        else return (hi << (SCALE - SH)) & MASK;
-    } else {
-        constexpr int S = 64 - R - 2 * KLEN;    // key = low32((hi:lo) >> S), 0 < S < 32
-        if constexpr (S >= SCALE) return __funnelshift_r(lo, hi, S - SCALE) & MASK;
-        else return (lo << (SCALE - S)) & MASK;
-    }
-}
-
-template <int U, int D, int I, int SCALE>
-struct Unroll {
-    static __device__ __forceinline__ void run(uint32_t base, uint32_t a, uint32_t b0, uint32_t b1, uint32_t c)
-    {
-        smem_inc(scaled_key<U, D, I, SCALE>(a, b0, b1, c) | base);
-        Unroll<U, D, I + 1, SCALE>::run(base, a, b0, b1, c);
-    }
-};
-template <int U, int D, int SCALE>
-struct Unroll<U, D, 32, SCALE> {
-    static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
-};
-
-// k-mer index of position `pos` (runtime) of the same four words
-template <int U, int D>
-__device__ __forceinline__ uint32_t runtime_key(uint32_t a, uint32_t b0, uint32_t b1, uint32_t c, int pos)
-{
-    constexpr int KLEN = U + D + 1;
-    const int bo = 2 * (16 + pos - U);
-    const int q = bo >> 5, r = bo & 31;
-    const uint32_t hi = q == 0 ? a : (q == 1 ? b0 : b1);
-    const uint32_t lo = q == 0 ? b0 : (q == 1 ? b1 : c);
-    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
-    return (uint32_t)(v >> (64 - r - 2 * KLEN)) & ((1u << (2 * KLEN)) - 1u);
-}
-
-struct WordLoad {
-    uint2 pw;
-    uint32_t nm;
-};
-
-// word `rel` of the current region (rel counts 32-base words from the region's first word)
-__device__ __forceinline__ WordLoad load_word(const uint2 *__restrict__ pv, const uint32_t *__restrict__ pn, int rel,
-                                              int avail)
-{
-    WordLoad x;
-    x.pw = make_uint2(0u, 0u);
-    x.nm = 0xFFFFFFFFu;
-    if (rel < avail) {
-        x.pw = __ldg(pv + rel);
-        x.nm = __ldg(pn + rel);
-    }
-    return x;
-}
+unsigned int g_tot_limit_kb = 1u << 20;   // kilobases a CTA may fold into int32 totals before it goes global
+int g_scan_variant = 0;   // 0 = hexamer-pair kernel for (2,2) plus-strand scans, 1 = per-base kernels only, 2 = hexamer, plain flush
 
 // ---------------------------------------------------------------------------------------
 // fast kernel: symmetric context (U == D).  PRIVATE selects the lane-private layout.
@@ -368,16 +255,6 @@ __global__ void __launch_bounds__(THREADS, PRIVATE ? 3 : 3) scan_sym_kernel(
 // chromosome, the last-but-one base): those are counted into a 64-bin correction histogram through
 // the cooperative path.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t range_mask(int lo, int hi)
-{
-    lo = lo < 0 ? 0 : lo;
-    hi = hi > 32 ? 32 : hi;
-    if (hi <= lo) return 0u;
-    const uint32_t from_lo = 0xFFFFFFFFu >> lo;                       // lo < 32 here
-    const uint32_t below_hi = hi >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
-    return from_lo & below_hi;
-}
-
 __global__ void __launch_bounds__(THREADS, 3) scan_fused53_kernel(
     const uint2 *__restrict__ p2v, const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask,
     int64_t n_words32, const int64_t *__restrict__ chrom_off, const int64_t *__restrict__ chrom_len,
@@ -638,6 +515,10 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
     DIG_CHECK_ARG((totals5_d == nullptr) == (totals3_d == nullptr), "pass both totals or neither");
     DIG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed2_d) & 7u) == 0 && (reinterpret_cast<uintptr_t>(counts5_d) & 15u) == 0,
                   "packed2_d must be 8-byte and counts5_d 16-byte aligned");
+    if (g_scan_variant != 1)
+        return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
+                               n_reg, counts5_d, counts3_d, totals5_d, totals3_d, g_tot_limit_kb, g_scan_variant == 2,
+                               (cudaStream_t)stream);
     const size_t smem = 1024 * 4 + 4096 + (size_t)WARPS_PER_BLOCK * 4096;
     static thread_local int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -656,6 +537,8 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
 
 // test hook (not part of the public header): lowers the int32-totals guard so tests can reach it
 extern "C" void dig_debug_set_totals_limit_kb(unsigned int kb) { g_tot_limit_kb = kb; }
+// test / A-B hook: 1 forces the per-base kernels (scan_sym_kernel, scan_fused53_kernel) for (2,2) scans
+extern "C" void dig_debug_set_scan_variant(int v) { g_scan_variant = v; }
 
 extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
                                   const int64_t *chrom_off_d, const int64_t *chrom_len_d,
@@ -672,6 +555,9 @@ extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nma
     DIG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed2_d) & 7u) == 0 && (reinterpret_cast<uintptr_t>(counts_d) & 15u) == 0,
                   "packed2_d must be 8-byte and counts_d 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && g_scan_variant != 1)
+        return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
+                               n_reg, counts_d, nullptr, totals_d, nullptr, g_tot_limit_kb, g_scan_variant == 2, st);
     if (n_up == n_down && n_up <= 2) {
         switch (n_up) {
         case 0:
