@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) gene_test_kernel(
     double scale_factor, double *__restrict__ out)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const double cj = isnan(scale_factor) ? n_syn / sums[0] : scale_factor;
+    const double cj = isnan(scale_factor) ? (isnan(n_syn) ? sums[3] : n_syn) / sums[0] : scale_factor;
     const double t_indel = sums[2] / sums[1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 13; i += stride) {
         const int64_t g = i / 13;

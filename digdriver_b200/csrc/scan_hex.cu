@@ -37,13 +37,11 @@ using namespace digscan;
 
 namespace {
 
-constexpr int HEX_WARPS = 8;
-constexpr int HEX_THREADS = HEX_WARPS * 32;
+// 8 warps x 2 CTAs per SM at 128 registers: 6 x 3 and 10 x 2 (96 registers, spills) measured 10-17 % slower
 constexpr uint32_t H6_BYTES = 8192u;     // 4096 x 16 bit, per warp, also its alignment
 constexpr uint32_t C5_BYTES = 2048u;     // 1024 x 16 bit single-pentanucleotide corrections
 constexpr uint32_t C3_BYTES = 256u;      // 64 x int32 trinucleotide corrections
 constexpr int CHUNK_ITERS = 96;          // 96 x 1024 bases between flushes (multiple of the 4-deep load ring)
-constexpr size_t HEX_SMEM = H6_BYTES + (size_t)HEX_WARPS * (H6_BYTES + C5_BYTES + C3_BYTES);
 
 __device__ __forceinline__ void smem_add(uint32_t addr, uint32_t val)
 {
@@ -171,7 +169,6 @@ struct HexRegion {
     int nw;                   // 32-base words touched (0 = nothing to scan)
     int avail;                // words that may be loaded (region + one halo word, clipped to the genome)
     int lo3, hi3, lo5, hi5;   // centre ranges relative to the first word: trinucleotide / pentanucleotide
-    unsigned int kb;          // kilobases, for the 32-bit totals guard
     WordLoad nxt, nx2, nx3, nx4;   // words lane, lane + 32, lane + 64, lane + 96 of the region, in flight
 };
 
@@ -222,7 +219,6 @@ __device__ __forceinline__ HexRegion hex_setup(const HexRaw raw, const uint2 *__
     g.hi3 = (int)(ge[1] - (w0 << 5));
     g.lo5 = (int)(gs[0] - (w0 << 5));
     g.hi5 = (int)(ge[0] - (w0 << 5));
-    g.kb = (unsigned int)((ge[o] - gs[o]) >> 10) + 1u;
     g.pv = p2v + w0;
     g.pn = nmask + w0;
     const int64_t left = n_words32 - w0;
@@ -235,8 +231,8 @@ __device__ __forceinline__ HexRegion hex_setup(const HexRaw raw, const uint2 *__
     return g;
 }
 
-template <bool TRI, bool TOT, bool EXCH>
-__global__ void __launch_bounds__(HEX_THREADS, 2) scan_hex_kernel(
+template <int HEX_WARPS, int MIN_CTAS, bool TRI, bool TOT, bool EXCH>
+__global__ void __launch_bounds__(HEX_WARPS * 32, MIN_CTAS) scan_hex_kernel(
     const uint2 *__restrict__ p2v, const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask,
     int64_t n_words32, const int64_t *__restrict__ chrom_off, const int64_t *__restrict__ chrom_len,
     const int32_t *__restrict__ reg_chrom, const int64_t *__restrict__ reg_start,
@@ -244,6 +240,7 @@ __global__ void __launch_bounds__(HEX_THREADS, 2) scan_hex_kernel(
     int32_t *__restrict__ counts3, unsigned long long *__restrict__ totals5,
     unsigned long long *__restrict__ totals3, unsigned int tot_limit_kb, uint32_t one)
 {
+    constexpr int HEX_THREADS = HEX_WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -285,11 +282,77 @@ __global__ void __launch_bounds__(HEX_THREADS, 2) scan_hex_kernel(
         if (more) raw_n = hex_load_raw(reg_chrom, reg_start, reg_end, r + nwarps);
         HexRegion gn;
         gn.nw = 0;
-        bool fetched = false;
-        const unsigned int kb = g.kb;
-        int acc[32];
+        int32_t *const row5 = counts5 + r * (int64_t)1024;
+        int32_t *const row3 = TRI ? counts3 + r * (int64_t)64 : nullptr;
+        // Folds one flushed chunk into rows r of both tables and into the register totals.  The 32 row values live
+        // in registers only from the flush to the store (not across the scan loop); a region longer than one chunk
+        // (98 304 bases) adds its later chunks onto the row it already stored.
+        auto emit = [&](const bool scanned, const bool singles, const bool first, const unsigned int kb) {
+            int acc[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0;
+            for (int i = 0; i < 32; ++i) acc[i] = 0;
+            if (scanned) hex_flush<EXCH>(h6, hist, c5, singles, lane, acc);
+            int tri[2] = {0, 0};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                // chunk 32 j + lane = x0 * 64 + (x1 x2 x3): its four values of x4 sum into trinucleotide bin (32 j + lane) & 63
+                tri[j & 1] += (acc[4 * j] + acc[4 * j + 1]) + (acc[4 * j + 2] + acc[4 * j + 3]);
+            if constexpr (TRI) {
+                if (scanned) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        tri[h] += c3[h * 32 + lane];
+                        c3[h * 32 + lane] = 0;
+                    }
+                    __syncwarp();
+                }
+            }
+            if constexpr (TOT) {
+                if (warp_kb + kb > tot_limit_kb || warp_kb + kb < warp_kb) {
+                    // the 32-bit register totals would no longer be safe: move them to the global uint64 totals now
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (tot5[i]) atomicAdd(totals5 + 4 * ((i >> 2) * 32 + lane) + (i & 3), (unsigned long long)tot5[i]);
+                        tot5[i] = 0u;
+                    }
+                    if constexpr (TRI) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (tot3[h]) atomicAdd(totals3 + h * 32 + lane, (unsigned long long)tot3[h]);
+                            tot3[h] = 0u;
+                        }
+                    }
+                    warp_kb = 0u;
+                }
+                warp_kb += kb;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tot5[i] += (unsigned int)acc[i];
+                tot3[0] += (unsigned int)tri[0];
+                tot3[1] += (unsigned int)tri[1];
+            }
+            int4 *out4 = reinterpret_cast<int4 *>(row5);
+            if (!first) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int4 v = out4[j * 32 + lane];
+                    acc[4 * j] += v.x;
+                    acc[4 * j + 1] += v.y;
+                    acc[4 * j + 2] += v.z;
+                    acc[4 * j + 3] += v.w;
+                }
+                if constexpr (TRI) {
+                    tri[0] += row3[lane];
+                    tri[1] += row3[32 + lane];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                __stcs(out4 + j * 32 + lane, make_int4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+            if constexpr (TRI) {
+                __stcs(row3 + lane, tri[0]);
+                __stcs(row3 + 32 + lane, tri[1]);
+            }
+        };
         if (g.nw > 0) {
             const int nw = g.nw, avail = g.avail;
             const int lo3 = g.lo3, hi3 = g.hi3, lo5 = g.lo5, hi5 = g.hi5;
@@ -360,56 +423,12 @@ __global__ void __launch_bounds__(HEX_THREADS, 2) scan_hex_kernel(
                     if (rel0 + 96 < c1) step(ring3, ring0, rel0 + 96);
                 }
                 __syncwarp();
-                if (c1 == nw && more) {
-                    gn = hex_setup<TRI>(raw_n, p2v, p2, nmask, n_words32, chrom_off, chrom_len, lane);
-                    fetched = true;
-                }
-                hex_flush<EXCH>(h6, hist, c5, singles, lane, acc);
+                if (c1 == nw && more) gn = hex_setup<TRI>(raw_n, p2v, p2, nmask, n_words32, chrom_off, chrom_len, lane);
+                emit(true, singles, c0 == 0, (unsigned int)((c1 - c0) >> 5) + 1u);
             }
-        }
-        if (more && !fetched) gn = hex_setup<TRI>(raw_n, p2v, p2, nmask, n_words32, chrom_off, chrom_len, lane);
-        // ---- write-out: rows r of both tables, register totals
-        int4 *out4 = reinterpret_cast<int4 *>(counts5 + r * (int64_t)1024);
-        int tri[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            // chunk 32 j + lane = x0 * 64 + (x1 x2 x3): its four values of x4 sum into trinucleotide bin (32 j + lane) & 63
-            __stcs(out4 + j * 32 + lane, make_int4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
-            tri[j & 1] += (acc[4 * j] + acc[4 * j + 1]) + (acc[4 * j + 2] + acc[4 * j + 3]);
-        }
-        if constexpr (TRI) {
-            int32_t *out3 = counts3 + r * (int64_t)64;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = h * 32 + lane;
-                tri[h] += c3[m];
-                c3[m] = 0;
-                __stcs(out3 + m, tri[h]);
-            }
-            __syncwarp();
-        }
-        if constexpr (TOT) {
-            if (warp_kb + kb > tot_limit_kb || warp_kb + kb < warp_kb) {
-                // the 32-bit register totals would no longer be safe: move them to the global uint64 totals now
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (tot5[i]) atomicAdd(totals5 + 4 * ((i >> 2) * 32 + lane) + (i & 3), (unsigned long long)tot5[i]);
-                    tot5[i] = 0u;
-                }
-                if constexpr (TRI) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (tot3[h]) atomicAdd(totals3 + h * 32 + lane, (unsigned long long)tot3[h]);
-                        tot3[h] = 0u;
-                    }
-                }
-                warp_kb = 0u;
-            }
-            warp_kb += kb;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) tot5[i] += (unsigned int)acc[i];
-            tot3[0] += (unsigned int)tri[0];
-            tot3[1] += (unsigned int)tri[1];
+        } else {
+            if (more) gn = hex_setup<TRI>(raw_n, p2v, p2, nmask, n_words32, chrom_off, chrom_len, lane);
+            emit(false, false, true, 1u);
         }
         g = gn;
     }
@@ -436,13 +455,15 @@ __global__ void __launch_bounds__(HEX_THREADS, 2) scan_hex_kernel(
     }
 }
 
-template <bool TRI, bool TOT, bool EXCH>
-int launch_hex(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
+template <int HEX_WARPS, int MIN_CTAS, bool TRI, bool TOT, bool EXCH>
+int launch_hex_cfg(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
                unsigned long long *totals3, unsigned int tot_limit_kb, cudaStream_t stream)
 {
-    auto kern = scan_hex_kernel<TRI, TOT, EXCH>;
+    constexpr int HEX_THREADS = HEX_WARPS * 32;
+    constexpr size_t HEX_SMEM = H6_BYTES + (size_t)HEX_WARPS * (H6_BYTES + C5_BYTES + C3_BYTES);
+    auto kern = scan_hex_kernel<HEX_WARPS, MIN_CTAS, TRI, TOT, EXCH>;
     static thread_local int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_SMEM));
@@ -458,6 +479,16 @@ int launch_hex(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const in
                                                               totals3, tot_limit_kb, 1u);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
+}
+
+template <bool TRI, bool TOT, bool EXCH>
+int launch_hex(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
+               const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
+               int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
+               unsigned long long *totals3, unsigned int tot_limit_kb, cudaStream_t stream)
+{
+    return launch_hex_cfg<8, 2, TRI, TOT, EXCH>(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end,
+                                                n_reg, counts5, counts3, totals5, totals3, tot_limit_kb, stream);
 }
 
 }  // namespace

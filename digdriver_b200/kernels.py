@@ -126,7 +126,12 @@ def _pow2_at_least(n):
     return c
 
 
-def _check_status(status, what):
+def _check_status(status, what, sink=None):
+    """Raises for a non-zero device status word.  Reading it is a host synchronisation; callers on a
+    stream-ordered hot path pass a list as `sink` and call check_deferred(sink) once at the end instead."""
+    if sink is not None:
+        sink.append((status, what))
+        return
     code = int(status.item())
     if code == 1:
         raise _lib.DigError("%s: hash table overflow" % what)
@@ -137,6 +142,13 @@ def _check_status(status, what):
         raise _lib.DigError("%s: element window span exceeds the shared-memory bitmap" % what)
     if code != 0:
         raise _lib.DigError("%s: status %d" % (what, code))
+
+
+def check_deferred(sink):
+    """Checks (and clears) the device status words collected through a `status_sink` list."""
+    pending, sink[:] = list(sink), []
+    for status, what in pending:
+        _check_status(status, what)
 
 
 def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_sample, mut_isindel,
@@ -178,7 +190,7 @@ def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_s
 
 
 def tabulate_genes(mut_gene, mut_sample, mut_class, n_gene, max_per_gene_per_sample=3 * 10 ** 9,
-                   device="cuda:0", stream=None):
+                   device="cuda:0", stream=None, status_sink=None):
     """K5 (genes): obs int64 [n_gene,5] (SYN, MIS, NONS, SPL, INDEL) and nsamp int64 [n_gene,7]
     (SYN, MIS, NONS, SPL, TRUNC, NONSYN, INDEL)."""
     dev = torch.device(device)
@@ -194,13 +206,13 @@ def tabulate_genes(mut_gene, mut_sample, mut_class, n_gene, max_per_gene_per_sam
         _lib.call("dig_tabulate_genes", mg.data_ptr(), ms.data_ptr(), mc.data_ptr(), n_mut, keys.data_ptr(),
                   cnt.data_ptr(), cap, int(min(max_per_gene_per_sample, 2 ** 62)), n_gene, obs.data_ptr(),
                   nsamp.data_ptr(), status.data_ptr(), _stream(dev, stream))
-        _check_status(status, "dig_tabulate_genes")
+        _check_status(status, "dig_tabulate_genes", status_sink)
     return obs[:n_gene], nsamp[:n_gene]
 
 
 def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window, win_map_off, win_map,
                      win_counts, y_pred, std, y_true, flag, d_pr, blk_counts=None, L_elt=None,
-                     device="cuda:0", stream=None, max_span=None):
+                     device="cuda:0", stream=None, max_span=None, status_sink=None):
     """K6.  Region-parameter arrays are [n_cohort, n_win] (1-D inputs are taken as one cohort), d_pr is
     [n_cohort, 192].  Returns a dict of device tensors (MU, SIGMA, R_OBS, FLAG: [n_cohort, n_elt];
     R_SIZE, ELT_SIZE, N_WIN: [n_elt]; P: [n_cohort, n_elt, n_col])."""
@@ -243,7 +255,7 @@ def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window,
                   out["MU"].data_ptr(), out["SIGMA"].data_ptr(), out["R_OBS"].data_ptr(), out["FLAG"].data_ptr(),
                   out["R_SIZE"].data_ptr(), out["ELT_SIZE"].data_ptr(), out["P"].data_ptr(),
                   out["N_WIN"].data_ptr(), status.data_ptr(), _stream(dev, stream))
-        _check_status(status, "dig_element_transfer")
+        _check_status(status, "dig_element_transfer", status_sink)
     return out
 
 
@@ -325,13 +337,14 @@ def gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc_mask=None, tp53=-1, stream=
 
 
 def gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, n_syn, scale_factor=None, stream=None):
-    """All 13 NB tests + Fisher per gene in one launch pair.  Returns float64 [27, E] (rows: GENE_OUT_ROWS)."""
+    """All 13 NB tests + Fisher per gene in one launch pair.  Returns float64 [27, E] (rows: GENE_OUT_ROWS).
+    n_syn=None: the synonymous count is sums[3] on the device (multi-GPU path, no host read)."""
     dev = mu.device
     E = mu.numel()
     out = torch.empty((len(GENE_OUT_ROWS), E), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dig_gene_burden_test", mu.data_ptr(), sigma.data_ptr(), P.data_ptr(), pi_indel.data_ptr(),
-                  obs.data_ptr(), nsamp.data_ptr(), E, sums.data_ptr(), float(n_syn),
+                  obs.data_ptr(), nsamp.data_ptr(), E, sums.data_ptr(), float("nan") if n_syn is None else float(n_syn),
                   float("nan") if scale_factor is None else float(scale_factor), out.data_ptr(), _stream(dev, stream))
     return out
 

@@ -74,10 +74,11 @@ def gene_burden_test(pre, obs, nsamp, n_syn_non_tp53, tp53=-1, cgc_mask=None, sc
     sums = kernels.gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc_mask, tp53)
     n_syn = float(n_syn_non_tp53)
     if collectives is not None and collectives.world > 1:
-        buf = torch.cat([sums, torch.tensor([n_syn], dtype=torch.float64, device=sums.device)])
-        collectives.all_reduce_sum(buf)
-        sums, n_syn_t = buf[:3].contiguous(), buf[3]
-        n_syn = float(n_syn_t)                                # one scalar read; only on the multi-GPU path
+        # sums[3] carries this shard's synonymous count; after the all-reduce the kernel reads the cohort-wide value
+        # from the device (no host read: the whole stage stays stream-ordered and CUDA-graph capturable)
+        sums = torch.cat([sums, torch.full((1,), n_syn, dtype=torch.float64, device=sums.device)])
+        collectives.all_reduce_sum(sums)
+        n_syn = None
     out = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, n_syn, scale_factor)
     res = {name: out[i] for i, name in enumerate(kernels.GENE_OUT_ROWS)}
     o = obs.to(torch.float64)

@@ -75,14 +75,16 @@ class Collectives:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t
 
-    def gather_rows(self, t):
-        """Concatenate per-rank row blocks (possibly of different length) on rank 0; None elsewhere."""
+    def gather_rows(self, t, sizes=None):
+        """Concatenate per-rank row blocks (possibly of different length) on rank 0; None elsewhere.
+        `sizes` (rows per rank), when the caller knows them, skips the size exchange and its host reads."""
         if not self.on or self.world == 1:
             return t
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        sizes = [torch.zeros_like(n) for _ in range(self.world)]
-        dist.all_gather(sizes, n)
-        sizes = [int(s.item()) for s in sizes]
+        if sizes is None:
+            n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+            sizes = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(sizes, n)
+            sizes = [int(s.item()) for s in sizes]
         m = max(sizes)
         pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         pad[: t.shape[0]] = t

@@ -202,3 +202,62 @@ def test_fused_penta_tri_scan_matches_two_scans(dev, oracle, gold_dev_genome):
     want3, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 1, 1)
     assert np.array_equal(c5.cpu().numpy(), want5) and np.array_equal(c3.cpu().numpy(), want3)
     assert np.array_equal(t5.cpu().numpy(), want5.sum(axis=0)) and np.array_equal(t3.cpu().numpy(), want3.sum(axis=0))
+
+
+def test_hexamer_pair_scan_adversarial(dev, oracle):
+    """scan_hex.cu counts pentanucleotides through hexamer pairs at even positions; this drives the parts
+    that differ from the per-base kernels: pairs with a single valid centre (N every few bases, odd
+    region boundaries, odd chromosome ends), 16-bit packed counters on homopolymers longer than one
+    flush interval (98 304 bases), regions shorter than one pair, and the register totals."""
+    import ctypes
+    from digdriver_b200 import kernels, _lib
+    from digdriver_b200.genome import Genome, DeviceGenome
+    rng = np.random.default_rng(2024)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    period6 = np.tile(np.frombuffer(b"AAAAAN", dtype=np.uint8), 5000)           # one valid 5-mer per 6 bases
+    period7 = np.tile(np.frombuffer(b"ACGTACN", dtype=np.uint8), 4001)
+    homo = np.full(300_007, ord("A"), dtype=np.uint8)                            # 3 flush intervals of one hexamer
+    homo[150_000] = ord("N")
+    mixed = rng.choice(acgt, size=250_003)
+    mixed[rng.integers(0, mixed.size, 4000)] = ord("N")                          # isolated N: singles everywhere
+    seqs = [period6, period7, homo, mixed, rng.choice(acgt, size=7)]
+    dg = DeviceGenome.from_genome(Genome(["c%d" % i for i in range(len(seqs))], seqs), dev)
+    lens = np.array([len(s) for s in seqs])
+    n = 400
+    chrom = rng.integers(0, len(seqs), n)
+    start = (rng.random(n) * lens[chrom]).astype(np.int64)
+    ln = np.where(rng.random(n) < 0.25, rng.integers(0, 8, n), rng.integers(0, 40_000, n))
+    end = start + ln
+    # whole chromosomes (multi-chunk regions), odd and even starts
+    chrom = np.concatenate([chrom, np.arange(len(seqs)), [2, 2, 3, 3]])
+    start = np.concatenate([start, np.zeros(len(seqs), dtype=np.int64), [1, 2, 3, 100_001]])
+    end = np.concatenate([end, lens, [300_007, 300_006, 250_003, 250_002]])
+    start = np.where((start > 0) & (start < 2), 2, start)
+    end = np.maximum(end, start)
+    seq = np.full(dg.n_bases, ord("N"), dtype=np.uint8)
+    for o, s in zip(dg.chrom_off, seqs):
+        seq[o:o + len(s)] = s
+    want5, _ = oracle.count_regions(seq, dg.chrom_off, dg.chrom_len, chrom, start, end, 2, 2)
+    want3, _ = oracle.count_regions(seq, dg.chrom_off, dg.chrom_len, chrom, start, end, 1, 1)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    try:
+        for variant in (0, 2):                       # ATOMS.EXCH.128 flush and plain LDS/STS flush
+            lib.dig_debug_set_scan_variant(variant)
+            for limit in (1 << 20, 64):              # 64 kb: the register totals spill to global many times
+                lib.dig_debug_set_totals_limit_kb(ctypes.c_uint(limit))
+                c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, chrom, start, end, want_totals=True)
+                bad = np.flatnonzero((c5.cpu().numpy() != want5).any(axis=1))
+                assert bad.size == 0, (variant, bad[:5], chrom[bad[:5]], start[bad[:5]], end[bad[:5]])
+                assert np.array_equal(c3.cpu().numpy(), want3)
+                assert np.array_equal(t5.cpu().numpy(), want5.sum(axis=0))
+                assert np.array_equal(t3.cpu().numpy(), want3.sum(axis=0))
+                p5, pt = kernels.count_contexts(dg, chrom, start, end, 2, 2, want_totals=True)
+                assert np.array_equal(p5.cpu().numpy(), want5) and np.array_equal(pt.cpu().numpy(), want5.sum(axis=0))
+                q5, _ = kernels.count_contexts(dg, chrom, start, end, 2, 2)
+                assert np.array_equal(q5.cpu().numpy(), want5)
+        lib.dig_debug_set_scan_variant(1)            # the per-base kernels stay available and agree
+        c5, c3, _, _ = kernels.count_contexts_fused53(dg, chrom, start, end)
+        assert np.array_equal(c5.cpu().numpy(), want5) and np.array_equal(c3.cpu().numpy(), want3)
+    finally:
+        lib.dig_debug_set_scan_variant(0)
+        lib.dig_debug_set_totals_limit_kb(ctypes.c_uint(1 << 20))

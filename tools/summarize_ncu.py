@@ -28,7 +28,7 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in rows]
-    marks = [i for i, (n, _) in enumerate(names) if "scan_fused53_kernel" in n or "scan_sym_kernel<2" in n]
+    marks = [i for i, (n, _) in enumerate(names) if "scan_fused53_kernel" in n or "scan_sym_kernel<2" in n or "scan_hex_kernel" in n]
     step = names[marks[-1]:] if marks else names
     tot = sum(v for _, v in step)
     agg = collections.OrderedDict()
