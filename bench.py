@@ -618,9 +618,20 @@ def main():
                 "note": "HBM is the roofline the contract asks for; ncu shows the kernel is bound by the shared-memory "
                         "atomic data pipe (87 % busy after halving the atomics with hexamer pairs), see DESIGN.md section 4", "share_of_step": k5_ms / ms_per_step}
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: destroy_process_group() after a CUDA graph that holds NCCL kernels was
+        captured can block for ever (seen at N=2), and the process is exiting anyway."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if dist_ctx is not None:
-            dist.destroy_process_group()
+            stepper.graph = None
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the reference's algorithm
@@ -644,8 +655,7 @@ def main():
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
-    if dist_ctx is not None:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
