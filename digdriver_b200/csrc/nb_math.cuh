@@ -130,6 +130,44 @@ __device__ inline double nb_midp(double k, double alpha, double p)
     return (isint ? 0.5 * exp(lg) : 0.0) + sf;
 }
 
+// nb_pvalue_exact (nb_model.py:298-314): lower tail I_p(alpha, k+1) when k is below the mean alpha (1-p)/p,
+// otherwise upper tail I_{1-p}(k, alpha) with the pmf as fallback when that underflows to 0.  Both tails come from
+// the same density + continued-fraction pieces as nb_midp, choosing per tail the form that has no cancellation.
+__device__ inline double nb_tail_upper_from(double kk, double alpha, double p, double q)     // P(X > kk) = I_q(kk+1, alpha)
+{
+    const double lg = log_nb_density(kk, alpha, p, q);
+    const double a = kk + 1.0;
+    if (q < (a + 1.0) / (a + alpha + 2.0)) return exp(lg + log(q * (kk + alpha) / a * beta_cf(a, alpha, q)));
+    return 1.0 - exp(lg + log(q * (kk + alpha) / alpha * beta_cf(alpha, a, p)));
+}
+
+__device__ inline double nb_tail_lower_to(double kk, double alpha, double p, double q)       // P(X <= kk) = I_p(alpha, kk+1)
+{
+    const double lg = log_nb_density(kk, alpha, p, q);
+    const double a = kk + 1.0;
+    if (q < (a + 1.0) / (a + alpha + 2.0)) return 1.0 - exp(lg + log(q * (kk + alpha) / a * beta_cf(a, alpha, q)));
+    return exp(lg + log(q * (kk + alpha) / alpha * beta_cf(alpha, a, p)));
+}
+
+__device__ inline double nb_exact(double k, double alpha, double p)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (isnan(k) || isnan(alpha) || isnan(p)) return nan;
+    if (!(alpha > 0.0) || isinf(alpha) || k < 0.0 || isinf(k) || p < 0.0 || p > 1.0) return nan;
+    const double q = 1.0 - p;
+    const double mean = alpha * q / p;                       // +inf when p == 0
+    if (k < mean) {
+        if (p <= 0.0) return 0.0;                            // betainc(alpha, k+1, 0)
+        if (k == 0.0) return exp(alpha * log(p));            // I_p(alpha, 1) = p^alpha
+        return nb_tail_lower_to(k, alpha, p, q);
+    }
+    // only reached with q < 1
+    if (k == 0.0) return 1.0;                                // betainc(0, alpha, q) = 1 (q > 0), else pmf(0; p = 1) = 1
+    if (q <= 0.0) return 0.0;                                // betainc(k, alpha, 0) = 0 and pmf(k > 0; p = 1) = 0
+    const double up = nb_tail_upper_from(k - 1.0, alpha, p, q);
+    if (up == 0.0) return exp(log_nb_density(k, alpha, p, q));
+    return up;
+}
 
 // chi2.sf(-2 (ln p1 + ln p2), df=4) = exp(-y) (1 + y), y = -(ln p1 + ln p2)  (transfer_tools.py:860-861)
 __device__ inline double fisher2(double a, double b)

@@ -358,3 +358,81 @@ def site_counts(site_elt, site_sub, n_elt, n_sub=192, device="cuda:0", stream=No
         _lib.call("dig_site_counts", se.data_ptr(), ss.data_ptr(), se.numel(), n_elt, n_sub, out.data_ptr(),
                   _stream(dev, stream))
     return out[:n_elt]
+
+
+def nb_pvalue_exact(k, alpha, p, device="cuda:0", stream=None):
+    """K8 scalar form: nb_model.nb_pvalue_exact(k, alpha, p) (nb_model.py:298-314) element-wise in FP64 on the GPU."""
+    dev = torch.device(device)
+    kk, aa, pp = (_dev(x, torch.float64, dev).contiguous() for x in (k, alpha, p))
+    out = torch.empty_like(kk)
+    with torch.cuda.device(dev):
+        _lib.call("dig_nb_pvalue_exact", kk.data_ptr(), aa.data_ptr(), pp.data_ptr(), kk.numel(), out.data_ptr(),
+                  _stream(dev, stream))
+    return out
+
+
+def position_bins(genome, reg_chrom, reg_start, reg_end, n_up, n_down, binsize):
+    """Host-side bin layout of K8: positions per region (the centres the scan walks, quirks a1-i/ii included)
+    and the CSR bin_ptr [n_reg + 1]."""
+    rc = np.asarray(reg_chrom, dtype=np.int64)
+    rs = np.asarray(reg_start, dtype=np.int64).copy()
+    re = np.asarray(reg_end, dtype=np.int64)
+    L = np.asarray(genome.chrom_len, dtype=np.int64)[rc]
+    rs[rs < n_up] = n_up                                     # START == 0 -> n_up (sequence_tools.py:25-26)
+    first = np.minimum(rs, L)
+    last = np.minimum(re + n_down, L) - n_down               # faidx clips at the chromosome end
+    n_pos = np.maximum(last - first, 0)
+    n_bin = -(-n_pos // binsize)
+    ptr = np.zeros(len(rc) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum(n_bin)
+    return first, n_pos, ptr
+
+
+def position_test(genome, reg_chrom, reg_start, reg_end, mu, sigma, s_prob, mut_chrom, mut_start, n_up=2, n_down=2,
+                  binsize=1, normed=True, want=("pt", "exp", "pos"), stream=None):
+    """K8: apply_nb_to_region / nb_model (nb_model.py:126-235) for a list of regions.  s_prob is the [K] table of
+    per-context probabilities in k-mer index order; (mut_chrom, mut_start) are the mutation rows (chromosome index
+    into the genome, 0-based START).  Returns a dict of device tensors over all bins (regions concatenated):
+    pval, obs and, if wanted, pt / exp / pos, plus the host arrays bin_ptr and n_pos."""
+    dev = genome.device
+    rc = _dev(reg_chrom, torch.int32, dev)
+    rs = _dev(reg_start, torch.int64, dev)
+    re = _dev(reg_end, torch.int64, dev)
+    n_reg = rc.numel()
+    K = 4 ** (n_up + n_down + 1)
+    sp = _dev(s_prob, torch.float64, dev).contiguous()
+    assert sp.numel() == K, "s_prob must have 4^(n_up+n_down+1) entries"
+    mu_d, sg_d = _dev(mu, torch.float64, dev).contiguous(), _dev(sigma, torch.float64, dev).contiguous()
+    assert mu_d.numel() == n_reg and sg_d.numel() == n_reg
+    host = lambda x: x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    first, n_pos, ptr = position_bins(genome, host(reg_chrom), host(reg_start), host(reg_end), n_up, n_down, binsize)
+    n_bin = int(ptr[-1])
+    ptr_d = torch.from_numpy(ptr).to(dev)
+    mk = (host(mut_chrom).astype(np.int64) << 32) | host(mut_start).astype(np.int64)
+    mk_d = torch.from_numpy(np.sort(mk)).to(dev)
+    sptr = _stream(dev, stream)
+    out = {"bin_ptr": ptr, "n_pos": n_pos, "first": first}
+    with torch.cuda.device(dev):
+        norm = None
+        if normed:
+            counts, _ = count_contexts(genome, rc, rs, re, n_up, n_down, stream=stream)
+            norm = torch.empty(n_reg, dtype=torch.float64, device=dev)
+            _lib.call("dig_region_prob_norm", counts.data_ptr(), sp.data_ptr(), n_reg, K, norm.data_ptr(), sptr)
+            out["norm"] = norm
+        obs = torch.empty(max(n_bin, 1), dtype=torch.int32, device=dev)
+        _lib.call("dig_position_obs", mk_d.data_ptr(), mk_d.numel(), genome.chrom_off_d.data_ptr(),
+                  genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(), re.data_ptr(), n_reg, int(n_up),
+                  int(n_down), int(binsize), ptr_d.data_ptr(), n_bin, obs.data_ptr(), sptr)
+        pval = torch.empty(max(n_bin, 1), dtype=torch.float64, device=dev)
+        extra = {k: (torch.empty(max(n_bin, 1), dtype=torch.float64, device=dev) if k in want else None)
+                 for k in ("pt", "exp", "pos")}
+        _lib.call("dig_position_test", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
+                  genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),
+                  re.data_ptr(), n_reg, int(n_up), int(n_down), sp.data_ptr(), _ptr(norm), mu_d.data_ptr(),
+                  sg_d.data_ptr(), int(binsize), ptr_d.data_ptr(), obs.data_ptr(), pval.data_ptr(),
+                  _ptr(extra["pt"]), _ptr(extra["exp"]), _ptr(extra["pos"]), sptr)
+    out["pval"], out["obs"] = pval[:n_bin], obs[:n_bin]
+    for k, v in extra.items():
+        if v is not None:
+            out[k] = v[:n_bin]
+    return out

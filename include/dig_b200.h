@@ -242,6 +242,37 @@ int dig_gene_burden_test(const double *mu_d, const double *sigma_d, const double
                          double n_syn, double scale_factor, double *out_d, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * K8: per-position / per-bin hotspot test (secondary path of the reference).
+ * dig_region_prob_norm replaces the normaliser of base_probabilities_by_region (sequence_tools.py:292-317,
+ *   `probs / np.sum(probs)`): norm[r] = sum_k counts[r,k] * s_prob[k], counts = dig_count_contexts of the same
+ *   regions with the same (n_up, n_down); s_prob_d [4^(n_up+n_down+1)] in k-mer index order.
+ * dig_position_obs replaces `df.START.value_counts()` + the per-position lookups of apply_nb_to_region
+ *   (nb_model.py:135-136, :149-151, :167-170): obs[bin_ptr[r] + (pos - first)/binsize] += 1 for every mutation row
+ *   whose START is a position of region r.  mut_key_d = chrom index << 32 | START, ascending; obs_d is zeroed here.
+ * dig_position_test replaces the loops of apply_nb_to_region (nb_model.py:146-178): per bin pt = sum of normalised
+ *   position probabilities (0 for k-mers with N), p = 1/(pt*theta + 1), pval = nb_pvalue_exact(k, alpha, p)
+ *   (nb_model.py:298-314), exp = pt*mu, pos = mean position (chromosome coordinates).  alpha/theta from mu_d/sigma_d
+ *   [n_reg] (normal_params_to_gamma, :237-241).  Region r owns bins bin_ptr[r] .. bin_ptr[r+1]-1 =
+ *   ceil(n_positions / binsize), positions being the centres dig_count_contexts walks.  norm_d NULL = unnormalised
+ *   (normed=False); pt_d / exp_d / pos_d may be NULL.
+ * dig_nb_pvalue_exact replaces nb_model.nb_pvalue_exact(k, alpha, p) (nb_model.py:298-314) element-wise.
+ */
+int dig_region_prob_norm(const int32_t *counts_d, const double *s_prob_d, int64_t n_reg, int n_ctx, double *norm_d,
+                         void *stream);
+int dig_position_obs(const int64_t *mut_key_d, int64_t n_mut, const int64_t *chrom_off_d, const int64_t *chrom_len_d,
+                     const int32_t *reg_chrom_d, const int64_t *reg_start_d, const int64_t *reg_end_d, int64_t n_reg,
+                     int n_up, int n_down, int binsize, const int64_t *bin_ptr_d, int64_t n_bin, int32_t *obs_d,
+                     void *stream);
+int dig_position_test(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases, const int64_t *chrom_off_d,
+                      const int64_t *chrom_len_d, const int32_t *reg_chrom_d, const int64_t *reg_start_d,
+                      const int64_t *reg_end_d, int64_t n_reg, int n_up, int n_down, const double *s_prob_d,
+                      const double *norm_d, const double *mu_d, const double *sigma_d, int binsize,
+                      const int64_t *bin_ptr_d, const int32_t *obs_d, double *pval_d, double *pt_d, double *exp_d,
+                      double *pos_d, void *stream);
+int dig_nb_pvalue_exact(const double *k_d, const double *alpha_d, const double *p_d, int64_t n, double *pval_out_d,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Synthetic genome generator (BASELINE.json configs are synthetic): position g is a pure
  * function of (seed, g); identical to orc_synth_genome in oracle/dig_oracle.c.
  */

@@ -443,3 +443,71 @@ def gene_observed_counts(df_mut_cds, max_muts_per_gene_per_sample=3e9):
         ns = sub.groupby(["GENE", "SAMPLE"]).size().reset_index(name="CNT").GENE.value_counts()
         out[col] = ns.reindex(out.index).fillna(0).astype(np.int64)
     return out
+
+
+# ----------------------------------------------------------------------------
+# per-position / per-bin hotspot test
+# ----------------------------------------------------------------------------
+
+def nb_pvalue_exact(k, alpha, p):
+    """nb_model.py:298-314 -- the reference's branches, evaluated with SciPy (scalar)."""
+    import scipy.special
+    import scipy.stats
+    mu = alpha * (1 - p) / p
+    if k < mu:
+        return float(scipy.special.betainc(alpha, k + 1, p))
+    pval = float(scipy.special.betainc(k, alpha, 1 - p))
+    if pval == 0:
+        pval = float(scipy.stats.nbinom.pmf(k, alpha, p))
+    return pval
+
+
+def base_probabilities(seq_chrom, start, end, s_prob, n_up=2, n_down=2, normed=True):
+    """base_probabilities_by_region (sequence_tools.py:292-317) on an upper-cased chromosome byte array:
+    returns (probs float64, positions int64).  s_prob is indexed by the k-mer's base-4 index."""
+    L = len(seq_chrom)
+    if start == 0:
+        start = n_up                                            # fetch_sequence, sequence_tools.py:25-26
+    f0, f1 = start - n_up, min(end + n_down, L)                 # faidx clips at the chromosome end
+    f0 = min(f0, L)
+    code = np.full(256, -1, dtype=np.int64)
+    for i, b in enumerate(b"ACGT"):
+        code[b] = i
+        code[b | 0x20] = i
+    c = code[np.asarray(seq_chrom[f0:f1], dtype=np.uint8)]
+    n = len(c)
+    poss = np.arange(f0 + n_up, f0 + max(n - n_down, n_up), dtype=np.int64)
+    probs = np.zeros(len(poss), dtype=np.float64)
+    klen = n_up + n_down + 1
+    for j in range(len(poss)):
+        w = c[j:j + klen]
+        if (w < 0).any():
+            continue
+        idx = 0
+        for v in w:
+            idx = idx * 4 + int(v)
+        probs[j] = s_prob[idx]
+    if normed:
+        with np.errstate(all="ignore"):
+            probs = probs / np.sum(probs)
+    return probs, poss
+
+
+def position_test(seq_chrom, start, end, mu, sigma, s_prob, mut_starts, n_up=2, n_down=2, binsize=1):
+    """apply_nb_to_region (nb_model.py:126-186): returns (pvals, poss, obss, exps, pts) for one region."""
+    probs, pos_lst = base_probabilities(seq_chrom, start, end, s_prob, n_up, n_down, normed=True)
+    vals, cnts = np.unique(np.asarray(mut_starts, dtype=np.int64), return_counts=True)
+    mut_counts = dict(zip(vals.tolist(), cnts.tolist()))
+    alpha, theta = mu ** 2 / sigma ** 2, sigma ** 2 / mu
+    pvals, poss, obss, exps, pts = [], [], [], [], []
+    for i in range(0, len(pos_lst), binsize):
+        pt = probs[i] if binsize == 1 else np.sum(probs[i:i + binsize])
+        k = sum(mut_counts.get(int(pos), 0) for pos in pos_lst[i:i + binsize])
+        with np.errstate(all="ignore"):
+            p = 1 / (pt * theta + 1)
+            pvals.append(nb_pvalue_exact(k, alpha, p))
+        poss.append(float(np.mean(pos_lst[i:i + binsize])))
+        obss.append(k)
+        exps.append(pt * mu)
+        pts.append(pt)
+    return (np.array(pvals, dtype=float), np.array(poss), np.array(obss), np.array(exps), np.array(pts))

@@ -192,3 +192,20 @@ def test_tabulate_mutations_in_element_small(oracle):
     assert summ.loc["E1"].tolist() == [2, 3, 0]
     summ, _ = oracle.tabulate_mutations_in_element(mut, blocks, max_muts_per_elt_per_sample=1)
     assert summ.loc["E1"].tolist() == [3, 2, 1]
+
+
+def test_position_test_oracle_matches_reference_golden(oracle):
+    """a16: the oracle's apply_nb_to_region / nb_pvalue_exact restatement against the frozen outputs of the
+    unmodified reference (tests/golden/make_golden_position.py)."""
+    z = golden("position")
+    seq, muts = z["seq"], z["mut_start"]
+    for ci, (u, d, binsize, s, e, mu, sigma, n) in enumerate(z["cases"]):
+        u, d, binsize, s, e = int(u), int(d), int(binsize), int(s), int(e)
+        pv, pos, obs, exp, pt = oracle.position_test(seq, s, e, mu, sigma, z["s_prob_%d_%d" % (u, d)], muts, u, d, binsize)
+        assert len(pv) == int(n)
+        assert np.array_equal(obs, z["obs_%d" % ci]) and np.array_equal(pos, z["pos_%d" % ci])
+        assert np.array_equal(pt, z["pt_%d" % ci], equal_nan=True) and np.array_equal(exp, z["exp_%d" % ci], equal_nan=True)
+        assert np.array_equal(pv, z["pval_%d" % ci], equal_nan=True)
+    with np.errstate(all="ignore"):
+        ex = np.array([oracle.nb_pvalue_exact(k, a, p) for k, a, p in zip(z["ex_k"], z["ex_alpha"], z["ex_p"])])
+    assert np.array_equal(ex, z["ex_pval"], equal_nan=True)
