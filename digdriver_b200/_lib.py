@@ -31,7 +31,7 @@ SIGNATURES = {
     "dig_substitution_counts": (_I, [_P, _P, _I64, _I, _I, _P, _P]),
     "dig_count_hits": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "dig_tabulate_elements": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I64, _P,
-                                   _I64, _I64, _I64, _P, _P, _P]),
+                                   _I64, _I64, _I64, _P, _P, _I, _P]),
     "dig_site_counts": (_I, [_P, _P, _I64, _I64, _I, _P, _P]),
     "dig_tabulate_genes": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P]),
     "dig_element_transfer": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P,

@@ -90,14 +90,15 @@ __global__ void __launch_bounds__(256) elt_insert_kernel(
 __global__ void __launch_bounds__(256) elt_sample_totals_kernel(const unsigned long long *__restrict__ keys,
                                                                 const uint32_t *__restrict__ snv,
                                                                 const uint32_t *__restrict__ indel, int64_t capacity,
-                                                                unsigned long long *sample_tot)
+                                                                int rows_mode, unsigned long long *sample_tot)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < capacity; s += stride) {
         const unsigned long long key = keys[s];
         if (key == 0ull) continue;
         const uint32_t sample = (uint32_t)((key - 1ull) & 0xFFFFFFFFull);
-        atomicAdd(sample_tot + sample, (unsigned long long)snv[s] + (unsigned long long)indel[s]);
+        // rows_mode: one per (element, sample) row = df.SAMPLE.value_counts() of the per-sample-per-element table
+        atomicAdd(sample_tot + sample, rows_mode ? 1ull : (unsigned long long)snv[s] + (unsigned long long)indel[s]);
     }
 }
 
@@ -221,7 +222,7 @@ int dig_tabulate_elements(const int64_t *blk_kstart_d, const int64_t *blk_kend_d
                           int64_t n_mut, unsigned long long *tab_key_d, uint32_t *tab_snv_d, uint32_t *tab_indel_d,
                           int64_t capacity, int64_t n_sample, unsigned long long *sample_tot_d,
                           int64_t max_muts_per_sample, int64_t max_per_elt_per_sample, int64_t n_elt,
-                          int64_t *obs_d, int32_t *status_d, void *stream)
+                          int64_t *obs_d, int32_t *status_d, int sample_rows_mode, void *stream)
 {
     DIG_CHECK_ARG(n_blk >= 0 && n_mut >= 0 && n_elt >= 0 && n_sample >= 0, "negative size");
     DIG_CHECK_ARG(is_pow2(capacity), "capacity must be a power of two");
@@ -243,7 +244,7 @@ int dig_tabulate_elements(const int64_t *blk_kstart_d, const int64_t *blk_kend_d
                                                        tab_key_d, tab_snv_d, tab_indel_d, capacity, status_d);
     DIG_CHECK_LAUNCH();
     elt_sample_totals_kernel<<<grid_for(capacity), 256, 0, st>>>(tab_key_d, tab_snv_d, tab_indel_d, capacity,
-                                                                 sample_tot_d);
+                                                                 sample_rows_mode, sample_tot_d);
     DIG_CHECK_LAUNCH();
     elt_finalize_kernel<<<grid_for(capacity), 256, 0, st>>>(tab_key_d, tab_snv_d, tab_indel_d, capacity, sample_tot_d,
                                                             max_muts_per_sample, max_per_elt_per_sample, n_elt, obs_d);

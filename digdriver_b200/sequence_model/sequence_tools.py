@@ -315,3 +315,29 @@ def precount_region_contexts_parallel(f_nonc_bed, f_fasta, n_procs, window, sub_
         all_regions = list(zip(chrom, bed[1], bed[2], bed[5]))
     results = nonc_elt_context_count(all_regions, trans_idx, f_fasta)
     return results.loc[~results.index.duplicated()]
+
+
+def _s_prob_table(S_prob, n_up, n_down, collapse=False):
+    """Dense [4^k] probability table in k-mer index order from the reference's {k-mer: probability} mapping
+    (dict or Series).  With collapse=True purine-centred k-mers take the value of their reverse complement
+    (seq_to_context, reference :42-55)."""
+    full = list(mk_context_sequences(n_up, n_down, collapse=False))
+    get = S_prob.__getitem__
+    out = np.empty(len(full), dtype=np.float64)
+    for i, kmer in enumerate(full):
+        key = reverse_complement(kmer) if (collapse and kmer[n_up] in 'GA') else kmer
+        out[i] = float(get(key))
+    return out
+
+
+def base_probabilities_by_region(fasta, S_prob, CHROM, START, END, n_up=2, n_down=2, normed=True, collapse=False):
+    """Probability of mutation at every position across a region (reference :292-317).  ``fasta`` is a FASTA path,
+    Genome or DeviceGenome; returns (probs, positions) as numpy arrays."""
+    g = get_device_genome(fasta)
+    if 0 < START < n_up:
+        raise ValueError("start out of range (%d)" % (START - n_up))
+    cidx = g.chrom_indices([CHROM], prefix="")
+    out = kernels.position_test(g, cidx, [START], [END], [1.0], [1.0], _s_prob_table(S_prob, n_up, n_down, collapse),
+                                np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64), n_up=n_up, n_down=n_down,
+                                binsize=1, normed=normed, want=("pt", "pos"))
+    return out["pt"].cpu().numpy(), out["pos"].cpu().numpy().astype(np.int64)

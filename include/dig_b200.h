@@ -133,7 +133,10 @@ int dig_substitution_counts(const int32_t *ctx_d, const uint8_t *alt_d, int64_t 
  * (capacity: power of two >= 2 * n_hits).
  * dig_tabulate_elements: builds the (element, sample) table, then
  *   sample_tot_d [n_sample] uint64: total OBS_MUT per sample over all elements (zeroed inside);
- *                samples with sample_tot > max_muts_per_sample are black-listed (:163-165)
+ *                samples with sample_tot > max_muts_per_sample are black-listed (:163-165).
+ *                sample_rows_mode != 0: sample_tot counts (element, sample) ROWS instead, which is what
+ *                add_objectives' filters see (filter_hypermut_samples / filter_samples_by_stdev applied to the
+ *                per-sample-per-element table: SAMPLE.value_counts(), mutation_tools.py:293-316, DataExtractor.py:548-552)
  *   obs_d        [n_elt, 3] int64: OBS_SAMPLES, OBS_SNV, OBS_INDEL (zeroed inside); per
  *                (element, sample) counts are capped at max_per_elt_per_sample (:168-169)
  *   status_d     [1] int32: set to 1 if the hash table overflowed (results invalid)
@@ -148,7 +151,7 @@ int dig_tabulate_elements(const int64_t *blk_kstart_d, const int64_t *blk_kend_d
                           uint32_t *tab_indel_d, int64_t capacity, int64_t n_sample,
                           unsigned long long *sample_tot_d, int64_t max_muts_per_sample,
                           int64_t max_per_elt_per_sample, int64_t n_elt, int64_t *obs_d, int32_t *status_d,
-                          void *stream);
+                          int sample_rows_mode, void *stream);
 
 /* Site sets (preprocess_sites, sequence_tools.py:692-703): L_d [n_elt, n_sub] uint64 (overwritten),
  * L[elt, sub] = number of sites of site-set `elt` whose substitution index is `sub` (negative / out-of-range

@@ -511,3 +511,80 @@ def position_test(seq_chrom, start, end, mu, sigma, s_prob, mut_starts, n_up=2, 
         exps.append(pt * mu)
         pts.append(pt)
     return (np.array(pvals, dtype=float), np.array(poss), np.array(obss), np.array(exps), np.array(pts))
+
+
+# ----------------------------------------------------------------------------
+# per-window observed counts: add_objectives, mutation branch
+# ----------------------------------------------------------------------------
+
+def muts_per_sample_per_element(df_mut, df_blocks, drop_duplicates=True):
+    """tabulate_muts_per_sample_per_element (mutation_tools.py:191-230): rows (ELT, SAMPLE, OBS_SNV, OBS_INDEL,
+    OBS_MUT).  Same restatement of ``bedtools intersect -wa -wb`` as tabulate_mutations_in_element above."""
+    import pandas as pd
+    hits = []
+    for chrom, dm in df_mut.groupby("CHROM", sort=False):
+        db = df_blocks[df_blocks.CHROM == chrom]
+        if len(db) == 0:
+            continue
+        bs, be, elt = db.START.values, db.END.values, db.ELT.values
+        for row in dm.itertuples(index=True):
+            m = (bs < row.END) & (be > row.START)
+            for e in elt[m]:
+                hits.append((row.Index, e))
+    if not hits:
+        return pd.DataFrame({'ELT': [], 'SAMPLE': [], 'OBS_SNV': [], 'OBS_INDEL': [], 'OBS_MUT': []})
+    h = pd.DataFrame(hits, columns=["ROW", "ELT"])
+    df = df_mut.loc[h.ROW.values].reset_index(drop=True)
+    df["ELT"] = h.ELT.values
+    if drop_duplicates:
+        df = df.drop_duplicates(["CHROM", "START", "END", "REF", "ALT", "SAMPLE", "ELT"])
+    is_indel = df.ANNOT == "INDEL"
+    snv = df[~is_indel].groupby(["ELT", "SAMPLE"]).size().reset_index(name="OBS_SNV")
+    ind = df[is_indel].groupby(["ELT", "SAMPLE"]).size().reset_index(name="OBS_INDEL")
+    cnt = snv.merge(ind, how="outer")
+    cnt["OBS_SNV"] = cnt.OBS_SNV.fillna(0)
+    cnt["OBS_INDEL"] = cnt.OBS_INDEL.fillna(0)
+    cnt["OBS_MUT"] = cnt.OBS_SNV + cnt.OBS_INDEL
+    return cnt[["ELT", "SAMPLE", "OBS_SNV", "OBS_INDEL", "OBS_MUT"]]
+
+
+def window_objectives(df_mut, idx, max_muts_per_elt_per_sample=None, sample_filter_stdev=None,
+                      max_muts_per_sample=None, filters=None):
+    """add_objectives, mutation branch (DataExtractor.py:540-559).  ``filters`` may supply the reference's own
+    (cap_muts_per_element_per_sample, filter_samples_by_stdev, filter_hypermut_samples) -- the golden generator
+    passes the unmodified functions; by default the restatements of mutation_tools.py:293-326 below are used."""
+    import pandas as pd
+
+    def cap(df, m):                                              # :318-326 -- caps OBS_MUT only
+        df.loc[df.OBS_MUT > m, 'OBS_MUT'] = m
+        return df
+
+    def by_stdev(df, cutoff):                                    # :306-316
+        cnt = df.SAMPLE.value_counts()
+        bl = cnt[cnt > cnt.std() * cutoff].index.to_list()
+        return df[~df.SAMPLE.isin(bl)]
+
+    def hypermut(df, m):                                         # :293-304
+        cnt = df.SAMPLE.value_counts()
+        bl = cnt[cnt > m].index.to_list()
+        return df[~df.SAMPLE.isin(bl)]
+
+    f_cap, f_std, f_hyp = filters or (cap, by_stdev, hypermut)
+    idx = np.asarray(idx)
+    df_idx = pd.DataFrame(idx, columns=['CHROM', 'START', 'END'])
+    df_idx['ELT'] = ['{}:{}-{}'.format(r[0], r[1], r[2]) for r in idx]
+    blocks = df_idx.copy()
+    blocks['CHROM'] = blocks.CHROM.astype(str)
+    df = muts_per_sample_per_element(df_mut, blocks, drop_duplicates=True)
+    if max_muts_per_elt_per_sample:
+        df = f_cap(df, max_muts_per_elt_per_sample)
+    if sample_filter_stdev:
+        df = f_std(df, sample_filter_stdev)
+    if max_muts_per_sample:
+        df = f_hyp(df, max_muts_per_sample)
+    if len(df) == 0:
+        return np.zeros(len(idx), dtype=np.int64)
+    df_elt = df.pivot_table(index='ELT', values='OBS_SNV', aggfunc='sum')
+    df_cnt = df_idx.merge(df_elt, on='ELT', how='left')
+    df_cnt.loc[df_cnt.OBS_SNV.isna(), 'OBS_SNV'] = 0
+    return df_cnt.OBS_SNV.astype(int).values.astype(np.int64)

@@ -87,3 +87,41 @@ def test_position_test_windows_vs_oracle(dev, oracle):
             assert np.array_equal(ob[a:b], wobs)
             _close(pt[a:b], wpt)
             assert_pvals_close(pv[a:b], wpv)
+
+
+def test_nb_model_api_matches_reference_golden(dev):
+    """The reference-facing functions (nb_model.nb_model / apply_nb_to_region / nb_pvalue_exact and
+    sequence_tools.base_probabilities_by_region) with the reference's own argument conventions."""
+    import pandas as pd
+    from digdriver_b200.genome import Genome
+    from digdriver_b200.sequence_model import nb_model as nb, sequence_tools as st
+    z = golden("position")
+    g = Genome(["chr1"], [z["seq"]])
+    df_mut = pd.DataFrame({"CHROM": "1", "START": z["mut_start"]})
+    cases = z["cases"]
+    for u, d in ((2, 2), (1, 1)):
+        S = dict(zip(st.mk_context_sequences(u, d).keys(), z["s_prob_%d_%d" % (u, d)]))
+        sel = [i for i, c in enumerate(cases) if (int(c[0]), int(c[1]), int(c[2])) == (u, d, 50)]
+        c = cases[sel]
+        idx = np.stack([np.ones(len(sel)), c[:, 3], c[:, 4]], axis=1).astype(np.int64)
+        df = nb.nb_model(S, idx, c[:, 5], c[:, 6], df_mut, g, n_up=u, n_down=d, binsize=50)
+        assert list(df.columns) == ['CHROM', 'POS', 'OBS', 'EXP', 'PVAL', 'Pi', 'MU', 'SIGMA', 'REGION']
+        want_p = np.concatenate([z["pval_%d" % ci] for ci in sel])
+        want_pos = np.concatenate([z["pos_%d" % ci] for ci in sel])
+        assert np.array_equal(df.POS.values, want_pos)
+        assert_pvals_close(df.PVAL.values, want_p)
+        assert df.REGION.iloc[0] == "1:%d-%d" % (idx[0, 1], idx[0, 2])
+        # one region, per position
+        ci = [i for i, cc in enumerate(cases) if (int(cc[0]), int(cc[1]), int(cc[2])) == (u, d, 1)][2]
+        cc = cases[ci]
+        pv, pos, obs, exps, pts = nb.apply_nb_to_region(1, int(cc[3]), int(cc[4]), cc[5], cc[6], S, df_mut, g,
+                                                        n_up=u, n_down=d, binsize=1)
+        assert np.array_equal(obs, z["obs_%d" % ci]) and np.array_equal(pos, z["pos_%d" % ci])
+        assert_pvals_close(pv, z["pval_%d" % ci])
+        _close(np.array(pts), z["pt_%d" % ci])
+        probs, poss = st.base_probabilities_by_region(g, S, "chr1", int(cc[3]), int(cc[4]), n_up=u, n_down=d)
+        _close(probs, z["pt_%d" % ci])
+        assert np.array_equal(poss, z["pos_%d" % ci].astype(np.int64))
+    got = nb.nb_pvalue_exact(z["ex_k"], z["ex_alpha"], z["ex_p"])
+    assert_pvals_close(got, z["ex_pval"])
+    assert isinstance(nb.nb_pvalue_exact(3, 2.0, 0.4), float)

@@ -209,3 +209,19 @@ def test_position_test_oracle_matches_reference_golden(oracle):
     with np.errstate(all="ignore"):
         ex = np.array([oracle.nb_pvalue_exact(k, a, p) for k, a, p in zip(z["ex_k"], z["ex_alpha"], z["ex_p"])])
     assert np.array_equal(ex, z["ex_pval"], equal_nan=True)
+
+
+def _objectives_frame(z):
+    return pd.DataFrame({k: z["mut_" + k] for k in ("CHROM", "START", "END", "REF", "ALT", "SAMPLE", "GENE", "ANNOT")})
+
+
+def test_window_objectives_oracle_matches_reference_filters(oracle):
+    """f-2: the oracle's own restatement of the three sample filters against the goldens produced with the
+    reference's unmodified filter functions."""
+    z = golden("objectives")
+    df = _objectives_frame(z)
+    for i, c in enumerate(z["cases"]):
+        cap, std, mx = [None if np.isnan(v) else v for v in c]
+        got = oracle.window_objectives(df.copy(), z["idx"], cap, std, mx)
+        assert np.array_equal(got, z["y_%d" % i]), i
+    assert z["y_0"].sum() > z["y_3"].sum() > 0 and np.array_equal(z["y_0"], z["y_1"])   # the cap quirk: no effect
