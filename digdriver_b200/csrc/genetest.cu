@@ -165,3 +165,140 @@ int dig_gene_burden_test(const double *mu_d, const double *sigma_d, const double
 }
 
 }
+
+// ---------------------------------------------------------------------------------------
+// Secondary gene tests: dN/dS-corrected expectations and burden p-values and the NB likelihood-
+// ratio selection tests, one thread per gene.
+//   gene_expected_muts_dnds  transfer_tools.py:363-392   EXP_x, T_SYN (_mle_t :1263-1271), MRFOLD (:1273-1276), EXP_x_ML
+//   gene_pvalue_burden_dnds  :617-653                    nb_midp(OBS_x, ALPHA, 1 / (EXP_x_ML / ALPHA + 1))
+//   gene_pvalue_sel_nb       :655-676 + _llr_test_nb :1172-1214   chi2.sf(-2 (ll0 - ll_k), df = 1 | 2)
+// Arithmetic follows the reference's operation order without FMA contraction.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+using namespace dig_nb;
+
+// scipy.stats.nbinom.logpmf(k, alpha, 1 / (1 + theta))  (_ll_nb, transfer_tools.py:1253-1255)
+__device__ inline double ll_nb(double k, double alpha, double theta)
+{
+    const double p = __ddiv_rn(1.0, __dadd_rn(1.0, theta));
+    const double q = 1.0 - p;
+    if (isnan(p) || isnan(k) || isnan(alpha)) return __longlong_as_double(0x7ff8000000000000LL);
+    if (q <= 0.0) return k == 0.0 ? 0.0 : -INFINITY;        // all mass at 0
+    if (p <= 0.0) return -INFINITY;
+    return log_nb_density(k, alpha, p, q);
+}
+
+__device__ inline double chi2_sf(double x, int df)
+{
+    if (isnan(x)) return x;
+    if (x <= 0.0) return 1.0;
+    return df == 1 ? erfc(sqrt(0.5 * x)) : exp(-0.5 * x);
+}
+
+__global__ void __launch_bounds__(128) gene_dnds_sel_kernel(const double *__restrict__ alpha,
+                                                            const double *__restrict__ theta,
+                                                            const double *__restrict__ pi,    // [n, 6]
+                                                            const double *__restrict__ obs,   // [n, 6]
+                                                            int64_t n, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        const double a = alpha[g], t = theta[g];
+        double P[6], O[6], E[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            P[j] = pi[g * 6 + j];
+            O[j] = obs[g * 6 + j];
+            E[j] = __dmul_rn(__dmul_rn(a, t), P[j]);
+            out[(int64_t)j * n + g] = E[j];
+        }
+        // _mle_t(OBS_SYN, 1, ALPHA, THETA * Pi_SYN)
+        const double th_syn = __dmul_rn(t, P[0]);
+        double tml = __ddiv_rn(__dadd_rn(__dadd_rn(O[0], a), -1.0), __dadd_rn(1.0, __ddiv_rn(1.0, th_syn)));
+        if (a <= 1.0) {
+            const double lo = __dmul_rn(a, th_syn);
+            tml = tml > lo ? tml : lo;                       // Python max(lo, tml): the first argument wins ties and NaN
+        }
+        const double ratio = __ddiv_rn(tml, E[0]);
+        const double mrf = ratio > 1e-10 ? ratio : 1e-10;    // Python max(1e-10, ratio)
+        out[6 * n + g] = tml;
+        out[7 * n + g] = mrf;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const double eml = __dmul_rn(E[j], mrf);
+            out[(int64_t)(8 + j) * n + g] = eml;
+            const double p = __ddiv_rn(1.0, __dadd_rn(__ddiv_rn(eml, a), 1.0));
+            out[(int64_t)(14 + j) * n + g] = nb_midp(O[j], a, p);
+        }
+        // likelihood-ratio selection tests on SYN (0), MIS (1), TRUNC (4)
+        const int cls[3] = {0, 1, 4};
+        double l0[3], l1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int j = cls[c];
+            l0[c] = ll_nb(O[j], a, __dmul_rn(__dmul_rn(t, P[j]), mrf));
+            l1[c] = ll_nb(O[j], a, __ddiv_rn(O[j], a));
+        }
+        const double ll0 = __dadd_rn(__dadd_rn(l0[0], l0[1]), l0[2]);
+        const double ll_syn = __dadd_rn(__dadd_rn(l1[0], l0[1]), l0[2]);
+        const double ll_mis = __dadd_rn(__dadd_rn(l0[0], l1[1]), l0[2]);
+        const double ll_tr = __dadd_rn(__dadd_rn(l0[0], l0[1]), l1[2]);
+        const double ll_ns = __dadd_rn(__dadd_rn(l0[0], l1[1]), l1[2]);
+        out[20 * n + g] = chi2_sf(-2.0 * (ll0 - ll_syn), 1);
+        out[21 * n + g] = chi2_sf(-2.0 * (ll0 - ll_mis), 1);
+        out[22 * n + g] = chi2_sf(-2.0 * (ll0 - ll_tr), 1);
+        out[23 * n + g] = chi2_sf(-2.0 * (ll0 - ll_ns), 2);
+    }
+}
+
+// selection_coefficient (transfer_tools.py:1279-1292): SEL = (OBS + 1e-16) / (EXP + 1e-16) and the LLR p-value of
+// nbinom(ALPHA, 1/(1 + THETA*Pi)) against nbinom(ALPHA, 1/(1 + THETA*Pi*SEL))
+__global__ void __launch_bounds__(128) selection_coef_kernel(const double *__restrict__ obs, const double *__restrict__ ex,
+                                                             const double *__restrict__ alpha,
+                                                             const double *__restrict__ theta,
+                                                             const double *__restrict__ pi, int64_t n,
+                                                             double *__restrict__ sel, double *__restrict__ pval)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        const double s = __ddiv_rn(__dadd_rn(obs[g], 1e-16), __dadd_rn(ex[g], 1e-16));
+        sel[g] = s;
+        if (pval) {
+            const double tp = __dmul_rn(theta[g], pi[g]);
+            const double ll0 = ll_nb(obs[g], alpha[g], tp);
+            const double ll1 = ll_nb(obs[g], alpha[g], __dmul_rn(tp, s));
+            pval[g] = chi2_sf(-2.0 * (ll0 - ll1), 1);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int dig_gene_dnds_sel(const double *alpha_d, const double *theta_d, const double *pi6_d, const double *obs6_d,
+                                 int64_t n_gene, double *out_d, void *stream)
+{
+    DIG_CHECK_ARG(n_gene >= 0, "negative size");
+    if (n_gene == 0) return DIG_OK;
+    DIG_CHECK_ARG(alpha_d && theta_d && pi6_d && obs6_d && out_d, "null pointer");
+    int64_t blocks = (n_gene + 127) / 128;
+    gene_dnds_sel_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(alpha_d, theta_d, pi6_d, obs6_d, n_gene,
+                                                                            out_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+extern "C" int dig_selection_coefficient(const double *obs_d, const double *exp_d, const double *alpha_d,
+                                         const double *theta_d, const double *pi_d, int64_t n, double *sel_d,
+                                         double *pval_d, void *stream)
+{
+    DIG_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return DIG_OK;
+    DIG_CHECK_ARG(obs_d && exp_d && sel_d, "null pointer");
+    DIG_CHECK_ARG(pval_d == nullptr || (alpha_d && theta_d && pi_d), "p-values need alpha, theta and pi");
+    int64_t blocks = (n + 127) / 128;
+    selection_coef_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(obs_d, exp_d, alpha_d, theta_d, pi_d, n,
+                                                                             sel_d, pval_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}

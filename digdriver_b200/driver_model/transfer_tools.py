@@ -264,6 +264,55 @@ def run_gene_model(f_mut, f_h5_genemodel, scale_by_sample=False, pval_burden_nb=
     return df_model
 
 
+def run_target_model(f_mut, f_h5_genemodel, scale_by_sample=False, panel="MSK_341", max_muts_per_sample=3e9,
+                     max_muts_per_gene_per_sample=3e9, drop_synonymous=True, cgc_genes=False, scale_factor=None):
+    """Analyse the genes of a targeted-sequencing panel with a pretrained gene model (reference :876-967).  The panel
+    scale factor uses the archive attributes N_MUT_<panel> / N_SAMPLE_<panel> written at pretraining time."""
+    print(panel)
+    genes1 = _panel(panel)
+    if genes1 is None:
+        raise FileNotFoundError("genes_{}.txt not found (set DIG_DATA_DIR)".format(panel))
+    genes = genes1
+    if cgc_genes:
+        genes = _panel(cgc_genes)
+        if genes is None:
+            raise FileNotFoundError("genes_{}.txt not found (set DIG_DATA_DIR)".format(cgc_genes))
+    df_mut = read_mutations_cds(f_mut)
+    df_mut = df_mut[df_mut.GENE.isin(genes)]
+    if drop_synonymous:
+        df_mut = df_mut[df_mut.ANNOT != 'Synonymous']
+    df_mut, sample_blacklist = mutation_tools.filter_hypermut_samples(df_mut, max_muts_per_sample, return_blacklist=True)
+    df_cnt = mutation_tools.mutations_per_gene(df_mut, max_muts_per_gene_per_sample=max_muts_per_gene_per_sample)
+    df_pretrain = load_pretrained_model(f_h5_genemodel)
+    df_pretrain = df_pretrain.loc[df_pretrain.index.isin(genes), :]
+    print(len(df_pretrain))
+    df_mut_dedup = mutation_tools.read_mutation_file(f_mut, drop_duplicates=True)
+    df_mut_dedup = df_mut_dedup[~df_mut_dedup.SAMPLE.isin(sample_blacklist)]
+    df_mut_dedup = df_mut_dedup[(df_mut_dedup.ANNOT != 'Noncoding') & (df_mut_dedup.ANNOT != 'Synonymous') &
+                                (df_mut_dedup.ANNOT != 'Essential_Splice')]
+    print(f_mut, df_mut_dedup.shape)
+    df_mut_dedup = df_mut_dedup[df_mut_dedup.GENE.isin(genes1)]
+    N_MUT = len(df_mut_dedup)
+    N_SAMPLE = len(df_mut_dedup.SAMPLE.unique())
+    attrs = storage.Store(f_h5_genemodel, "r").get_attrs()
+    N_MUT_MSK = attrs['N_MUT_{}'.format(panel)]
+    N_SAMPLE_MSK = attrs['N_SAMPLE_{}'.format(panel)]
+    if scale_factor:
+        cj = scale_factor
+    elif scale_by_sample:
+        print(N_SAMPLE, N_SAMPLE_MSK)
+        cj = N_SAMPLE / N_SAMPLE_MSK
+    else:
+        cj = N_MUT / N_MUT_MSK
+    print("\tScaling factor is: {}".format(cj))
+    df_model = transfer_gene_model(df_mut, df_cnt, df_pretrain, cj)
+    df_model = df_model.loc[df_model.index.isin(genes), :]
+    df_model = gene_expected_muts_nb(df_model)
+    df_model = gene_pvalue_burden_nb(df_model)
+    df_model = gene_pvalue_burden_nb_by_sample(df_model)
+    return df_model
+
+
 def _expectation_scale_factors(f_mut, f_h5_pretrain, blacklist):
     """cj / cj_indel of reference :996-1017 (also onthefly_tools.py:45-62), including the no-op COSMIC filter
     on the mutation frame's integer index (:1014) that makes cj_indel count ALL coding indels."""
@@ -352,4 +401,66 @@ def run_sites_region_model(f_mut, f_sites, f_h5_pretrain, pretrain_key, scale_fa
     df_model = element_expected_muts_nb(df_model)
     df_model = element_pvalue_burden_nb(df_model)
     df_model = element_pvalue_burden_nb_by_sample(df_model)
+    return df_model
+
+
+# ---------------------------------------------------------------------------------------------
+# secondary gene tests (reference :363-392, :617-676, :1172-1292) -- one kernel launch per call
+# ---------------------------------------------------------------------------------------------
+
+def _dnds_rows(df_model):
+    cls = kernels.DNDS_CLASSES
+    pi6 = np.stack([df_model["Pi_%s" % c].values.astype(np.float64) for c in cls], axis=1)
+    obs6 = np.stack([df_model["OBS_%s" % c].values.astype(np.float64) for c in cls], axis=1)
+    out = kernels.gene_dnds_sel(df_model.ALPHA.values.astype(np.float64), df_model.THETA.values.astype(np.float64),
+                                pi6, obs6, _dev()).cpu().numpy()
+    return dict(zip(kernels.DNDS_OUT_ROWS, out))
+
+
+def gene_expected_muts_dnds(df_model):
+    """Expected mutations in genes using the dN/dS rate correction (reference :363-392)."""
+    rows = _dnds_rows(df_model)
+    for c in kernels.DNDS_CLASSES:
+        df_model["EXP_%s" % c] = rows["EXP_%s" % c]
+    df_model["T_SYN"] = rows["T_SYN"]
+    df_model["MRFOLD"] = rows["MRFOLD"]
+    for c in kernels.DNDS_CLASSES:
+        df_model["EXP_%s_ML" % c] = rows["EXP_%s_ML" % c]
+    return df_model
+
+
+def gene_pvalue_burden_dnds(df_model):
+    """Burden p-values from the dN/dS-corrected expectations (reference :617-653); needs gene_expected_muts_dnds."""
+    cls = kernels.DNDS_CLASSES
+    alpha = df_model.ALPHA.values.astype(np.float64)
+    k = np.concatenate([df_model["OBS_%s" % c].values.astype(np.float64) for c in cls])
+    p = np.concatenate([1 / (df_model["EXP_%s_ML" % c].values.astype(np.float64) / alpha + 1) for c in cls])
+    pv = kernels.nb_pvalue_greater_midp(k, np.tile(alpha, len(cls)), p, _dev()).cpu().numpy().reshape(len(cls), -1)
+    for i, c in enumerate(cls):
+        df_model["PVAL_%s_BURDEN_DNDS" % c] = pv[i]
+    return df_model
+
+
+def gene_pvalue_sel_nb(df_model):
+    """dN/dS selection p-values from the NB likelihood-ratio tests (reference :655-676, _llr_test_nb :1172-1214).
+    Uses the MRFOLD column when present (as the reference's rows do), otherwise the one computed here."""
+    if "MRFOLD" not in df_model.columns:
+        df_model = gene_expected_muts_dnds(df_model)
+    rows = _dnds_rows(df_model)
+    for c in ("SYN", "MIS", "TRUNC", "NONSYN"):
+        df_model["PVAL_%s_SEL_NB" % c] = rows["PVAL_%s_SEL_NB" % c]
+    return df_model
+
+
+def selection_coefficient(df_model, mut_type, pvalue=True):
+    """Observed / expected ratio of a mutation class and its LLR p-value (reference :1279-1292)."""
+    obs, ex = df_model['OBS_{}'.format(mut_type)].values, df_model['EXP_{}'.format(mut_type)].values
+    if pvalue:
+        sel, pv = kernels.selection_coefficient(obs, ex, df_model.ALPHA.values, df_model.THETA.values,
+                                                df_model['Pi_{}'.format(mut_type)].values, _dev())
+        df_model['SEL_{}'.format(mut_type)] = sel.cpu().numpy()
+        df_model['PVAL_{}_SEL'.format(mut_type)] = pv.cpu().numpy()
+    else:
+        sel, _ = kernels.selection_coefficient(obs, ex, device=_dev())
+        df_model['SEL_{}'.format(mut_type)] = sel.cpu().numpy()
     return df_model

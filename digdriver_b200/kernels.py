@@ -437,3 +437,37 @@ def position_test(genome, reg_chrom, reg_start, reg_end, mu, sigma, s_prob, mut_
         if v is not None:
             out[k] = v[:n_bin]
     return out
+
+
+DNDS_CLASSES = ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")
+DNDS_OUT_ROWS = (["EXP_%s" % c for c in DNDS_CLASSES] + ["T_SYN", "MRFOLD"] + ["EXP_%s_ML" % c for c in DNDS_CLASSES] +
+                 ["PVAL_%s_BURDEN_DNDS" % c for c in DNDS_CLASSES] +
+                 ["PVAL_SYN_SEL_NB", "PVAL_MIS_SEL_NB", "PVAL_TRUNC_SEL_NB", "PVAL_NONSYN_SEL_NB"])
+
+
+def gene_dnds_sel(alpha, theta, pi6, obs6, device="cuda:0", stream=None):
+    """Secondary gene tests in one launch: float64 [24, E] with rows DNDS_OUT_ROWS (include/dig_b200.h)."""
+    dev = torch.device(device)
+    a, t = _dev(alpha, torch.float64, dev).contiguous(), _dev(theta, torch.float64, dev).contiguous()
+    p6, o6 = _dev(pi6, torch.float64, dev).contiguous(), _dev(obs6, torch.float64, dev).contiguous()
+    E = a.numel()
+    assert p6.shape == (E, 6) and o6.shape == (E, 6)
+    out = torch.empty((len(DNDS_OUT_ROWS), E), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_gene_dnds_sel", a.data_ptr(), t.data_ptr(), p6.data_ptr(), o6.data_ptr(), E, out.data_ptr(),
+                  _stream(dev, stream))
+    return out
+
+
+def selection_coefficient(obs, exp, alpha=None, theta=None, pi=None, device="cuda:0", stream=None):
+    """SEL = (OBS + 1e-16) / (EXP + 1e-16) and (when alpha/theta/pi are given) its LLR p-value."""
+    dev = torch.device(device)
+    o, e = _dev(obs, torch.float64, dev).contiguous(), _dev(exp, torch.float64, dev).contiguous()
+    want_p = alpha is not None
+    a, t, p = ((_dev(x, torch.float64, dev).contiguous() for x in (alpha, theta, pi)) if want_p else (None, None, None))
+    sel = torch.empty_like(o)
+    pval = torch.empty_like(o) if want_p else None
+    with torch.cuda.device(dev):
+        _lib.call("dig_selection_coefficient", o.data_ptr(), e.data_ptr(), _ptr(a), _ptr(t), _ptr(p), o.numel(),
+                  sel.data_ptr(), _ptr(pval), _stream(dev, stream))
+    return sel, pval

@@ -245,6 +245,25 @@ int dig_gene_burden_test(const double *mu_d, const double *sigma_d, const double
                          double n_syn, double scale_factor, double *out_d, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * Secondary gene tests (commented out of run_gene_model at transfer_tools.py:833-853 but part of
+ * the reference's API).  pi6_d / obs6_d are [n_gene, 6] in the order SYN, MIS, NONS, SPL, TRUNC, NONSYN; alpha_d /
+ * theta_d the transferred (scaled) gamma parameters.
+ * dig_gene_dnds_sel: out_d [24, n_gene] rows
+ *   0-5   EXP_x = ALPHA*THETA*Pi_x                                  (gene_expected_muts_dnds, :363-392)
+ *   6     T_SYN = _mle_t(OBS_SYN, 1, ALPHA, THETA*Pi_SYN)           (:1263-1271)
+ *   7     MRFOLD = max(1e-10, T_SYN / EXP_SYN)                      (:1273-1276)
+ *   8-13  EXP_x_ML = EXP_x * MRFOLD
+ *   14-19 PVAL_x_BURDEN_DNDS = nb_pvalue_greater_midp(OBS_x, ALPHA, 1/(EXP_x_ML/ALPHA + 1))   (:617-653)
+ *   20-23 PVAL_{SYN,MIS,TRUNC,NONSYN}_SEL_NB = chi2.sf(-2(ll0 - ll_k), df 1,1,1,2)            (_llr_test_nb, :1172-1214)
+ * dig_selection_coefficient: SEL = (OBS + 1e-16)/(EXP + 1e-16) and, when pval_d is given, the LLR p-value of
+ *   selection_coefficient (:1279-1292).
+ */
+int dig_gene_dnds_sel(const double *alpha_d, const double *theta_d, const double *pi6_d, const double *obs6_d,
+                      int64_t n_gene, double *out_d, void *stream);
+int dig_selection_coefficient(const double *obs_d, const double *exp_d, const double *alpha_d, const double *theta_d,
+                              const double *pi_d, int64_t n, double *sel_d, double *pval_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * K8: per-position / per-bin hotspot test (secondary path of the reference).
  * dig_region_prob_norm replaces the normaliser of base_probabilities_by_region (sequence_tools.py:292-317,
  *   `probs / np.sum(probs)`): norm[r] = sum_k counts[r,k] * s_prob[k], counts = dig_count_contexts of the same

@@ -588,3 +588,50 @@ def window_objectives(df_mut, idx, max_muts_per_elt_per_sample=None, sample_filt
     df_cnt = df_idx.merge(df_elt, on='ELT', how='left')
     df_cnt.loc[df_cnt.OBS_SNV.isna(), 'OBS_SNV'] = 0
     return df_cnt.OBS_SNV.astype(int).values.astype(np.int64)
+
+
+# ----------------------------------------------------------------------------
+# secondary gene tests
+# ----------------------------------------------------------------------------
+
+def gene_dnds_sel(alpha, theta, pi6, obs6):
+    """gene_expected_muts_dnds, gene_pvalue_burden_dnds, gene_pvalue_sel_nb (transfer_tools.py:363-392, :617-676,
+    :1172-1214, :1253-1276), vectorised with SciPy.  pi6 / obs6 columns: SYN, MIS, NONS, SPL, TRUNC, NONSYN.
+    Returns a dict of [n] arrays with the reference's column names."""
+    import scipy.stats
+    alpha, theta = np.asarray(alpha, dtype=np.float64), np.asarray(theta, dtype=np.float64)
+    pi6, obs6 = np.asarray(pi6, dtype=np.float64), np.asarray(obs6, dtype=np.float64)
+    cls = ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")
+    out = {}
+    with np.errstate(all="ignore"):
+        for j, c in enumerate(cls):
+            out["EXP_" + c] = alpha * theta * pi6[:, j]
+        th = theta * pi6[:, 0]
+        tml = (obs6[:, 0] + alpha - 1) / (1 + (1 / th))
+        lo = alpha * th
+        tml = np.where(alpha <= 1, np.where(tml > lo, tml, lo), tml)             # Python max(lo, tml)
+        out["T_SYN"] = tml
+        ratio = tml / out["EXP_SYN"]
+        out["MRFOLD"] = np.where(ratio > 1e-10, ratio, 1e-10)                    # Python max(1e-10, ratio)
+        for j, c in enumerate(cls):
+            out["EXP_%s_ML" % c] = out["EXP_" + c] * out["MRFOLD"]
+            out["PVAL_%s_BURDEN_DNDS" % c] = nb_pvalue_greater_midp(obs6[:, j], alpha, 1 / (out["EXP_%s_ML" % c] / alpha + 1))
+        ll = lambda k, t: scipy.stats.nbinom.logpmf(k, alpha, 1 / (1 + t))
+        l0 = {j: ll(obs6[:, j], theta * pi6[:, j] * out["MRFOLD"]) for j in (0, 1, 4)}
+        l1 = {j: ll(obs6[:, j], obs6[:, j] / alpha) for j in (0, 1, 4)}
+        ll0 = l0[0] + l0[1] + l0[4]
+        out["PVAL_SYN_SEL_NB"] = scipy.stats.chi2.sf(-2 * (ll0 - (l1[0] + l0[1] + l0[4])), df=1)
+        out["PVAL_MIS_SEL_NB"] = scipy.stats.chi2.sf(-2 * (ll0 - (l0[0] + l1[1] + l0[4])), df=1)
+        out["PVAL_TRUNC_SEL_NB"] = scipy.stats.chi2.sf(-2 * (ll0 - (l0[0] + l0[1] + l1[4])), df=1)
+        out["PVAL_NONSYN_SEL_NB"] = scipy.stats.chi2.sf(-2 * (ll0 - (l0[0] + l1[1] + l1[4])), df=2)
+    return out
+
+
+def selection_coefficient(obs, exp, alpha, theta, pi):
+    """selection_coefficient (transfer_tools.py:1279-1292): (SEL, PVAL_SEL)."""
+    import scipy.stats
+    with np.errstate(all="ignore"):
+        sel = (obs + 1e-16) / (exp + 1e-16)
+        ll0 = scipy.stats.nbinom.logpmf(obs, alpha, 1 / (1 + theta * pi))
+        ll1 = scipy.stats.nbinom.logpmf(obs, alpha, 1 / (1 + theta * pi * sel))
+        return sel, scipy.stats.chi2.sf(-2 * (ll0 - ll1), df=1)

@@ -27,6 +27,17 @@ def gene_driver(args):
     _save(df_dig, args)
 
 
+def target_driver(args):
+    """Reference scripts/DigDriver.py:45-65."""
+    print('Running MSK-IMPACT driver detection')
+    os.makedirs(args.outdir, exist_ok=True)
+    df_dig = transfer_tools.run_target_model(
+        args.fmut, args.model, scale_by_sample=args.scale_by_samples, panel=args.panel,
+        max_muts_per_sample=args.max_muts_per_sample, max_muts_per_gene_per_sample=args.max_muts_per_gene_per_sample,
+        cgc_genes=args.cgc_genes, scale_factor=args.scale_factor_manual, drop_synonymous=False)
+    _save(df_dig, args)
+
+
 def _scale_flags(args):
     args.scale_by_expectation = not (args.scale_type or args.scale_factor_manual)
     if args.scale_factor_manual or args.scale_factor_indel_manual:
@@ -101,6 +112,17 @@ def parse_args(text=None):
     a.add_argument('--cgc-genes', choices=['CGC_ALL', 'CGC_ONC', 'CGC_TSG'], default=False)
     a.add_argument('--no-pval-burden', dest='pval_burden', action='store_false', default=True)
     a.set_defaults(func=gene_driver)
+    b = sub.add_parser('targetDriver', help='detect driver genes in an MSK-IMPACT targeted sequencing cohort.')
+    b.add_argument('fmut', type=str)
+    b.add_argument('model', type=str)
+    _common_out(b)
+    b.add_argument('--panel', type=str,
+                   choices=['MSK_230', 'MSK_341', 'MSK_410', 'MSK_468', 'metabric_173', 'ucla_1202'])
+    b.add_argument('--max-muts-per-gene-per-sample', type=int, default=3e9)
+    b.add_argument('--scale-by-samples', action='store_true', default=False)
+    b.add_argument('--scale-factor-manual', default=None, type=float)
+    b.add_argument('--cgc-genes', choices=['CGC_ALL', 'CGC_ONC', 'CGC_TSG'], default=False)
+    b.set_defaults(func=target_driver)
     c = sub.add_parser('elementDriver', help='detect drivers in user-defined elements')
     c.add_argument('fmut', type=str)
     c.add_argument('model', type=str)

@@ -384,3 +384,50 @@ def test_cli_flow_matches_oracle(workdir, oracle):
     t_ind = obs.OBS_INDEL.values[null].sum() / (wantg["P_INDEL"][null] * a_g[null] * t_g[null]).sum()
     _, pgi = oracle.burden_test(obs.OBS_INDEL.values.astype(float), a_g, t_g * t_ind, wantg["P_INDEL"])
     assert_pvals_close(gres.PVAL_INDEL_BURDEN.values, pgi)
+
+
+def test_target_driver_cli(workdir, oracle, tmp_path):
+    """DigDriver.py targetDriver (run_target_model, transfer_tools.py:876-967) on the project of the CLI flow test:
+    panel restriction, panel scale factor N_MUT / N_MUT_<panel> from the archive attributes, burden tests."""
+    from digdriver_b200 import storage
+    d = workdir["dir"]
+    p = lambda x: str(d / x)
+    if not os.path.exists(p("annot.tsv")) or not storage.Store(p("pretrained"), "r").has("genic_model"):
+        test_cli_flow_matches_oracle(workdir, oracle)
+    genes = [g[0] for g in workdir["genes"]]
+    panel = genes[::2]
+    (tmp_path / "genes_MSK_341.txt").write_text("\n".join(panel) + "\n")
+    storage.Store(p("pretrained"), "a").set_attrs(N_MUT_MSK_341=1234, N_SAMPLE_MSK_341=77, N_MUT_SAMPLE_MSK_341=999)
+    old = os.environ.get("DIG_DATA_DIR")
+    os.environ["DIG_DATA_DIR"] = str(tmp_path)
+    try:
+        _cli("DigDriver", "targetDriver %s %s --panel MSK_341 --outpfx targ --outdir %s" %
+             (p("annot.tsv"), p("pretrained"), p("out")))
+    finally:
+        os.environ["DIG_DATA_DIR"] = old
+    res = pd.read_table(p("out/targ.results.txt"), index_col=0)
+    assert sorted(res.index) == sorted(panel)
+    res = res.loc[panel]
+    raw = pd.read_table(p("annot.tsv"), header=None)
+    raw.columns = ["CHROM", "START", "END", "REF", "ALT", "SAMPLE", "GENE", "ANNOT", "MUT_TYPE", "CONTEXT"]
+    cds = raw[raw.GENE != "."]
+    cds = pd.concat([cds[cds.ANNOT != "INDEL"], cds[cds.ANNOT == "INDEL"].drop_duplicates(
+        ["CHROM", "START", "END", "REF", "ALT", "GENE"])])
+    cds = cds[cds.GENE.isin(panel)]
+    dd = raw.drop_duplicates(["CHROM", "START", "END", "REF", "ALT", "SAMPLE"])
+    dd = pd.concat([dd[dd.ANNOT != "INDEL"], dd[dd.ANNOT == "INDEL"].drop_duplicates(
+        ["CHROM", "START", "END", "REF", "ALT", "GENE"])])
+    dd = dd[~dd.ANNOT.isin(["Noncoding", "Synonymous", "Essential_Splice"]) & dd.GENE.isin(panel)]
+    cj = len(dd) / 1234
+    gm = storage.Store(p("pretrained"), "r").read_table("genic_model")
+    gm = gm.set_index(gm.GENE).loc[panel]
+    a_g, t_g = oracle.normal_params_to_gamma(gm.MU.values, gm.SIGMA.values)
+    obs = oracle.gene_observed_counts(cds).reindex(panel).fillna(0)
+    pis = {"SYN": gm.P_SILENT.values, "MIS": gm.P_MIS.values, "TRUNC": gm.P_NONS.values + gm.P_SPLICE.values}
+    ks = {"SYN": obs.OBS_SYN.values.astype(float), "MIS": obs.OBS_MIS.values.astype(float),
+          "TRUNC": (obs.OBS_NONS + obs.OBS_SPL).values.astype(float)}
+    for c in ("SYN", "MIS", "TRUNC"):
+        e_, p_ = oracle.burden_test(ks[c], a_g, t_g * cj, pis[c])
+        assert np.array_equal(res["OBS_" + c].values, ks[c]), c
+        np.testing.assert_allclose(res["EXP_" + c].values, e_, rtol=1e-9)
+        assert_pvals_close(res["PVAL_%s_BURDEN" % c].values, p_)

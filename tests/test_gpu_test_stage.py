@@ -339,3 +339,42 @@ def test_fused_gene_test_kernels_golden():
     # scale by expectation: cj = n_syn / sums[0]
     out2 = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, 1234.0).cpu().numpy()
     np.testing.assert_allclose(out2[22], z["pre_THETA"] * (1234.0 / s[0]), rtol=1e-14)
+
+
+def test_secondary_gene_tests_golden():
+    """f-4: dig_gene_dnds_sel / dig_selection_coefficient and the DataFrame-level functions of transfer_tools against
+    the outputs of the unmodified reference (gene_expected_muts_dnds, gene_pvalue_burden_dnds, gene_pvalue_sel_nb,
+    selection_coefficient).  Expectations rel. 1e-9 (measured: bit-identical), p-values |dlog10 p| <= 1e-6."""
+    import pandas as pd
+    from digdriver_b200 import kernels
+    from digdriver_b200.driver_model import transfer_tools as tt
+    dev = torch.device("cuda:0")
+    z = golden("secondary")
+    cls = kernels.DNDS_CLASSES
+    pi6 = np.stack([z["in_Pi_" + c] for c in cls], axis=1)
+    obs6 = np.stack([z["in_OBS_" + c] for c in cls], axis=1)
+    out = kernels.gene_dnds_sel(z["in_ALPHA"], z["in_THETA"], pi6, obs6, dev).cpu().numpy()
+    for name, row in zip(kernels.DNDS_OUT_ROWS, out):
+        want = z["out_" + name]
+        if name.startswith("PVAL"):
+            assert_pvals_close(row, want)
+        else:
+            assert np.array_equal(np.isnan(row), np.isnan(want)), name
+            m = ~np.isnan(want)
+            assert np.allclose(row[m], want[m], rtol=1e-9, atol=0), name
+    # DataFrame-level API, called in the reference's order
+    df = pd.DataFrame({k[3:]: z[k] for k in z.files if k.startswith("in_")})
+    df = tt.gene_expected_muts_dnds(df)
+    df = tt.gene_pvalue_burden_dnds(df)
+    df = tt.gene_pvalue_sel_nb(df)
+    for c in ("SYN", "MIS", "TRUNC"):
+        tt.selection_coefficient(df, c, pvalue=True)
+    for k in z.files:
+        if not k.startswith("out_"):
+            continue
+        got, want = df[k[4:]].values, z[k]
+        if k[4:].startswith("PVAL"):
+            assert_pvals_close(got, want)
+        else:
+            m = ~np.isnan(want)
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and np.allclose(got[m], want[m], rtol=1e-9, atol=0), k

@@ -225,3 +225,27 @@ def test_window_objectives_oracle_matches_reference_filters(oracle):
         got = oracle.window_objectives(df.copy(), z["idx"], cap, std, mx)
         assert np.array_equal(got, z["y_%d" % i]), i
     assert z["y_0"].sum() > z["y_3"].sum() > 0 and np.array_equal(z["y_0"], z["y_1"])   # the cap quirk: no effect
+
+
+def _secondary_inputs(z):
+    cls = ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")
+    pi6 = np.stack([z["in_Pi_" + c] for c in cls], axis=1)
+    obs6 = np.stack([z["in_OBS_" + c] for c in cls], axis=1)
+    return z["in_ALPHA"], z["in_THETA"], pi6, obs6
+
+
+def test_secondary_gene_tests_oracle_matches_reference_golden(oracle):
+    """f-4: dN/dS expectations, dN/dS burden p-values, LLR selection tests and selection coefficients."""
+    z = golden("secondary")
+    alpha, theta, pi6, obs6 = _secondary_inputs(z)
+    got = oracle.gene_dnds_sel(alpha, theta, pi6, obs6)
+    for k, v in got.items():
+        want = z["out_" + k]
+        if k.startswith("PVAL"):
+            assert_pvals_close(v, want, tol=1e-9)
+        else:
+            assert np.array_equal(v, want, equal_nan=True), k
+    for j, c in ((0, "SYN"), (1, "MIS"), (4, "TRUNC")):
+        sel, pv = oracle.selection_coefficient(obs6[:, j], z["out_EXP_" + c], alpha, theta, pi6[:, j])
+        assert np.array_equal(sel, z["out_SEL_" + c], equal_nan=True)
+        assert_pvals_close(pv, z["out_PVAL_%s_SEL" % c], tol=1e-9)
