@@ -31,7 +31,7 @@ __device__ __forceinline__ int revcomp3(int c)
 __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 
-__global__ void __launch_bounds__(TW * 32) transfer_kernel(
+__global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
     const int32_t *__restrict__ elt_chrom, const int8_t *__restrict__ elt_strand,
     const int64_t *__restrict__ blk_ptr, const int64_t *__restrict__ blk_start,
     const int64_t *__restrict__ blk_end, int64_t n_elt, int64_t window, const int64_t *__restrict__ win_map_off,
@@ -112,16 +112,21 @@ __global__ void __launch_bounds__(TW * 32) transfer_kernel(
         const int64_t map0 = win_map_off[c];
         const int64_t map_n = win_map_off[c + 1] - map0;
         for (int w = 0; ok && w < words; ++w) {
-            uint32_t bits = bitmap[w];
-            while (bits) {
-                const int bit = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int64_t wi = wmin + ((int64_t)w << 5) + bit;
-                const int32_t row = (wi >= 0 && wi < map_n) ? __ldg(win_map + map0 + wi) : -1;
-                if (row < 0) {
-                    if (lane == 0) atomicMax(status, 2);     // the reference raises KeyError here
-                    continue;
-                }
+            const uint32_t bits = bitmap[w];
+            const int cnt = __popc(bits);
+            if (cnt == 0) continue;
+            // the rows of all (up to 32) set windows of this word are looked up by 32 lanes at once; the gather loop
+            // below then has no load that depends on a previous load, so several windows are in flight together
+            int32_t my_row = -1;
+            if (lane < cnt) {
+                const int64_t wi = wmin + ((int64_t)w << 5) + (int64_t)__fns(bits, 0, lane + 1);
+                my_row = (wi >= 0 && wi < map_n) ? __ldg(win_map + map0 + wi) : -1;
+            }
+            if (__any_sync(0xffffffffu, lane < cnt && my_row < 0) && lane == 0) atomicMax(status, 2);   // KeyError in the reference
+#pragma unroll 4
+            for (int k = 0; k < cnt; ++k) {
+                const int32_t row = __shfl_sync(0xffffffffu, my_row, k);
+                if (row < 0) continue;
                 ++nw;
                 const int32_t *wc = win_counts + (int64_t)row * 64;
                 r_lo += (double)__ldg(wc + lane);
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(TW * 32) transfer_kernel(
         __syncwarp();
         const double rsum = warp_sum(r_lo + r_hi);
         const double lsum = warp_sum(l_lo + l_hi);
+
         // ---- per cohort: denom = sum_j d_pr[j] R192[j];  P[col] = sum_j (d_pr[j]/denom) L[j][col]
         for (int ci = 0; ci < n_cohort; ++ci) {
             const double *dp = d_pr + (int64_t)ci * 192;
@@ -177,6 +183,9 @@ __global__ void __launch_bounds__(TW * 32) transfer_kernel(
                 part += __ldg(dp + j) * r64[j / 3];
             }
             const double denom = warp_sum(part);
+            double wgt[6];                                    // d_pr[j] / denom, shared by every column
+#pragma unroll
+            for (int t = 0; t < 6; ++t) wgt[t] = __ldg(dp + lane + 32 * t) / denom;
             for (int col = 0; col < n_col; ++col) {
                 double acc = 0.0;
 #pragma unroll
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(TW * 32) transfer_kernel(
                     const int j = lane + 32 * t;
                     const double Lj = blk_counts != nullptr ? l64[j / 3]
                                                             : __ldg(L_elt + ((int64_t)e * 192 + j) * n_col + col);
-                    acc += (__ldg(dp + j) / denom) * Lj;
+                    acc += wgt[t] * Lj;
                 }
                 acc = warp_sum(acc);
                 if (lane == 0) p_out[((int64_t)ci * n_elt + e) * n_col + col] = acc;
@@ -244,7 +253,7 @@ extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *el
     }
     DIG_CUDA(cudaFuncSetAttribute(transfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (n_elt + TW - 1) / TW;
-    const int64_t cap = (int64_t)dig::sm_count() * 8;
+    const int64_t cap = (int64_t)dig::sm_count() * 64;      // ~one element per warp: the hardware scheduler balances long genes
     if (blocks > cap) blocks = cap;
     transfer_kernel<<<(unsigned)blocks, TW * 32, smem, st>>>(
         elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, win_map_off_d, win_map_d,
