@@ -43,6 +43,15 @@ B_PER_BASE_FUSED = 0.25 + 0.125 + 4.0 * (1024 + 64) / WINDOW  # both tables writ
 B_PER_BASE_K64 = 0.25 + 0.125 + 4.0 * 64 / WINDOW
 
 
+_JSON_OUT = None
+
+
+def emit_json(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -491,7 +500,7 @@ def run_reference(args):
             "config": workload_config(args.bases, args.gpus),
             "cpu_baseline": {"value": v, "unit": "bases/s", "cores": n_proc, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def workload_config(bases, n_gpus):
@@ -510,6 +519,12 @@ def workload_config(bases, n_gpus):
 
 def main():
     args = parse_args()
+    # Only the JSON line may appear on stdout: library banners (NCCL prints its version to stdout under torchrun)
+    # and the prints of helper code are sent to stderr for the whole run.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -654,7 +669,7 @@ def main():
             "cuda_graph": {"test_stage_captured": stepper.graph is not None, "error": stepper.error},
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
-    print(json.dumps(line))
+    emit_json(line)
     finish()
 
 
