@@ -75,23 +75,27 @@ __global__ void __launch_bounds__(256) position_obs_kernel(
     }
 }
 
-// S_prob of the k-mer centred on global position g, 0 when it touches a non-ACGT base
+// S_prob of the k-mer centred on global position g, 0 when it touches a non-ACGT base.  The k-mer (at most 6 bases)
+// lies inside two consecutive packed words and its N bits inside two consecutive mask words: four loads, one 64-bit
+// shift each.  last_p / last_m are the last valid word indices: a k-mer that ends in the last word never needs the
+// (clamped) second word.
 __device__ __forceinline__ double kmer_prob(const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask,
-                                            int64_t g, int n_up, int n_down, const double *s_prob_s)
+                                            int64_t g, int n_up, int klen, int64_t last_p, int64_t last_m,
+                                            const double *s_prob_s)
 {
-    uint32_t key = 0;
-    bool bad = false;
-    for (int t = -n_up; t <= n_down; ++t) {
-        const int64_t gg = g + t;
-        const uint32_t code = (__ldg(p2 + (gg >> 4)) >> (30 - 2 * (int)(gg & 15))) & 3u;
-        bad |= ((__ldg(nmask + (gg >> 5)) >> (31 - (int)(gg & 31))) & 1u) != 0u;
-        key = (key << 2) | code;
-    }
+    const int64_t f = g - n_up;                                   // first base of the k-mer
+    const int64_t w = f >> 4;
+    const unsigned long long pk = ((unsigned long long)__ldg(p2 + w) << 32) | __ldg(p2 + (w < last_p ? w + 1 : last_p));
+    const uint32_t key = (uint32_t)(pk >> (64 - 2 * ((int)(f & 15) + klen))) & ((1u << (2 * klen)) - 1u);
+    const int64_t m = f >> 5;
+    const unsigned long long mk = ((unsigned long long)__ldg(nmask + m) << 32) | __ldg(nmask + (m < last_m ? m + 1 : last_m));
+    const uint32_t bad = (uint32_t)(mk >> (64 - ((int)(f & 31) + klen))) & ((1u << klen) - 1u);
     return bad ? 0.0 : s_prob_s[key];
 }
 
-__global__ void __launch_bounds__(256) position_test_kernel(
-    const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask, const int64_t *__restrict__ chrom_off,
+__global__ void __launch_bounds__(256, 4) position_test_kernel(
+    const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask, int64_t last_p, int64_t last_m,
+    const int64_t *__restrict__ chrom_off,
     const int64_t *__restrict__ chrom_len, const int32_t *__restrict__ reg_chrom, const int64_t *__restrict__ reg_start,
     const int64_t *__restrict__ reg_end, int64_t n_reg, int n_up, int n_down, const double *__restrict__ s_prob,
     const double *__restrict__ norm, const double *__restrict__ mu, const double *__restrict__ sigma, int binsize,
@@ -99,7 +103,8 @@ __global__ void __launch_bounds__(256) position_test_kernel(
     double *__restrict__ pt_out, double *__restrict__ exp_out, double *__restrict__ pos_out)
 {
     extern __shared__ double s_prob_s[];
-    const int K = 1 << (2 * (n_up + n_down + 1));
+    const int klen = n_up + n_down + 1;
+    const int K = 1 << (2 * klen);
     for (int k = threadIdx.x; k < K; k += blockDim.x) s_prob_s[k] = s_prob[k];
     __syncthreads();
     for (int64_t r = blockIdx.x; r < n_reg; r += gridDim.x) {
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(256) position_test_kernel(
             const int64_t g1 = g0 + binsize < sp.ge ? g0 + binsize : sp.ge;
             double pt = 0.0;
             // the reference normalises every position first and then sums the bin (nb_model.py:165)
-            for (int64_t g = g0; g < g1; ++g) pt += __ddiv_rn(kmer_prob(p2, nmask, g, n_up, n_down, s_prob_s), nrm);
+            for (int64_t g = g0; g < g1; ++g) pt += __ddiv_rn(kmer_prob(p2, nmask, g, n_up, klen, last_p, last_m, s_prob_s), nrm);
             const double k = (double)obs[b0 + b];
             const double p = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(pt, theta), 1.0));
             pval[b0 + b] = nb_exact(k, alpha, p);
@@ -194,8 +199,8 @@ int dig_position_test(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_
     int64_t blocks = (int64_t)dig::sm_count() * 8;
     if (blocks > n_reg) blocks = n_reg;
     position_test_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
-        packed2_d, nmask_d, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d, n_reg, n_up, n_down,
-        s_prob_d, norm_d, mu_d, sigma_d, binsize, bin_ptr_d, obs_d, pval_d, pt_d, exp_d, pos_d);
+        packed2_d, nmask_d, (((n_bases + 31) >> 5) << 1) - 1, ((n_bases + 31) >> 5) - 1, chrom_off_d, chrom_len_d,
+        reg_chrom_d, reg_start_d, reg_end_d, n_reg, n_up, n_down, s_prob_d, norm_d, mu_d, sigma_d, binsize, bin_ptr_d, obs_d, pval_d, pt_d, exp_d, pos_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

@@ -261,3 +261,37 @@ def test_hexamer_pair_scan_adversarial(dev, oracle):
     finally:
         lib.dig_debug_set_scan_variant(0)
         lib.dig_debug_set_totals_limit_kb(ctypes.c_uint(1 << 20))
+
+
+def test_empty_inputs_through_the_c_abi(dev):
+    """Zero regions / mutations / elements / p-values: every entry point returns cleanly with empty (or zeroed)
+    outputs instead of launching an empty grid or touching a null pointer."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.genome import Genome, DeviceGenome
+    dg = DeviceGenome.from_genome(Genome(["chr1"], [np.frombuffer(b"ACGTNACGTACGTTTGACA" * 20, dtype=np.uint8)]), dev)
+    e32, e64 = np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64)
+    for (u, d) in ((1, 1), (2, 2), (0, 3)):
+        c, t = kernels.count_contexts(dg, e32, e64, e64, u, d, want_totals=True)
+        assert c.shape == (0, 4 ** (u + d + 1)) and int(t.sum()) == 0
+    c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, e32, e64, e64, want_totals=True)
+    assert c5.shape == (0, 1024) and c3.shape == (0, 64) and int(t5.sum()) == 0 and int(t3.sum()) == 0
+    # regions that contain no centre at all (length 0, beyond the chromosome end) give zero rows
+    c5, c3, _, _ = kernels.count_contexts_fused53(dg, [0, 0, 0], [5, 380, 1000], [5, 380, 2000])
+    assert int(c5.sum()) == 0 and int(c3.sum()) == 0
+    assert kernels.mutation_contexts(dg, e32, e64, np.zeros(0, dtype=np.uint8), 1, 1).numel() == 0
+    assert int(kernels.substitution_counts(torch.zeros(0, dtype=torch.int32, device=dev), np.zeros(0, dtype=np.uint8), 1, 1).sum()) == 0
+    f = np.zeros(0)
+    assert kernels.nb_pvalue_greater_midp(f, f, f, dev).numel() == 0
+    assert kernels.nb_pvalue_exact(f, f, f, dev).numel() == 0
+    exp, pv = kernels.nb_burden_test(f, f, f, f, dev)
+    assert exp.numel() == 0 and pv.numel() == 0
+    obs, nsamp = kernels.tabulate_genes(e32, e32, np.zeros(0, dtype=np.uint8), 7, device=dev)
+    assert obs.shape == (7, 5) and int(obs.sum()) == 0 and int(nsamp.sum()) == 0
+    obs, stot = kernels.tabulate_elements(np.array([10], dtype=np.int64), np.array([20], dtype=np.int64), [0], e64, e64,
+                                          e32, np.zeros(0, dtype=np.uint8), 1, 3, device=dev)
+    assert obs.shape == (1, 3) and int(obs.sum()) == 0 and int(stot.sum()) == 0
+    out = kernels.position_test(dg, e32, e64, e64, f, f, np.ones(1024), e32, e64, 2, 2, 1)
+    assert out["pval"].numel() == 0 and out["obs"].numel() == 0
+    out = kernels.position_test(dg, [0], [0], [40], [3.0], [1.0], np.ones(64), e32, e64, 1, 1, 7)
+    assert out["pval"].numel() == 6 and int(out["obs"].sum()) == 0           # 39 positions in bins of 7
+    assert kernels.gene_dnds_sel(f, f, np.zeros((0, 6)), np.zeros((0, 6)), dev).shape == (24, 0)
