@@ -9,19 +9,36 @@ namespace {
 
 // 4 ASCII bytes (little endian: lowest byte = first base) -> 8 bits of 2-bit codes, first base
 // most significant, and 4 validity bits in the same order (1 = not ACGT).
+//
+// The kernel is ALU-bound (the byte compares of the obvious formulation are emulated), so everything is done on
+// whole 32-bit words:
+//  * validity: upper-cased letters are 0x41 0x43 0x47 0x54, i.e. (c >> 3) must equal LUT[c & 7] with
+//    LUT = {1: 8, 3: 8, 7: 8, 4: 10}; the 8-entry byte LUT is ONE PRMT for all four bytes, a zero-byte test of
+//    ((c >> 3) ^ LUT[c & 7]) gives the four validity bits;
+//  * codes: ((c >> 1) & 3) ^ ((c >> 2) & 1) -> 0,1,2,3; the four 2-bit fields and the four validity bits are gathered
+//    with one multiply each (no partial product of the magic constants carries into the result byte);
+//  * non-ACGT letters other than N are counted only in words that contain an invalid byte (N runs are rare).
 __device__ __forceinline__ void convert4(uint32_t w, uint32_t &codes8, uint32_t &n4, uint32_t &other)
 {
     const uint32_t up = w & 0xDFDFDFDFu;                       // upper-case
-    const uint32_t ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) |
-                        __vcmpeq4(up, 0x47474747u) | __vcmpeq4(up, 0x54545454u);
-    const uint32_t isn = __vcmpeq4(up, 0x4E4E4E4Eu);           // 'N' / 'n'
-    // A=0x41 C=0x43 G=0x47 T=0x54: ((c>>1)&3) ^ ((c>>2)&1) -> 0,1,2,3
+    // selector nibbles (c & 7) of the four bytes packed into 16 bits
+    const uint32_t lo3 = w & 0x07070707u;
+    const uint32_t y = lo3 | (lo3 >> 4);
+    const uint32_t sel = (y & 0xFFu) | ((y >> 8) & 0xFF00u);
+    // LUT bytes 0..7 = FF 08 FF 08 0A FF FF 08 (index = c & 7)
+    const uint32_t want = __byte_perm(0x08FF08FFu, 0x08FFFF0Au, sel);
+    const uint32_t d = ((up >> 3) & 0x1F1F1F1Fu) ^ want;       // byte == 0 <=> valid letter
+    const uint32_t nz = ((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d; // bit 7 of each byte: byte != 0
+    const uint32_t bad = (nz >> 7) & 0x01010101u;              // 1 per invalid byte
     uint32_t t = ((w >> 1) & 0x03030303u) ^ ((w >> 2) & 0x01010101u);
-    t &= ok;                                                   // non-ACGT stored as 0
-    codes8 = ((t & 3u) << 6) | (((t >> 8) & 3u) << 4) | (((t >> 16) & 3u) << 2) | ((t >> 24) & 3u);
-    const uint32_t bad = ~ok;
-    n4 = ((bad & 1u) << 3) | (((bad >> 8) & 1u) << 2) | (((bad >> 16) & 1u) << 1) | ((bad >> 24) & 1u);
-    other += __popc(~(ok | isn) & 0x01010101u);
+    t &= (bad ^ 0x01010101u) * 3u;                             // non-ACGT stored as 0
+    codes8 = (t * 0x40100401u) >> 24;                          // t0<<6 | t1<<4 | t2<<2 | t3
+    n4 = (bad * 0x08040201u) >> 24;                            // b0<<3 | b1<<2 | b2<<1 | b3
+    if (bad) {
+        const uint32_t x = up ^ 0x4E4E4E4Eu;                   // byte == 0 <=> 'N' / 'n'
+        const uint32_t notn = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u;
+        other += __popc(bad & notn);
+    }
 }
 
 constexpr int PACK_UNROLL = 4;     // independent 128-bit loads in flight per thread
