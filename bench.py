@@ -65,6 +65,34 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------------
+# host placement
+# ------------------------------------------------------------------------------------------------
+
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA node its
+    GPU hangs off, so that the e2e leg's host<->device copies of eight ranks do not all cross the socket interconnect.
+    Returns a short description for the JSON line; never raises."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "numa node unknown for %s" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no allowed cpu on numa node %d" % node
+        os.sched_setaffinity(0, cpus)
+        return "gpu %s -> numa node %d (%d cpus)" % (bdf, node, len(cpus))
+    except Exception as exc:
+        return "not bound: %r" % (exc,)
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
 
@@ -538,6 +566,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    placement = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process, not bound"
     dist_ctx = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
@@ -667,6 +696,7 @@ def main():
             "config": workload_config(args.bases, world),
             "elements_tested_per_s": N_GENES * world / (ms_per_step * 1e-3),
             "cuda_graph": {"test_stage_captured": stepper.graph is not None, "error": stepper.error},
+            "host_placement": placement,
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     emit_json(line)

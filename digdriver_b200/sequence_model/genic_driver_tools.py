@@ -244,3 +244,56 @@ def sites_model_arrays(df_sites, region_model, win_counts64, d_pr):
         'ELT': elts, 'ELT_SIZE': elt_size, 'FLAG': res["FLAG"], 'R_SIZE': res["R_SIZE"], 'R_OBS': res["R_OBS"],
         'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"], 'MU_INDEL': res["MU"],
         'SIGMA_INDEL': res["SIGMA"], 'P_SUM': res["P"][:, 0], 'P_INDEL': p_indel})
+
+
+# --------------------------------------------------------------------------------------------
+# tiled model (reference :599-720): every tile is transferred from the ONE window that contains its start
+# --------------------------------------------------------------------------------------------
+
+def _index_transform(s):
+    """'chr1:100-200' -> 'region_1_100_200' (reference :721-725)."""
+    chrom = int(s.split(":")[0].lstrip("chr"))
+    start = int(s.split(":")[-1].split('-')[0])
+    end = int(s.split(":")[-1].split('-')[1])
+    return "region_{}_{}_{}".format(chrom, start, end)
+
+
+def tiled_model_arrays(elt_lst, L_table, region_model, win_counts64, d_pr):
+    """tiled_nonc_model (reference :599-690) on in-memory inputs, one K6 launch for all tiles.  elt_lst: tile names
+    'chr{c}:{s}-{e}'; L_table: DataFrame indexed by those names with the 192 substitution columns.
+
+    The reference locates the window as floor(start / 10000) * 10000 with the 10 000 hard-coded (:636) while the
+    window LENGTH comes from region_params: for any other window size its lookup raises KeyError, and so does this."""
+    elt_lst = list(elt_lst)
+    if int(region_model.window) != 10000 and len(elt_lst):
+        raise KeyError("tiled_nonc_model looks windows up on a 10000-base grid (genic_driver_tools.py:636); "
+                       "region_params uses window {}".format(region_model.window))
+    chrom = np.array([int(e.split(":")[0].lstrip("chr")) for e in elt_lst], dtype=np.int64)
+    start = np.array([int(e.split(":")[1].split("-")[0]) for e in elt_lst], dtype=np.int64)
+    E = len(elt_lst)
+    L = L_table.loc[elt_lst].values.astype(np.float64).reshape(E, 192)
+    # a 1-base block at the tile's start overlaps exactly the window that contains it
+    res = transfer_elements(region_model, win_counts64, d_pr, chrom, np.ones(E, dtype=np.int8), np.arange(E + 1),
+                            start, start + 1, L_elt=L.reshape(E, 192, 1))
+    elt_size = (L.sum(axis=1) / 3).astype(np.int64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_indel = elt_size / res["R_SIZE"].astype(np.float64)
+    return pd.DataFrame({
+        'ELT': [_index_transform(e) for e in elt_lst], 'ELT_SIZE': elt_size, 'FLAG': res["FLAG"],
+        'R_SIZE': res["R_SIZE"], 'R_OBS': res["R_OBS"], 'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"],
+        'MU_INDEL': res["MU"], 'SIGMA_INDEL': res["SIGMA"], 'P_SUM': res["P"][:, 0], 'P_INDEL': p_indel})
+
+
+def tiled_model_parallel(f_pretrained, f_nonc_data, save_key, N_procs=1):
+    """Reference :692-719 on the directory/HDF5 stores (L_counts written by DigPreprocess.py preprocess_tiled)."""
+    pre = storage.Store(f_pretrained, "r")
+    rm = RegionModel(pre.read_table('region_params'))
+    d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
+    data = storage.Store(f_nonc_data, "r")
+    wkey = 'window_{}'.format(rm.window)
+    win_idx = data.read_array('{}/full_window_si_index'.format(wkey))
+    win_vals = data.read_array('{}/full_window_si_values'.format(wkey))
+    key = {tuple(r): i for i, r in enumerate(map(tuple, win_idx))}
+    rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
+    L_table = data.read_table("{}/L_counts".format(save_key))
+    return tiled_model_arrays(L_table.index, L_table, rm, win_vals[rows].astype(np.int32), d_pr)

@@ -107,6 +107,13 @@ def preprocess_nonc_contexts(args):
     st.write_table('{}/{}/L_contexts'.format(wkey, args.save_key), L)
 
 
+def preprocess_tiled(args):
+    """Reference DigPreprocess.py:155-158: context counts of every tile of a bed file (no sub-elements)."""
+    print("Counting sequence contexts in regions")
+    L = sequence_tools.precount_region_contexts_parallel(args.f_nonc_bed, args.f_fasta, args.N_procs, args.window, False)
+    storage.Store(args.f_nonc_data, "a").write_table("{}/L_counts".format(args.save_key), L)
+
+
 def parse_args(text=None):
     parser = argparse.ArgumentParser(description='Preprocess genome and mutation files for use with Dig (B200).')
     sub = parser.add_subparsers()
@@ -140,6 +147,14 @@ def parse_args(text=None):
     e.add_argument('--n-procs', default=get_cpus(), type=int, dest='N_procs')
     e.add_argument('--window', type=int, default=10000)
     e.set_defaults(func=preprocess_nonc_contexts)
+    g = sub.add_parser('preprocess_tiled', help='preprocess a tiled genome')
+    g.add_argument('f_nonc_bed', help='bed file containing tiled elements')
+    g.add_argument('f_nonc_data', help='path to elements data store')
+    g.add_argument('f_fasta', help='genome fasta file')
+    g.add_argument('--n-procs', default=get_cpus(), type=int, dest='N_procs')
+    g.add_argument('window', help='size of windows', type=int, default=10000)
+    g.add_argument('save_key', help="key to save L_counts under in nonc_data")
+    g.set_defaults(func=preprocess_tiled)
     f = sub.add_parser('initialize_f_data', help='copy window counts into the element data store')
     f.add_argument('f_annot_data')
     f.add_argument('f_genome_counts')

@@ -49,6 +49,13 @@ def pretrain_nonc_model(args):
     storage.Store(args.output_h5 or args.f_pretrained, "a").write_table(args.save_key, df)
 
 
+def pretrain_tiled(args):
+    """Reference DigPretrain.py:271-278."""
+    df = genic_driver_tools.tiled_model_parallel(args.f_pretrained, args.f_element_data, args.save_key, args.N_procs)
+    print("saving")
+    storage.Store(args.output_h5 or args.f_pretrained, "a").write_table(args.save_key, df)
+
+
 def pretrain_genic_model(args):
     """Reference DigPretrain.py:225-236."""
     print('Running Genic model')
@@ -84,6 +91,13 @@ def parse_args(text=None):
     e.add_argument('--indels-direct', action='store_true', default=False)
     e.add_argument('--n-procs', default=get_cpus(), type=int, dest='N_procs')
     e.set_defaults(func=pretrain_nonc_model)
+    f = sub.add_parser('tiledModel', help='pretrain a model for the tiles of a tiled genome')
+    f.add_argument('f_pretrained')
+    f.add_argument('f_element_data')
+    f.add_argument('save_key')
+    f.add_argument('--output_h5')
+    f.add_argument('--n-procs', default=get_cpus(), type=int, dest='N_procs')
+    f.set_defaults(func=pretrain_tiled)
     return parser.parse_args(text.split()) if text else parser.parse_args()
 
 

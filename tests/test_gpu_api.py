@@ -431,3 +431,57 @@ def test_target_driver_cli(workdir, oracle, tmp_path):
         assert np.array_equal(res["OBS_" + c].values, ks[c]), c
         np.testing.assert_allclose(res["EXP_" + c].values, e_, rtol=1e-9)
         assert_pvals_close(res["PVAL_%s_BURDEN" % c].values, p_)
+
+
+def test_tiled_model_cli(workdir, oracle):
+    """DigPreprocess.py preprocess_tiled + DigPretrain.py tiledModel (tiled_nonc_model, genic_driver_tools.py:599-690):
+    every tile takes the parameters of the ONE window containing its start.  The flow project uses 1 kb windows, and
+    the reference's lookup is hard-wired to a 10 kb grid (:636) -> KeyError there; a 10 kb project checks the numbers."""
+    from digdriver_b200 import storage
+    from digdriver_b200.sequence_model import genic_driver_tools as gd
+    d = workdir["dir"]
+    p = lambda x: str(d / x)
+    if not storage.Store(p("pretrained"), "r").has("sequence_model_192") or not os.path.isdir(p("eltdata")):
+        test_cli_flow_matches_oracle(workdir, oracle)
+    rng = np.random.default_rng(31)
+    tiles = []
+    for c, L in ((1, 60_000), (2, 45_500)):
+        for s in range(2000, L - 4000, 1700):
+            tiles.append((c, s, s + int(rng.integers(50, 900)), "t%d_%d" % (c, s), 0, "+"))
+    pd.DataFrame(tiles).to_csv(p("tiles.bed"), sep="\t", header=False, index=False)
+    _cli("DigPreprocess", "preprocess_tiled %s %s %s 1000 TILES" % (p("tiles.bed"), p("eltdata"), p("genome.fa")))
+    with pytest.raises(KeyError):
+        _cli("DigPretrain", "tiledModel %s %s TILES" % (p("pretrained"), p("eltdata")))
+    # ---- a 10 kb region model over the same genome: numbers against the oracle's element transfer
+    W10 = 10_000
+    wins = np.array([(c, i, i + W10) for c, L in ((1, 60_000), (2, 45_500)) for i in range(0, L - W10, W10)])
+    rp = pd.DataFrame({"CHROM": wins[:, 0], "START": wins[:, 1], "END": wins[:, 2], "Y_TRUE": rng.poisson(20, len(wins)),
+                       "Y_PRED": rng.gamma(2.0, 10.0, len(wins)), "STD": rng.uniform(0.5, 5.0, len(wins)),
+                       "FLAG": rng.random(len(wins)) < 0.3}, index=["chr%d:%d-%d" % tuple(r) for r in wins])
+    off2 = 60_032
+    seq = np.full(off2 + 45_500, ord("N"), dtype=np.uint8)
+    seq[:60_000] = workdir["seqs"]["chr1"]
+    seq[off2:] = workdir["seqs"]["chr2"]
+    off, ln = np.array([0, off2]), np.array([60_000, 45_500])
+    wc, _ = oracle.count_regions(seq, off, ln, wins[:, 0] - 1, wins[:, 1], wins[:, 2], 1, 1)
+    d_pr = np.random.default_rng(1).lognormal(np.log(1e-6), 1.0, 192)
+    L_table = storage.Store(p("eltdata"), "r").read_table("TILES/L_counts")
+    have = {(int(c), int(s)) for c, s, _ in wins}
+    keep = [t for t in L_table.index
+            if (int(t.split(":")[0][3:]), int(t.split(":")[1].split("-")[0]) // W10 * W10) in have]
+    assert len(keep) > 40
+    got = gd.tiled_model_arrays(keep, L_table, gd.RegionModel(rp), wc.astype(np.int32), d_pr)
+    chrom = np.array([int(t.split(":")[0][3:]) for t in keep])
+    start = np.array([int(t.split(":")[1].split("-")[0]) for t in keep])
+    win_index = {(int(c), int(s)): i for i, (c, s, e) in enumerate(wins)}
+    want = oracle.element_transfer(chrom, np.ones(len(keep), dtype=np.int8), np.arange(len(keep) + 1), start, start + 1,
+                                   L_table.loc[keep].values, W10, win_index, wc, rp.Y_PRED.values, rp.STD.values,
+                                   rp.Y_TRUE.values.astype(float), rp.FLAG.values, d_pr)
+    assert list(got.ELT) == ["region_%d_%s" % (c, t.split(":")[1].replace("-", "_")) for c, t in zip(chrom, keep)]
+    for col in ("MU", "SIGMA", "P_SUM"):
+        np.testing.assert_allclose(got[col].values, want[col], rtol=1e-9, err_msg=col)
+    assert np.array_equal(got.R_SIZE.values, want["R_SIZE"]) and np.array_equal(got.FLAG.values, want["FLAG"])
+    assert np.array_equal(got.ELT_SIZE.values, (L_table.loc[keep].values.sum(axis=1) / 3).astype(np.int64))
+    # the window really is the one containing the tile's start
+    r = wc[[win_index[(c, s // W10 * W10)] for c, s in zip(chrom, start)]].sum(axis=1)
+    assert np.array_equal(got.R_SIZE.values, r)
