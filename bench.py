@@ -504,8 +504,9 @@ def run_reference(args):
     import multiprocessing as mp
     n_proc = max(1, min((os.cpu_count() or 2) - 2, 64))
     n_steps = args.warmup + args.steps
-    # about 2 s of pool work per step, the whole run bounded to ~2.5 minutes
-    wpp = 100
+    # about 3 s of pool work per step (1000 windows = 10 Mb per worker and context size), the whole run bounded
+    # to ~2.5 minutes
+    wpp = 1000
     pool = mp.Pool(n_proc) if n_proc > 1 else None
     vals, t0, sample = [], time.perf_counter(), ""
     for i in range(n_steps):
