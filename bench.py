@@ -245,6 +245,7 @@ class DeviceInputs:
         self.counts3 = torch.empty((n_win, 64), dtype=torch.int32, device=device)
         self.totals5 = torch.zeros(1024, dtype=torch.int64, device=device)
         self.totals3 = torch.zeros(64, dtype=torch.int64, device=device)
+        self.side_stream = torch.cuda.Stream(device)
 
 
 def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
@@ -270,6 +271,14 @@ def test_stage(dg, di, d, dist_ctx, sink=None):
     import torch
     from digdriver_b200 import kernels, pipeline
     dev = dg.device
+    # the observed counts (K5) depend on nothing else in the stage: they run on a second stream next to the
+    # K3 -> sequence model -> K6 chain (both are latency-bound and leave most SMs idle); inside the CUDA graph
+    # this becomes two parallel branches
+    main = torch.cuda.current_stream(dev)
+    side = di.side_stream
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        obs, nsamp = kernels.tabulate_genes(di.m_gene, di.m_sample, di.m_cls, N_GENES, device=dev, status_sink=sink)
     ctx = kernels.mutation_contexts(dg, di.m_chrom, di.m_pos, di.m_ref, 1, 1)
     sub = kernels.substitution_counts(ctx, di.m_alt, 1, 1)
     if dist_ctx is not None:
@@ -283,7 +292,10 @@ def test_stage(dg, di, d, dist_ctx, sink=None):
     pre = kernels.element_transfer(di.g_chrom, di.g_strand, di.g_ptr, di.g_bs, di.g_be, WINDOW, di.wmap_off,
                                    di.wmap, di.counts3, di.y_pred, di.std, di.y_true, di.flag, d_pr,
                                    L_elt=di.L, device=dev, max_span=di.max_span, status_sink=sink)
-    obs, nsamp = kernels.tabulate_genes(di.m_gene, di.m_sample, di.m_cls, N_GENES, device=dev, status_sink=sink)
+    main.wait_stream(side)
+    if not torch.cuda.is_current_stream_capturing():
+        obs.record_stream(main)          # allocated on the side stream, consumed on the main one
+        nsamp.record_stream(main)
     return pipeline.gene_burden_test(pre, obs, nsamp, d["n_syn"], collectives=dist_ctx)
 
 
