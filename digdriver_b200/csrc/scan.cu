@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(THREADS, PRIVATE ? 3 : 3) scan_sym_kernel(
                 if (K >= 32 || b < K) {
                     // sum the 32 lane-private copies of bin b with eight 128-bit reads; chunk
                     // (s + lane) & 7 keeps every quarter-warp on 8 distinct 16-byte bank groups
-                    int4 *row4 = reinterpret_cast<int4 *>(hist_p + b * 32);
+                    // read-and-zero in one shared-memory operation (ATOMS.EXCH.128, see scan_hex.cu)
+                    const uint32_t row = hist + (uint32_t)b * 128u;
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {
                         const int ch = (s + lane) & 7;
-                        const int4 v = row4[ch];
-                        row4[ch] = make_int4(0, 0, 0, 0);
-                        acc += (v.x + v.y) + (v.z + v.w);
+                        const uint4 v = smem_take128(row + (uint32_t)ch * 16u);
+                        acc += (int)((v.x + v.y) + (v.z + v.w));
                     }
                 }
                 bins[q] = acc;

@@ -83,19 +83,6 @@ struct HexUnroll<32> {
     static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
 };
 
-// 128-bit read-and-zero in one shared-memory operation (ATOMS.EXCH.128: 75 cycles per 8 KB against 128 for
-// LDS.128 + STS.128, tools/micro_atoms.cu)
-__device__ __forceinline__ uint4 smem_take128(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("{\n\t.reg .b128 v, z;\n\tmov.b128 z, {%5, %5, %5, %5};\n\tatom.shared.exch.b128 v, [%4], z;\n\t"
-                 "mov.b128 {%0, %1, %2, %3}, v;\n\t}"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(addr), "r"(0u)
-                 : "memory");
-    return v;
-}
-
 // acc += both marginals of the warp's hexamer histogram (+ the single-pentanucleotide corrections),
 // leaving them zeroed.  Lane owns output chunks cidx = 32 j + lane (bins 4 cidx .. 4 cidx + 3), j < 8.
 template <bool EXCH>
