@@ -44,6 +44,8 @@ SIGNATURES = {
     "dig_gene_burden_test": (_I, [_P, _P, _P, _P, _P, _P, _I64, _P, _D, _D, _P, _P]),
     "dig_gene_dnds_sel": (_I, [_P, _P, _P, _P, _I64, _P, _P]),
     "dig_selection_coefficient": (_I, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "dig_window_denominators": (_I, [_P, _P, _I64, _P, _P, _P]),
+    "dig_site_test": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "dig_region_prob_norm": (_I, [_P, _P, _I64, _I, _P, _P]),
     "dig_position_obs": (_I, [_P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _P, _I64, _P, _P]),
     "dig_position_test": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
@@ -60,7 +62,7 @@ KERNELS_PER_CALL = {
     "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2, "dig_site_counts": 1,
     "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
     "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
-    "dig_gene_dnds_sel": 1, "dig_selection_coefficient": 1, "dig_region_prob_norm": 1, "dig_position_obs": 1, "dig_position_test": 1, "dig_nb_pvalue_exact": 1,
+    "dig_window_denominators": 1, "dig_site_test": 1, "dig_gene_dnds_sel": 1, "dig_selection_coefficient": 1, "dig_region_prob_norm": 1, "dig_position_obs": 1, "dig_position_test": 1, "dig_nb_pvalue_exact": 1,
 }
 launch_count = 0
 

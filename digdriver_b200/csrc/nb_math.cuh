@@ -117,6 +117,8 @@ __device__ inline double nb_midp(double k, double alpha, double p)
     const bool isint = (k == floor(k));
     if (q <= 0.0) return k == 0.0 ? 0.5 : 0.0;   // p == 1: all mass at 0
     if (p <= 0.0) return 1.0;
+    // k = 0 (most sites / positions): pmf = p^alpha and sf = betainc(1, alpha, q) = 1 - (1 - q)^alpha in closed form
+    if (k == 0.0) return 1.0 - 0.5 * exp(alpha * (p > 0.5 ? log1p(-q) : log(p)));
     const double lg = log_nb_density(k, alpha, p, q);
     const double a = k + 1.0;
     double sf;

@@ -471,3 +471,35 @@ def selection_coefficient(obs, exp, alpha=None, theta=None, pi=None, device="cud
         _lib.call("dig_selection_coefficient", o.data_ptr(), e.data_ptr(), _ptr(a), _ptr(t), _ptr(p), o.numel(),
                   sel.data_ptr(), _ptr(pval), _stream(dev, stream))
     return sel, pval
+
+
+def site_test(site_chrom, site_start, site_sub, site_k, window, win_map_off, win_map, win_counts, y_pred, std, d_pr,
+              cj=1.0, site_strand=None, device="cuda:0", want=("P", "EXP"), stream=None, status_sink=None):
+    """Per-site burden test (config 3): P, EXP and PVAL for every site as a one-site site set.  site_chrom indexes
+    win_map_off like dig_element_transfer's elt_chrom; site_sub is the substitution index 0..191 (already flipped for
+    minus-strand sites); win_counts int32 [n_win, 64]; y_pred / std [n_win].  Returns a dict of device tensors."""
+    dev = torch.device(device)
+    sc, ss = _dev(site_chrom, torch.int32, dev), _dev(site_start, torch.int64, dev)
+    sb, sk = _dev(site_sub, torch.uint8, dev), _dev(site_k, torch.float64, dev)
+    st = _dev(site_strand, torch.int8, dev) if site_strand is not None else None
+    wmo, wm = _dev(win_map_off, torch.int64, dev), _dev(win_map, torch.int32, dev)
+    wc = _dev(win_counts, torch.int32, dev).contiguous()
+    yp, sd = _dev(y_pred, torch.float64, dev).contiguous(), _dev(std, torch.float64, dev).contiguous()
+    dp = _dev(d_pr, torch.float64, dev).contiguous()
+    n_win, n = wc.shape[0], sc.numel()
+    den_p = torch.empty(n_win, dtype=torch.float64, device=dev)
+    den_m = torch.empty(n_win, dtype=torch.float64, device=dev)
+    out = {"PVAL": torch.empty(n, dtype=torch.float64, device=dev)}
+    for k in ("P", "EXP"):
+        out[k] = torch.empty(n, dtype=torch.float64, device=dev) if k in want else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    sptr = _stream(dev, stream)
+    with torch.cuda.device(dev):
+        _lib.call("dig_window_denominators", wc.data_ptr(), dp.data_ptr(), n_win, den_p.data_ptr(), den_m.data_ptr(), sptr)
+        _lib.call("dig_site_test", sc.data_ptr(), ss.data_ptr(), sb.data_ptr(), _ptr(st), sk.data_ptr(), n, int(window),
+                  wmo.data_ptr(), wm.data_ptr(), yp.data_ptr(), sd.data_ptr(), den_p.data_ptr(), den_m.data_ptr(),
+                  dp.data_ptr(), float(cj), _ptr(out["P"]), _ptr(out["EXP"]), out["PVAL"].data_ptr(),
+                  status.data_ptr(), sptr)
+        _check_status(status, "dig_site_test", status_sink)
+    out["DENOM_PLUS"], out["DENOM_MINUS"] = den_p, den_m
+    return {k: v for k, v in out.items() if v is not None}

@@ -264,6 +264,27 @@ int dig_selection_coefficient(const double *obs_d, const double *exp_d, const do
                               const double *pi_d, int64_t n, double *sel_d, double *pval_d, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * Per-site test (BASELINE.json config 3): every site is a one-site "site set" of preprocess_sites
+ * (sequence_tools.py:647-711) + nonc_model (genic_driver_tools.py:361-381) + element_expected_muts_nb /
+ * element_pvalue_burden_nb (transfer_tools.py:343-355, :473-482), without a 192-double L row per site.
+ * dig_window_denominators: denom_plus[w] = sum_i d_pr[i] * R_w[i/3], denom_minus[w] the same with the region counts
+ *   re-ordered for minus-strand elements (R_w[revcomp(i/3)], sequence_tools.py:633-634); win_counts_d [n_win, 64] are
+ *   the trinucleotide rows of dig_count_contexts; same lane assignment and reduction order as dig_element_transfer.
+ * dig_site_test: site i lies in window floor(START/window) of chromosome site_chrom[i] (looked up in the same dense
+ *   win_map as dig_element_transfer; a missing window sets status 2 = the reference's KeyError and writes NaN);
+ *   site_sub_d = substitution index 0..191 in sorted 'CTX>CTX2' order (already strand-flipped as :681-685 does);
+ *   P = d_pr[sub] / denom, MU = Y_PRED[w], SIGMA = sqrt(STD[w]^2), THETA scaled by cj; out: P (nullable),
+ *   EXP (nullable), PVAL.  site_k_d = observed count of exactly that substitution at that site.
+ */
+int dig_window_denominators(const int32_t *win_counts_d, const double *d_pr_d, int64_t n_win, double *denom_plus_d,
+                            double *denom_minus_d, void *stream);
+int dig_site_test(const int32_t *site_chrom_d, const int64_t *site_start_d, const uint8_t *site_sub_d,
+                  const int8_t *site_strand_d, const double *site_k_d, int64_t n_site, int64_t window,
+                  const int64_t *win_map_off_d, const int32_t *win_map_d, const double *y_pred_d, const double *std_d,
+                  const double *denom_plus_d, const double *denom_minus_d, const double *d_pr_d, double cj,
+                  double *p_out_d, double *exp_out_d, double *pval_out_d, int32_t *status_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * K8: per-position / per-bin hotspot test (secondary path of the reference).
  * dig_region_prob_norm replaces the normaliser of base_probabilities_by_region (sequence_tools.py:292-317,
  *   `probs / np.sum(probs)`): norm[r] = sum_k counts[r,k] * s_prob[k], counts = dig_count_contexts of the same

@@ -270,3 +270,67 @@ def test_config3_site_sets(world, oracle, tmp_path):
     e_, p_ = oracle.burden_test(cnt.OBS_SNV.values, a, t * 1.7, df.Pi_SUM.values)
     np.testing.assert_allclose(df.EXP_SNV.values, e_, rtol=1e-12)
     assert_pvals_close(df.PVAL_SNV_BURDEN.values, p_)
+
+
+def test_config3_per_site_test_30m_sites(world, oracle):
+    """BASELINE config 3 at scale: 30 M sites, each its own one-site site set.  (1) a random subset is bit-identical to
+    the same sites pushed through K6 as one-site elements (one-hot L) and within tolerance of the oracle's
+    element_transfer + burden_test; (2) size-independent properties over all 30 M: the result of a site depends only
+    on (window, strand, substitution, k) -- permuting the sites permutes the outputs -- and P * denom == d_pr[sub]."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.sequence_model import genic_driver_tools as gd
+    rng, lengths = np.random.default_rng(33), world["lengths"]
+    m = world["maps"][10_000]
+    wins, d_pr, cj = m["wins"], world["d_pr"], 1.37
+    n = 30_000_000
+    chrom = rng.integers(1, 4, n).astype(np.int32)
+    usable = ((lengths - 1) // 10_000 * 10_000)[chrom - 1]
+    start = (rng.random(n) * (usable - 1)).astype(np.int64)
+    sub = rng.integers(0, 192, n).astype(np.uint8)
+    strand = np.where(rng.random(n) < 0.5, -1, 1).astype(np.int8)
+    k = rng.poisson(0.05, n).astype(np.float64)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    dev = torch.device(DEV)
+    args_d = [torch.from_numpy(a).to(dev) for a in (chrom, start, sub, k, strand)]
+    for rep in range(2):                                     # the second call re-uses the allocator's blocks
+        torch.cuda.synchronize()
+        t0.record()
+        out = kernels.site_test(args_d[0], args_d[1], args_d[2], args_d[3], 10_000, m["off"], m["wmap"], m["c64"],
+                                m["y_pred"], m["std"], d_pr, cj=cj, site_strand=args_d[4], device=dev)
+        t1.record()
+        torch.cuda.synchronize()
+    print("per-site test: %d sites in %.2f ms -> %.2f G sites/s" % (n, t0.elapsed_time(t1), n / t0.elapsed_time(t1) / 1e6))
+    P, EXP, PV = (out[x].cpu().numpy() for x in ("P", "EXP", "PVAL"))
+    assert not np.isnan(PV).any()
+    # (2a) P * denom == d_pr[sub] up to one rounding
+    row = np.array([m["index"][(int(c), int(s) // 10_000 * 10_000)] for c, s in zip(chrom[:200_000], start[:200_000])])
+    den = np.where(strand[:200_000] < 0, out["DENOM_MINUS"].cpu().numpy()[row], out["DENOM_PLUS"].cpu().numpy()[row])
+    fin = den > 0                                            # windows that are all N have denom 0 (P = inf, as in the reference)
+    assert fin.mean() > 0.9 and np.all(np.isinf(P[:200_000][~fin]))
+    np.testing.assert_allclose((P[:200_000] * den)[fin], d_pr[sub[:200_000]][fin], rtol=1e-15)
+    # (2b) permutation invariance over all sites
+    perm = torch.randperm(n, device=dev)
+    out2 = kernels.site_test(args_d[0][perm], args_d[1][perm], args_d[2][perm], args_d[3][perm], 10_000, m["off"],
+                             m["wmap"], m["c64"], m["y_pred"], m["std"], d_pr, cj=cj, site_strand=args_d[4][perm],
+                             device=dev)
+    assert torch.equal(out2["PVAL"], out["PVAL"][perm]) and torch.equal(out2["EXP"], out["EXP"][perm])
+    # (1) subset through K6 as one-site elements, and through the oracle
+    sel = rng.choice(np.flatnonzero(np.isfinite(P[:5_000_000])), 3000, replace=False)
+    rp = pd.DataFrame({"CHROM": wins[:, 0], "START": wins[:, 1], "END": wins[:, 2], "Y_TRUE": m["y_true"],
+                       "Y_PRED": m["y_pred"], "STD": m["std"], "FLAG": m["flag"]})
+    L = np.zeros((len(sel), 192))
+    L[np.arange(len(sel)), sub[sel]] = 1.0
+    res = gd.transfer_elements(gd.RegionModel(rp), m["c64"], d_pr, chrom[sel], strand[sel], np.arange(len(sel) + 1),
+                               start[sel], start[sel] + 1, L_elt=L.reshape(len(sel), 192, 1))
+    assert np.array_equal(res["P"][:, 0], P[sel]), np.abs(res["P"][:, 0] / P[sel] - 1).max()
+    want = oracle.element_transfer(chrom[sel], strand[sel], np.arange(len(sel) + 1), start[sel], start[sel] + 1, L,
+                                   10_000, m["index"], m["c64h"], m["y_pred"], m["std"], m["y_true"], m["flag"], d_pr)
+    np.testing.assert_allclose(P[sel], want["P_SUM"], rtol=1e-9)
+    a, t = oracle.normal_params_to_gamma(want["MU"], want["SIGMA"])
+    e_, p_ = oracle.burden_test(k[sel], a, t * cj, want["P_SUM"])
+    np.testing.assert_allclose(EXP[sel], e_, rtol=1e-9)
+    assert_pvals_close(PV[sel], p_)
+    # a site outside every window raises like the reference's KeyError
+    with pytest.raises(KeyError):
+        kernels.site_test([3], [int(lengths[2]) + 50_000], [5], [0.0], 10_000, m["off"], m["wmap"], m["c64"], m["y_pred"],
+                          m["std"], d_pr, device=dev)
