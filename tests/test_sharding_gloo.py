@@ -38,7 +38,11 @@ def _worker(rank, world, port, ret):
                                              off, sub.lengths, c, s, e, u, d)
         totals = coll.all_reduce_sum(torch.from_numpy(counts.sum(axis=0)))
         rows = coll.gather_rows(torch.from_numpy(counts))
+        # the known-sizes form (no size exchange, no host reads: the one used inside the CUDA graph of bench.py)
+        sizes = [b - a for a, b in sharding.partition_windows(wins[:, 1], wins[:, 2], world)]
+        rows2 = coll.gather_rows(torch.from_numpy(counts), sizes=sizes)
         if rank == 0:
+            assert torch.equal(rows, rows2)
             full_off = np.concatenate([[0], np.cumsum(lengths)[:-1]])
             want, _ = dig_oracle.count_regions(np.concatenate(seqs), full_off, lengths, wins[:, 0], wins[:, 1],
                                                wins[:, 2], u, d)
