@@ -4,7 +4,6 @@ K5 (observed counts) and K7 (burden test) back to back on the GPU."""
 import os
 import tempfile
 
-import numpy as np
 import pandas as pd
 
 from .. import storage

@@ -4,7 +4,6 @@ The reference reads the genome through ``pysam.FastaFile`` one window at a time
 (DIGDriver/sequence_model/sequence_tools.py:21-29, :84); here the whole genome is packed once
 into HBM (0.375 B/base: 2-bit bases + N bitmask) and every kernel works on that.
 """
-import os
 
 import numpy as np
 import torch

@@ -12,7 +12,6 @@ import numpy as np
 import torch
 
 from . import kernels
-from .genome import DeviceGenome
 
 GENE_CLASSES = ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NONSYN")
 ANNOT_CLASS = {"Synonymous": 0, "Missense": 1, "Nonsense": 2, "Essential_Splice": 3, "INDEL": 4}

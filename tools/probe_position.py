@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from digdriver_b200 import genome as G, kernels, _lib
+from digdriver_b200 import genome as G, kernels
 
 total = int(float(sys.argv[1])) if len(sys.argv) > 1 else 500_000_000
 lengths = np.array([total // 2, total - total // 2], dtype=np.int64)
