@@ -140,6 +140,53 @@ def _tabulate(f_mut, f_elt_bed, bed12, drop_duplicates, max_muts_per_sample, max
     return df[df.OBS_SAMPLES > 0], blacklist
 
 
+def tabulate_muts_per_sample_per_element(f_mut, f_elt_bed, bed12=False, drop_duplicates=False, unique_indels=True):
+    """Reference :191-230: one row per (ELT, SAMPLE) with OBS_SNV, OBS_INDEL, OBS_MUT -- the K5 hash table read back."""
+    mut = _read_raw_mutations(f_mut) if not isinstance(f_mut, pd.DataFrame) else f_mut.copy()
+    mut.columns = range(mut.shape[1])
+    blocks = _read_bed_blocks(f_elt_bed, bed12) if not isinstance(f_elt_bed, pd.DataFrame) else f_elt_bed
+    empty = pd.DataFrame({'ELT': [], 'SAMPLE': [], 'OBS_SNV': [], 'OBS_INDEL': [], 'OBS_MUT': []})
+    if len(mut) == 0 or len(blocks) == 0:
+        return empty
+    if drop_duplicates:
+        mut = mut.drop_duplicates([0, 1, 2, 3, 4, 5])
+    elts, elt_id = np.unique(blocks.ELT.values.astype(str), return_inverse=True)
+    samples, sample_id = np.unique(mut[5].astype(str).values, return_inverse=True)
+    mc, bc = _chrom_codes(mut[0].values, blocks.CHROM.values)
+    is_indel = (mut[7].values == 'INDEL') if mut.shape[1] > 7 else np.zeros(len(mut), dtype=bool)
+    _, _, (keys, snv, ind) = kernels.tabulate_elements(
+        (bc << 32) | blocks.START.values.astype(np.int64), (bc << 32) | blocks.END.values.astype(np.int64), elt_id,
+        (mc << 32) | mut[1].values.astype(np.int64), (mc << 32) | mut[2].values.astype(np.int64), sample_id, is_indel,
+        len(elts), len(samples), return_table=True)
+    keys = keys.cpu().numpy().astype(np.uint64)
+    used = keys != 0
+    if not used.any():
+        return empty
+    k = keys[used] - np.uint64(1)
+    df = pd.DataFrame({'ELT': elts[(k >> np.uint64(32)).astype(np.int64)],
+                       'SAMPLE': samples[(k & np.uint64(0xFFFFFFFF)).astype(np.int64)],
+                       'OBS_SNV': snv.cpu().numpy()[used].astype(np.float64),
+                       'OBS_INDEL': ind.cpu().numpy()[used].astype(np.float64)})
+    df['OBS_MUT'] = df.OBS_SNV + df.OBS_INDEL
+    return df.sort_values(['ELT', 'SAMPLE'], kind='stable').reset_index(drop=True)
+
+
+def filter_samples_by_stdev(df_mut, stdev_cutoff):
+    """Reference :306-316: drop samples whose row count exceeds stdev_cutoff * stdev of the per-sample row counts."""
+    sample_cnt = df_mut.SAMPLE.value_counts()
+    stdev = sample_cnt.std()
+    print(stdev)
+    samples_blacklist = sample_cnt[sample_cnt > stdev * stdev_cutoff].index.to_list()
+    return df_mut[~df_mut.SAMPLE.isin(samples_blacklist)]
+
+
+def cap_muts_per_element_per_sample(df_mut_elt_samp, max_muts_per_elt_per_sample):
+    """Reference :318-326: caps the OBS_MUT column (only) of the per-sample-per-element table."""
+    mask = df_mut_elt_samp.OBS_MUT > max_muts_per_elt_per_sample
+    df_mut_elt_samp.loc[mask, 'OBS_MUT'] = max_muts_per_elt_per_sample
+    return df_mut_elt_samp
+
+
 def tabulate_mutations_in_element(f_mut, f_elt_bed, bed12=False, drop_duplicates=False, all_elements=False,
                                   max_muts_per_sample=1e9, max_muts_per_elt_per_sample=3e9, return_blacklist=False):
     """Reference :155-189: OBS_SAMPLES, OBS_SNV, OBS_INDEL per element (index ELT)."""

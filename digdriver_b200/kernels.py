@@ -153,7 +153,7 @@ def check_deferred(sink):
 
 def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_sample, mut_isindel,
                       n_elt, n_sample, max_muts_per_sample=10 ** 9, max_per_elt_per_sample=3 * 10 ** 9,
-                      device="cuda:0", stream=None, sample_rows_mode=False):
+                      device="cuda:0", stream=None, sample_rows_mode=False, return_table=False):
     """K5: (OBS_SAMPLES, OBS_SNV, OBS_INDEL) per element and the per-sample totals used for the
     hypermutator black-list.  Blocks need not be sorted.  Returns (obs int64 [n_elt,3], sample_tot [n_sample])."""
     dev = torch.device(device)
@@ -187,6 +187,9 @@ def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_s
                   int(min(max_per_elt_per_sample, 2 ** 62)), n_elt, obs.data_ptr(), status.data_ptr(),
                   int(bool(sample_rows_mode)), sptr)
         _check_status(status, "dig_tabulate_elements")
+    if return_table:
+        # the (element, sample) hash table itself: key = (element << 32 | sample) + 1, 0 = empty slot
+        return obs[:n_elt], sample_tot[:n_sample], (keys, snv, ind)
     return obs[:n_elt], sample_tot[:n_sample]
 
 

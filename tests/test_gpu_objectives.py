@@ -64,3 +64,24 @@ def test_add_objectives_cli_and_tiling(tmp_path, oracle):
     # unfiltered: every de-duplicated SNV row inside a tiled window counts once
     plain = objectives.window_mutation_counts(str(f_mut), idx)
     assert np.array_equal(plain, oracle.window_objectives(df.copy(), idx))
+
+
+def test_muts_per_sample_per_element_table(oracle):
+    """tabulate_muts_per_sample_per_element (mutation_tools.py:191-230): the (ELT, SAMPLE) rows read back from the K5
+    hash table equal the pandas restatement, and the reference-named filters applied to it reproduce add_objectives."""
+    from digdriver_b200.data_tools import mutation_tools as mt
+    z = golden("objectives")
+    df = _frame(z)
+    idx = z["idx"]
+    blocks = pd.DataFrame({"CHROM": idx[:, 0].astype(str), "START": idx[:, 1], "END": idx[:, 2],
+                           "ELT": ["%d:%d-%d" % tuple(r) for r in idx]})
+    got = mt.tabulate_muts_per_sample_per_element(df, blocks, drop_duplicates=True)
+    want = oracle.muts_per_sample_per_element(df, blocks, drop_duplicates=True)
+    want = want.sort_values(["ELT", "SAMPLE"], kind="stable").reset_index(drop=True)
+    assert list(got.columns) == ['ELT', 'SAMPLE', 'OBS_SNV', 'OBS_INDEL', 'OBS_MUT']
+    assert got.ELT.tolist() == want.ELT.tolist() and got.SAMPLE.tolist() == want.SAMPLE.tolist()
+    for c in ("OBS_SNV", "OBS_INDEL", "OBS_MUT"):
+        assert np.array_equal(got[c].values, want[c].values), c
+    t = mt.filter_hypermut_samples(mt.filter_samples_by_stdev(mt.cap_muts_per_element_per_sample(got.copy(), 3), 3.0), 13)
+    y = t.groupby("ELT").OBS_SNV.sum().reindex(blocks.ELT).fillna(0).astype(int).values
+    assert np.array_equal(y, z["y_4"])                      # golden case (cap 3, stdev 3.0, max 13)
