@@ -134,3 +134,24 @@ def test_cli_parsers_accept_the_reference_arguments():
     assert a.f_bed == "e.bed" and a.scale_type == "genome" and a.max_muts_per_sample == 3e9
     a = mods["DigDriver"].parse_args("geneDriver m.txt model.h5 --outpfx x --outdir o --scale-by-mutations")
     assert a.scale_by_expectation is False
+    a = mods["DigDriver"].parse_args("targetDriver m.txt model.h5 --panel MSK_341 --outpfx x --outdir o --scale-by-samples")
+    assert a.panel == "MSK_341" and a.scale_by_samples and a.func.__name__ == "target_driver"
+    a = mods["DigPreprocess"].parse_args("preprocess_tiled tiles.bed data.h5 g.fa 10000 TILES --n-procs 2")
+    assert a.window == 10000 and a.save_key == "TILES" and a.func.__name__ == "preprocess_tiled"
+    a = mods["DigPretrain"].parse_args("tiledModel pre.h5 data.h5 TILES --output_h5 out.h5")
+    assert a.output_h5 == "out.h5" and a.func.__name__ == "pretrain_tiled"
+    spec = importlib.util.spec_from_file_location("cli_DataExtractor", os.path.join(root, "scripts", "DataExtractor.py"))
+    de = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(de)
+    a = de.parse_args(["addObjectives", "d.h5", "m.txt", "--sample-filter-stdev", "2.5", "--max-muts-per-sample", "9"])
+    assert a.sample_filter_stdev == 2.5 and a.max_muts_per_sample == 9 and a.cnv is False
+
+
+def test_window_tiling_rule_and_tile_names():
+    """extract_high_mappability's tiling (DataExtractor.py:70-77): from 0 while i + window < size; tiled-model names."""
+    from digdriver_b200.data_tools import objectives
+    from digdriver_b200.sequence_model.genic_driver_tools import _index_transform
+    idx = objectives.tile_windows({1: 30_000, 2: 10_000, 3: 10_001}, 10_000)
+    assert idx.tolist() == [[1, 0, 10_000], [1, 10_000, 20_000], [3, 0, 10_000]]      # the last partial window is dropped
+    assert objectives.tile_windows({7: 100}, 30, overlap=10).tolist() == [[7, 0, 30], [7, 20, 50], [7, 40, 70], [7, 60, 90]]
+    assert _index_transform("chr12:100-250") == "region_12_100_250"
