@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(1024) gene_scale_sums_kernel(
 {
     __shared__ double sh[3][1024];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    // unrolled so that the (independent) loads of four strides are in flight together; the additions keep their order
+#pragma unroll 4
     for (int64_t g = threadIdx.x; g < n; g += 1024) {
         const double m = mu[g], s = sigma[g];
         if (g != tp53) a0 += m * P[g * 4 + 0];
