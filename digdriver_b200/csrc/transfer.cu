@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
     double *l64 = r64 + 64;
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(l64 + 64);
 
+    const bool l4_aligned = (reinterpret_cast<uintptr_t>(L_elt) & 15u) == 0;
     const int64_t gwarp = (int64_t)blockIdx.x * TW + warp;
     const int64_t nwarps = (int64_t)gridDim.x * TW;
 
@@ -123,24 +124,63 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
                 my_row = (wi >= 0 && wi < map_n) ? __ldg(win_map + map0 + wi) : -1;
             }
             if (__any_sync(0xffffffffu, lane < cnt && my_row < 0) && lane == 0) atomicMax(status, 2);   // KeyError in the reference
-#pragma unroll 4
-            for (int k = 0; k < cnt; ++k) {
-                const int32_t row = __shfl_sync(0xffffffffu, my_row, k);
-                if (row < 0) continue;
-                ++nw;
-                const int32_t *wc = win_counts + (int64_t)row * 64;
-                r_lo += (double)__ldg(wc + lane);
-                r_hi += (double)__ldg(wc + lane + 32);
+            // counts: four windows' rows in flight, added in ascending window order
+            for (int k0 = 0; k0 < cnt; k0 += 4) {
+                int32_t row[4], clo[4], chi[4];
 #pragma unroll
-                for (int q = 0; q < MAX_COHORT_PER_LANE; ++q) {
-                    const int ci = lane + 32 * q;
-                    if (ci < n_cohort) {
-                        const int64_t o = (int64_t)ci * n_win + row;
-                        const double s = __ldg(stdv + o);
-                        mu[q] += __ldg(y_pred + o);
-                        var[q] = __dadd_rn(var[q], __dmul_rn(s, s));
-                        ro[q] += __ldg(y_true + o);
-                        fl[q] |= __ldg(flag + o) != 0;
+                for (int u = 0; u < 4; ++u) {
+                    row[u] = k0 + u < cnt ? __shfl_sync(0xffffffffu, my_row, (k0 + u) & 31) : -1;
+                    clo[u] = chi[u] = 0;
+                    if (row[u] >= 0) {
+                        const int32_t *wc = win_counts + (int64_t)row[u] * 64;
+                        clo[u] = __ldg(wc + lane);
+                        chi[u] = __ldg(wc + lane + 32);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (row[u] < 0) continue;
+                    ++nw;
+                    r_lo += (double)clo[u];
+                    r_hi += (double)chi[u];
+                }
+            }
+            if (n_cohort == 1) {
+                // one cohort (the CLI / bench case): lane k loads the region parameters of window k, so all windows of
+                // this word are fetched at once; the sums are then formed in ascending window order through shuffles
+                double yp = 0.0, sd = 0.0, yt = 0.0;
+                int fg = 0;
+                if (lane < cnt && my_row >= 0) {
+                    yp = __ldg(y_pred + my_row);
+                    sd = __ldg(stdv + my_row);
+                    yt = __ldg(y_true + my_row);
+                    fg = __ldg(flag + my_row) != 0;
+                }
+                for (int k = 0; k < cnt; ++k) {
+                    const double a = __shfl_sync(0xffffffffu, yp, k), b = __shfl_sync(0xffffffffu, sd, k);
+                    const double t = __shfl_sync(0xffffffffu, yt, k);
+                    const int f = __shfl_sync(0xffffffffu, fg, k);
+                    if (__shfl_sync(0xffffffffu, my_row, k) < 0) continue;
+                    mu[0] += a;
+                    var[0] = __dadd_rn(var[0], __dmul_rn(b, b));
+                    ro[0] += t;
+                    fl[0] |= f;
+                }
+            } else {
+                for (int k = 0; k < cnt; ++k) {
+                    const int32_t row = __shfl_sync(0xffffffffu, my_row, k);
+                    if (row < 0) continue;
+#pragma unroll
+                    for (int q = 0; q < MAX_COHORT_PER_LANE; ++q) {
+                        const int ci = lane + 32 * q;
+                        if (ci < n_cohort) {
+                            const int64_t o = (int64_t)ci * n_win + row;
+                            const double s = __ldg(stdv + o);
+                            mu[q] += __ldg(y_pred + o);
+                            var[q] = __dadd_rn(var[q], __dmul_rn(s, s));
+                            ro[q] += __ldg(y_true + o);
+                            fl[q] |= __ldg(flag + o) != 0;
+                        }
                     }
                 }
             }
@@ -186,17 +226,48 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
             double wgt[6];                                    // d_pr[j] / denom, shared by every column
 #pragma unroll
             for (int t = 0; t < 6; ++t) wgt[t] = __ldg(dp + lane + 32 * t) / denom;
-            for (int col = 0; col < n_col; ++col) {
-                double acc = 0.0;
+            if (blk_counts == nullptr && n_col == 4 && l4_aligned) {
+                // gene mode: the four columns of a substitution are 32 contiguous bytes -- two 128-bit loads per
+                // substitution, all twelve issued before the first use (same products and summation order per column)
+                const double2 *L2 = reinterpret_cast<const double2 *>(L_elt + (int64_t)e * 192 * 4);
+                double2 la[6], lb[6];
 #pragma unroll
                 for (int t = 0; t < 6; ++t) {
-                    const int j = lane + 32 * t;
-                    const double Lj = blk_counts != nullptr ? l64[j / 3]
-                                                            : __ldg(L_elt + ((int64_t)e * 192 + j) * n_col + col);
-                    acc += wgt[t] * Lj;
+                    la[t] = __ldg(L2 + 2 * (lane + 32 * t));
+                    lb[t] = __ldg(L2 + 2 * (lane + 32 * t) + 1);
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) p_out[((int64_t)ci * n_elt + e) * n_col + col] = acc;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    a0 += wgt[t] * la[t].x;
+                    a1 += wgt[t] * la[t].y;
+                    a2 += wgt[t] * lb[t].x;
+                    a3 += wgt[t] * lb[t].y;
+                }
+                a0 = warp_sum(a0);
+                a1 = warp_sum(a1);
+                a2 = warp_sum(a2);
+                a3 = warp_sum(a3);
+                if (lane == 0) {
+                    double *po = p_out + ((int64_t)ci * n_elt + e) * 4;
+                    po[0] = a0;
+                    po[1] = a1;
+                    po[2] = a2;
+                    po[3] = a3;
+                }
+            } else {
+                for (int col = 0; col < n_col; ++col) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        const int j = lane + 32 * t;
+                        const double Lj = blk_counts != nullptr ? l64[j / 3]
+                                                                : __ldg(L_elt + ((int64_t)e * 192 + j) * n_col + col);
+                        acc += wgt[t] * Lj;
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) p_out[((int64_t)ci * n_elt + e) * n_col + col] = acc;
+                }
             }
         }
 #pragma unroll
