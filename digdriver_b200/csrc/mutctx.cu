@@ -1,50 +1,46 @@
 // K3: mutation context lookup with REF check (mutation_contexts_by_chrom, sequence_tools.py:130-178).
-// One thread per mutation row; random 4-byte reads of the packed genome (latency bound, tiny data).
+// One thread per mutation row (latency bound, tiny data).
 #include "dig_common.cuh"
 
 namespace {
 
-// 0..3, or 4 when the base is not A/C/G/T
-__device__ __forceinline__ uint32_t base_at(const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask,
-                                            int64_t g)
-{
-    const uint32_t isn = (__ldg(nmask + (g >> 5)) >> (31 - (int)(g & 31))) & 1u;
-    if (isn) return 4u;
-    return (__ldg(p2 + (g >> 4)) >> (30 - 2 * (int)(g & 15))) & 3u;
-}
-
+// The k-mer (at most 15 bases) lies inside two consecutive packed words and its N bits inside two consecutive mask
+// words: four independent loads give the context AND the base under the mutation for the REF check, so a mutation
+// costs one memory round trip instead of a chain of dependent 4-byte reads.
 __global__ void __launch_bounds__(256) mutctx_kernel(
-    const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask, const int64_t *__restrict__ chrom_off,
-    const int64_t *__restrict__ chrom_len, const int32_t *__restrict__ mut_chrom,
-    const int64_t *__restrict__ mut_start, const uint8_t *__restrict__ mut_ref, int64_t n_mut, int n_up,
-    int n_down, int32_t *__restrict__ ctx_out)
+    const uint32_t *__restrict__ p2, const uint32_t *__restrict__ nmask, int64_t last_p, int64_t last_m,
+    const int64_t *__restrict__ chrom_off, const int64_t *__restrict__ chrom_len,
+    const int32_t *__restrict__ mut_chrom, const int64_t *__restrict__ mut_start,
+    const uint8_t *__restrict__ mut_ref, int64_t n_mut, int n_up, int n_down, int32_t *__restrict__ ctx_out)
 {
+    const int klen = n_up + n_down + 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_mut; i += stride) {
         const int32_t c = mut_chrom[i];
         const int64_t p = mut_start[i];
-        const int64_t L = chrom_len[c];
-        const int64_t off = chrom_off[c];
-        auto mismatch = [&](int64_t row) -> bool {
-            const uint32_t ref = mut_ref[row];
-            if (ref > 3u || p < 0 || p >= L) return true;
-            return base_at(p2, nmask, off + p) != ref;       // an N in the genome never equals A/C/G/T
-        };
+        const int64_t L = __ldg(chrom_len + c);
+        const int64_t off = __ldg(chrom_off + c);
         int32_t ctx = -1;
-        bool dropped = mismatch(i);
-        // same-START run: the reference re-uses the previous row's context string, so a REF
-        // mismatch earlier in the run drops every later row of the run (sequence_tools.py:150-151)
-        for (int64_t j = i - 1; !dropped && j >= 0 && mut_chrom[j] == c && mut_start[j] == p; --j)
-            dropped = mismatch(j);
-        if (!dropped && p - n_up >= 0 && p + n_down < L) {
-            uint32_t key = 0;
-            bool bad = false;
-            for (int t = -n_up; t <= n_down; ++t) {
-                const uint32_t b = base_at(p2, nmask, off + p + t);
-                bad |= b > 3u;
-                key = (key << 2) | (b & 3u);
-            }
-            if (!bad) ctx = (int32_t)key;
+        // a context that would leave the chromosome is dropped whatever the REF check says
+        if (p - n_up >= 0 && p + n_down < L) {
+            const int64_t f = off + p - n_up;                          // first base of the k-mer
+            const int64_t w = f >> 4, m = f >> 5;
+            const unsigned long long pk = ((unsigned long long)__ldg(p2 + w) << 32) | __ldg(p2 + (w < last_p ? w + 1 : last_p));
+            const unsigned long long mk = ((unsigned long long)__ldg(nmask + m) << 32) | __ldg(nmask + (m < last_m ? m + 1 : last_m));
+            const uint32_t key = (uint32_t)(pk >> (64 - 2 * ((int)(f & 15) + klen))) & ((1u << (2 * klen)) - 1u);
+            const uint32_t bad = (uint32_t)(mk >> (64 - ((int)(f & 31) + klen))) & ((1u << klen) - 1u);
+            const uint32_t base = (key >> (2 * n_down)) & 3u;          // the base under the mutation ...
+            const bool base_n = ((bad >> n_down) & 1u) != 0u;          // ... and whether it is not A/C/G/T
+            auto mismatch = [&](int64_t row) -> bool {
+                const uint32_t ref = mut_ref[row];
+                return ref > 3u || base_n || base != ref;              // an N in the genome never equals A/C/G/T
+            };
+            bool dropped = mismatch(i);
+            // same-START run: the reference re-uses the previous row's context string, so a REF
+            // mismatch earlier in the run drops every later row of the run (sequence_tools.py:150-151)
+            for (int64_t j = i - 1; !dropped && j >= 0 && mut_chrom[j] == c && mut_start[j] == p; --j)
+                dropped = mismatch(j);
+            if (!dropped && bad == 0u) ctx = (int32_t)key;
         }
         ctx_out[i] = ctx;
     }
@@ -108,11 +104,11 @@ extern "C" int dig_mutation_contexts(const uint32_t *packed2_d, const uint32_t *
                       ctx_out_d,
                   "null pointer");
     int64_t blocks = (n_mut + 255) / 256;
-    const int64_t cap = (int64_t)dig::sm_count() * 16;
+    const int64_t cap = (int64_t)dig::sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    mutctx_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed2_d, nmask_d, chrom_off_d, chrom_len_d,
-                                                                      mut_chrom_d, mut_start_d, mut_ref_d, n_mut,
-                                                                      n_up, n_down, ctx_out_d);
+    mutctx_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        packed2_d, nmask_d, (((n_bases + 31) >> 5) << 1) - 1, ((n_bases + 31) >> 5) - 1, chrom_off_d, chrom_len_d,
+        mut_chrom_d, mut_start_d, mut_ref_d, n_mut, n_up, n_down, ctx_out_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
