@@ -51,6 +51,11 @@ SIGNATURES = {
     "dig_position_test": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                                _P, _P, _P]),
     "dig_nb_pvalue_exact": (_I, [_P, _P, _P, _I64, _P, _P]),
+    "dig_nb_pvalue_variant": (_I, [_I, _P, _P, _P, _P, _I64, _P, _P]),
+    "dig_loglik": (_I, [_I, _P, _P, _P, _I64, _P, _P]),
+    "dig_gene_llr_test": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "dig_overlap_count": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
+    "dig_overlap_fill": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -63,6 +68,7 @@ KERNELS_PER_CALL = {
     "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
     "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
     "dig_window_denominators": 1, "dig_site_test": 1, "dig_gene_dnds_sel": 1, "dig_selection_coefficient": 1, "dig_region_prob_norm": 1, "dig_position_obs": 1, "dig_position_test": 1, "dig_nb_pvalue_exact": 1,
+    "dig_nb_pvalue_variant": 1, "dig_loglik": 1, "dig_gene_llr_test": 1, "dig_overlap_count": 1, "dig_overlap_fill": 1,
 }
 launch_count = 0
 

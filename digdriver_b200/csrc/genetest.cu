@@ -191,13 +191,6 @@ __device__ inline double ll_nb(double k, double alpha, double theta)
     return log_nb_density(k, alpha, p, q);
 }
 
-__device__ inline double chi2_sf(double x, int df)
-{
-    if (isnan(x)) return x;
-    if (x <= 0.0) return 1.0;
-    return df == 1 ? erfc(sqrt(0.5 * x)) : exp(-0.5 * x);
-}
-
 __global__ void __launch_bounds__(128) gene_dnds_sel_kernel(const double *__restrict__ alpha,
                                                             const double *__restrict__ theta,
                                                             const double *__restrict__ pi,    // [n, 6]
@@ -301,6 +294,46 @@ extern "C" int dig_selection_coefficient(const double *obs_d, const double *exp_
     int64_t blocks = (n + 127) / 128;
     selection_coef_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(obs_d, exp_d, alpha_d, theta_d, pi_d, n,
                                                                              sel_d, pval_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+// Row-level likelihood-ratio selection tests with the caller's MRFOLD (and T_SYN): _llr_test_nb
+// (transfer_tools.py:1172-1213, classes SYN / MIS / TRUNC) and _llr_test_gamma_poiss (:1215-1252, classes SYN / MIS /
+// NONS plus the gamma prior term of T_SYN, which is common to all five likelihoods but is added in the reference's
+// order so that NaN / inf propagate the same way).  One thread per row; out [4, n] = p_syn, p_mis, p_third, p_nonsyn.
+namespace {
+
+__global__ void __launch_bounds__(128) gene_llr_kernel(int model, const double *__restrict__ alpha,
+                                                       const double *__restrict__ theta,
+                                                       const double *__restrict__ pi,     // [n, 3]
+                                                       const double *__restrict__ obs,    // [n, 3]
+                                                       const double *__restrict__ mrfold, const double *__restrict__ t_syn,
+                                                       int64_t n, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        double r[4];
+        llr_row(model, alpha[g], theta[g], pi + g * 3, obs + g * 3, mrfold[g], t_syn ? t_syn[g] : 0.0, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[(int64_t)j * n + g] = r[j];
+    }
+}
+
+}  // namespace
+
+extern "C" int dig_gene_llr_test(int model, const double *alpha_d, const double *theta_d, const double *pi3_d,
+                                 const double *obs3_d, const double *mrfold_d, const double *t_syn_d, int64_t n,
+                                 double *out_d, void *stream)
+{
+    DIG_CHECK_ARG(n >= 0, "negative size");
+    DIG_CHECK_ARG(model == DIG_LLR_NB || model == DIG_LLR_GAMMA_POISSON, "unknown model");
+    if (n == 0) return DIG_OK;
+    DIG_CHECK_ARG(alpha_d && theta_d && pi3_d && obs3_d && mrfold_d && out_d, "null pointer");
+    DIG_CHECK_ARG(model == DIG_LLR_NB || t_syn_d, "the gamma-Poisson model needs T_SYN");
+    int64_t blocks = (n + 127) / 128;
+    gene_llr_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(model, alpha_d, theta_d, pi3_d, obs3_d, mrfold_d,
+                                                                       t_syn_d, n, out_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

@@ -1,6 +1,8 @@
 // FP64 negative-binomial mid-p arithmetic shared by nbtest.cu and genetest.cu (see nbtest.cu for the method).
 #pragma once
+#ifndef DIG_NB_MATH_HOST_CHECK      /* tools/host_nb_check.cpp compiles this header with g++ */
 #include "dig_common.cuh"
+#endif
 
 namespace dig_nb {
 
@@ -169,6 +171,166 @@ __device__ inline double nb_exact(double k, double alpha, double p)
     const double up = nb_tail_upper_from(k - 1.0, alpha, p, q);
     if (up == 0.0) return exp(log_nb_density(k, alpha, p, q));
     return up;
+}
+
+// General regularized incomplete beta I_x(a, b) (lgamma prefactor + the same continued fraction); only used by
+// nb_variant for the rare non-integer 0 < k < 1, where the density-relative forms above do not apply.
+__device__ inline double ibeta_general(double a, double b, double x)
+{
+    if (x <= 0.0) return 0.0;
+    if (x >= 1.0) return 1.0;
+    const double lf = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x);
+    if (x < (a + 1.0) / (a + b + 2.0)) return exp(lf + log(beta_cf(a, b, x) / a));
+    return 1.0 - exp(lf + log(beta_cf(b, a, 1.0 - x) / b));
+}
+
+// The other tail conventions of nb_model.py, selected by `mode` (include/dig_b200.h DIG_NB_*):
+//   GREATER    :243-256  k == 0 -> 1, else betainc(k, alpha, 1-p), pmf(k) when that underflows to 0
+//   LESS       :280-283  betainc(alpha, k+1, p)   (the reference computes this value and forgets to return it)
+//   LESS_MIDP  :285-296  0.5 pmf(k) + (k > 0 ? betainc(alpha, k, p) : 0)
+//   EXACT      :298-314  lower tail when k < mu, else GREATER without the k == 0 shortcut
+//   MIDP       :316-337  k < mu ? LESS_MIDP : 0.5 pmf(k) + betainc(k+1, alpha, 1-p)
+// mu is the caller's expectation; a falsy value (absent or 0) means alpha (1-p)/p as in `if not mu`.
+enum { NB_GREATER = 0, NB_GREATER_MIDP = 1, NB_LESS = 2, NB_LESS_MIDP = 3, NB_EXACT = 4, NB_MIDP = 5 };
+
+__device__ inline double nb_upper_incl(double k, double alpha, double p, double q)   // betainc(k, alpha, q), k > 0
+{
+    if (q <= 0.0) return 0.0;
+    if (p <= 0.0) return 1.0;
+    if (k < 1.0) return ibeta_general(k, alpha, q);
+    return nb_tail_upper_from(k - 1.0, alpha, p, q);
+}
+
+__device__ inline double nb_lower_excl(double k, double alpha, double p, double q)   // betainc(alpha, k, p), k > 0
+{
+    if (q <= 0.0) return 1.0;
+    if (p <= 0.0) return 0.0;
+    if (k < 1.0) return ibeta_general(alpha, k, p);
+    return nb_tail_lower_to(k - 1.0, alpha, p, q);
+}
+
+__device__ inline double nb_pmf(double k, double alpha, double p, double q)          // scipy.stats.nbinom.pmf
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (p <= 0.0) return nan;                                  // outside nbinom's parameter domain
+    if (k != floor(k)) return 0.0;
+    if (q <= 0.0) return k == 0.0 ? 1.0 : 0.0;
+    return exp(log_nb_density(k, alpha, p, q));
+}
+
+__device__ inline double nb_variant(int mode, double k, double alpha, double p, double mu, bool has_mu)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (mode == NB_GREATER_MIDP) return nb_midp(k, alpha, p);
+    if (isnan(k) || isnan(alpha) || isnan(p)) return nan;
+    if (!(alpha > 0.0) || isinf(alpha) || k < 0.0 || isinf(k) || p < 0.0 || p > 1.0) return nan;
+    const double q = 1.0 - p;
+    if (mode == NB_GREATER || mode == NB_EXACT || mode == NB_MIDP) {
+        bool lower = false;
+        if (mode != NB_GREATER) {
+            const double m = (has_mu && mu != 0.0) ? mu : alpha * q / p;     // +inf (or NaN -> upper) when p == 0
+            lower = k < m;
+        }
+        if (mode == NB_GREATER || (mode == NB_EXACT && !lower)) {
+            if (k == 0.0) return 1.0;
+            const double up = nb_upper_incl(k, alpha, p, q);
+            return up == 0.0 ? nb_pmf(k, alpha, p, q) : up;
+        }
+        if (mode == NB_EXACT) {                                // lower tail betainc(alpha, k+1, p)
+            if (p <= 0.0) return 0.0;
+            if (q <= 0.0) return 1.0;
+            if (k == 0.0) return exp(alpha * log(p));
+            return nb_tail_lower_to(k, alpha, p, q);
+        }
+        if (!lower) return nb_midp(k, alpha, p);               // MIDP, upper side
+        const double half = 0.5 * nb_pmf(k, alpha, p, q);      // MIDP, lower side == LESS_MIDP
+        return k > 0.0 ? half + nb_lower_excl(k, alpha, p, q) : half;
+    }
+    if (mode == NB_LESS) {
+        if (p <= 0.0) return 0.0;
+        if (q <= 0.0) return 1.0;
+        if (k == 0.0) return exp(alpha * log(p));
+        return nb_tail_lower_to(k, alpha, p, q);
+    }
+    if (mode == NB_LESS_MIDP) {
+        const double half = 0.5 * nb_pmf(k, alpha, p, q);
+        return k > 0.0 ? half + nb_lower_excl(k, alpha, p, q) : half;
+    }
+    return nan;
+}
+
+// Log-likelihood terms of the selection tests (transfer_tools.py:1254-1262), in SciPy's own formulas:
+//   kind 0  _ll_nb(k, alpha, theta)      nbinom.logpmf(k, alpha, 1 / (1 + theta))
+//   kind 1  _ll_pois(k, lam)             poisson.logpmf = xlogy(k, lam) - gammaln(k + 1) - lam
+//   kind 2  _ll_gamma(lam, alpha, theta) gamma.logpdf(lam, alpha, scale=theta)
+//                                        = xlogy(alpha - 1, lam/theta) - lam/theta - gammaln(alpha) - log(theta)
+__device__ inline double xlogy(double x, double y) { return (x == 0.0 && !isnan(y)) ? 0.0 : x * log(y); }
+
+__device__ inline double ll_pois_dev(double k, double lam)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (isnan(k) || isnan(lam) || lam < 0.0) return nan;
+    if (k < 0.0 || k != floor(k)) return -INFINITY;
+    return xlogy(k, lam) - lgamma(k + 1.0) - lam;
+}
+
+__device__ inline double ll_gamma_dev(double x, double a, double theta)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (isnan(x) || isnan(a) || isnan(theta) || !(a > 0.0) || !(theta > 0.0)) return nan;
+    const double y = x / theta;
+    if (y < 0.0) return -INFINITY;
+    return xlogy(a - 1.0, y) - y - lgamma(a) - log(theta);
+}
+
+__device__ inline double ll_nb_dev(double k, double alpha, double theta)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double p = __ddiv_rn(1.0, __dadd_rn(1.0, theta));
+    const double q = 1.0 - p;
+    if (isnan(p) || isnan(k) || isnan(alpha) || !(alpha > 0.0) || p <= 0.0 || p > 1.0) return nan;
+    if (k < 0.0 || k != floor(k)) return -INFINITY;
+    if (q <= 0.0) return k == 0.0 ? 0.0 : -INFINITY;
+    return log_nb_density(k, alpha, p, q);
+}
+
+// chi2.sf(x, df) for df = 1, 2 (the likelihood-ratio tests)
+__device__ inline double chi2_sf(double x, int df)
+{
+    if (isnan(x)) return x;
+    if (x <= 0.0) return 1.0;
+    return df == 1 ? erfc(sqrt(0.5 * x)) : exp(-0.5 * x);
+}
+
+// One row of _llr_test_nb (model 0; P / O = SYN, MIS, TRUNC) or _llr_test_gamma_poiss (model 1; SYN, MIS, NONS and the
+// gamma prior term of T_SYN) -- transfer_tools.py:1172-1252, sums in the reference's order, no FMA contraction.
+__device__ inline void llr_row(int model, double a, double t, const double *P, const double *O, double mrf, double t_syn,
+                               double *out4)
+{
+    double l0[3], l1[3];
+    for (int c = 0; c < 3; ++c) {
+        if (model == 0) {
+            l0[c] = ll_nb_dev(O[c], a, __dmul_rn(__dmul_rn(t, P[c]), mrf));
+            l1[c] = ll_nb_dev(O[c], a, __ddiv_rn(O[c], a));
+        } else {
+            l0[c] = ll_pois_dev(O[c], __dmul_rn(__dmul_rn(__dmul_rn(a, t), P[c]), mrf));
+            l1[c] = ll_pois_dev(O[c], O[c]);
+        }
+    }
+    double ll[5];
+    ll[0] = __dadd_rn(__dadd_rn(l0[0], l0[1]), l0[2]);
+    ll[1] = __dadd_rn(__dadd_rn(l1[0], l0[1]), l0[2]);
+    ll[2] = __dadd_rn(__dadd_rn(l0[0], l1[1]), l0[2]);
+    ll[3] = __dadd_rn(__dadd_rn(l0[0], l0[1]), l1[2]);
+    ll[4] = __dadd_rn(__dadd_rn(l0[0], l1[1]), l1[2]);
+    if (model != 0) {
+        const double lg = ll_gamma_dev(t_syn, a, __dmul_rn(__dmul_rn(t, P[0]), mrf));
+        for (int j = 0; j < 5; ++j) ll[j] = __dadd_rn(ll[j], lg);
+    }
+    out4[0] = chi2_sf(-2.0 * (ll[0] - ll[1]), 1);
+    out4[1] = chi2_sf(-2.0 * (ll[0] - ll[2]), 1);
+    out4[2] = chi2_sf(-2.0 * (ll[0] - ll[3]), 1);
+    out4[3] = chi2_sf(-2.0 * (ll[0] - ll[4]), 2);
 }
 
 // chi2.sf(-2 (ln p1 + ln p2), df=4) = exp(-y) (1 + y), y = -(ln p1 + ln p2)  (transfer_tools.py:860-861)

@@ -56,6 +56,25 @@ __global__ void __launch_bounds__(256) fisher2_kernel(const double *__restrict__
     }
 }
 
+// The remaining tail conventions of nb_model.py (:243-337) -- see nb_variant in nb_math.cuh.
+__global__ void __launch_bounds__(128) nb_variant_kernel(int mode, const double *__restrict__ k,
+                                                         const double *__restrict__ alpha, const double *__restrict__ p,
+                                                         const double *__restrict__ mu, int64_t n,
+                                                         double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = nb_variant(mode, k[i], alpha[i], p[i], mu ? mu[i] : 0.0, mu != nullptr);
+}
+
+__global__ void __launch_bounds__(128) loglik_kernel(int kind, const double *__restrict__ x, const double *__restrict__ a,
+                                                     const double *__restrict__ b, int64_t n, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = kind == 0 ? ll_nb_dev(x[i], a[i], b[i]) : kind == 1 ? ll_pois_dev(x[i], a[i]) : ll_gamma_dev(x[i], a[i], b[i]);
+}
+
 inline unsigned grid_for(int64_t n, int threads)
 {
     int64_t blocks = (n + threads - 1) / threads;
@@ -97,6 +116,29 @@ int dig_fisher_combine2(const double *p1_d, const double *p2_d, int64_t n, doubl
     if (n == 0) return DIG_OK;
     DIG_CHECK_ARG(p1_d && p2_d && out_d, "null pointer");
     fisher2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p1_d, p2_d, n, out_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_nb_pvalue_variant(int mode, const double *k_d, const double *alpha_d, const double *p_d, const double *mu_d,
+                          int64_t n, double *pval_out_d, void *stream)
+{
+    DIG_CHECK_ARG(n >= 0, "negative size");
+    DIG_CHECK_ARG(mode >= DIG_NB_GREATER && mode <= DIG_NB_MIDP, "unknown mode");
+    if (n == 0) return DIG_OK;
+    DIG_CHECK_ARG(k_d && alpha_d && p_d && pval_out_d, "null pointer");
+    nb_variant_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(mode, k_d, alpha_d, p_d, mu_d, n, pval_out_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_loglik(int kind, const double *x_d, const double *a_d, const double *b_d, int64_t n, double *out_d, void *stream)
+{
+    DIG_CHECK_ARG(n >= 0, "negative size");
+    DIG_CHECK_ARG(kind >= DIG_LL_NB && kind <= DIG_LL_GAMMA, "unknown kind");
+    if (n == 0) return DIG_OK;
+    DIG_CHECK_ARG(x_d && a_d && out_d && (kind == DIG_LL_POIS || b_d), "null pointer");
+    loglik_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(kind, x_d, a_d, b_d, n, out_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

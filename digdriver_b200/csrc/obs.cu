@@ -195,6 +195,50 @@ inline unsigned grid_for(int64_t n)
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// Overlap join (`bedtools intersect -wa -wb` itself, one output row per overlapping (mutation, block) pair) behind
+// mutation_tools.restrict_mutations_by_bed(_efficient) (:8-43), mutations_by_element (:363-381) and
+// tabulate_nonc_mutations_split (:120-153).  Two passes over the same stabbing walk: count per mutation, then (after
+// the caller's exclusive scan) fill.  Within a mutation the pairs come out by ascending sorted-block index.
+__global__ void __launch_bounds__(256) overlap_count_kernel(
+    const int64_t *__restrict__ bks, const int64_t *__restrict__ bke, const int64_t *__restrict__ pmax, int64_t n_blk,
+    const int64_t *__restrict__ mks, const int64_t *__restrict__ mke, int64_t n_mut, int64_t *__restrict__ n_pairs)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_mut; i += stride) {
+        const int64_t ks = mks[i], ke = mke[i];
+        int64_t c = 0;
+        if (ke > ks) {
+            const int64_t hi = upper_bound_ge(bks, n_blk, ke);
+            for (int64_t idx = hi - 1; idx >= 0; --idx) {
+                if (__ldg(pmax + idx) <= ks) break;
+                c += __ldg(bke + idx) > ks;
+            }
+        }
+        n_pairs[i] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) overlap_fill_kernel(
+    const int64_t *__restrict__ bks, const int64_t *__restrict__ bke, const int64_t *__restrict__ pmax, int64_t n_blk,
+    const int64_t *__restrict__ mks, const int64_t *__restrict__ mke, int64_t n_mut,
+    const int64_t *__restrict__ pair_off, int64_t *__restrict__ pair_mut, int64_t *__restrict__ pair_blk)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_mut; i += stride) {
+        const int64_t ks = mks[i], ke = mke[i];
+        if (ke <= ks) continue;
+        int64_t w = pair_off[i + 1];                         // filled back to front: ascending block order
+        const int64_t hi = upper_bound_ge(bks, n_blk, ke);
+        for (int64_t idx = hi - 1; idx >= 0; --idx) {
+            if (__ldg(pmax + idx) <= ks) break;
+            if (__ldg(bke + idx) <= ks) continue;
+            --w;
+            pair_mut[w] = i;
+            pair_blk[w] = idx;
+        }
+    }
+}
+
 inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace
@@ -289,6 +333,35 @@ int dig_site_counts(const int32_t *site_elt_d, const int32_t *site_sub_d, int64_
     if (n_site == 0 || n_elt == 0) return DIG_OK;
     DIG_CHECK_ARG(site_elt_d && site_sub_d, "null pointer");
     site_counts_kernel<<<grid_for(n_site), 256, 0, st>>>(site_elt_d, site_sub_d, n_site, n_elt, n_sub, L_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_overlap_count(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d, int64_t n_blk,
+                      const int64_t *mut_kstart_d, const int64_t *mut_kend_d, int64_t n_mut, int64_t *n_pairs_d,
+                      void *stream)
+{
+    DIG_CHECK_ARG(n_blk >= 0 && n_mut >= 0, "negative size");
+    if (n_mut == 0) return DIG_OK;
+    DIG_CHECK_ARG(mut_kstart_d && mut_kend_d && n_pairs_d, "null pointer");
+    DIG_CHECK_ARG(n_blk == 0 || (blk_kstart_d && blk_kend_d && blk_pmax_d), "null pointer");
+    overlap_count_kernel<<<grid_for(n_mut), 256, 0, (cudaStream_t)stream>>>(blk_kstart_d, blk_kend_d, blk_pmax_d, n_blk,
+                                                                            mut_kstart_d, mut_kend_d, n_mut, n_pairs_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+int dig_overlap_fill(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d, int64_t n_blk,
+                     const int64_t *mut_kstart_d, const int64_t *mut_kend_d, int64_t n_mut, const int64_t *pair_off_d,
+                     int64_t *pair_mut_d, int64_t *pair_blk_d, void *stream)
+{
+    DIG_CHECK_ARG(n_blk >= 0 && n_mut >= 0, "negative size");
+    if (n_mut == 0 || n_blk == 0) return DIG_OK;
+    DIG_CHECK_ARG(blk_kstart_d && blk_kend_d && blk_pmax_d && mut_kstart_d && mut_kend_d && pair_off_d, "null pointer");
+    DIG_CHECK_ARG(pair_mut_d && pair_blk_d, "null pointer");
+    overlap_fill_kernel<<<grid_for(n_mut), 256, 0, (cudaStream_t)stream>>>(blk_kstart_d, blk_kend_d, blk_pmax_d, n_blk,
+                                                                           mut_kstart_d, mut_kend_d, n_mut, pair_off_d,
+                                                                           pair_mut_d, pair_blk_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

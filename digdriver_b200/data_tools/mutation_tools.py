@@ -4,6 +4,7 @@ tabulation.  The bedtools subprocess + pandas group-bys of the reference are rep
 """
 import csv
 import gzip
+import os
 
 import numpy as np
 import pandas as pd
@@ -269,3 +270,121 @@ def tabulate_nonc_mutations_at_sites(f_sites, f_mut, return_sites=False):
 def tabulate_sites_in_element(f_sites, f_mut):
     df_res = tabulate_nonc_mutations_at_sites(f_sites, f_mut).set_index('ELT')
     return df_res[['OBS_SAMPLES', 'OBS_SNV']]
+
+
+# ---------------------------------------------------------------------------------------------
+# bedtools-intersect front ends of the reference, on the overlap-join kernel (dig_overlap_count / dig_overlap_fill)
+# ---------------------------------------------------------------------------------------------
+
+_BED_FIELDS = ['chrom', 'start', 'end', 'name', 'score', 'strand', 'thickStart', 'thickEnd', 'itemRgb', 'blockCount',
+               'blockSizes', 'blockStarts']
+
+
+def _overlap_join(a_chrom, a_start, a_end, b_chrom, b_start, b_end):
+    """(index into a, index into b) for every pair with a.start < b.end and b.start < a.end on the same chromosome
+    label (string comparison, as bedtools does)."""
+    ac, bc = _chrom_codes(np.asarray(a_chrom), np.asarray(b_chrom))
+    return kernels.overlap_pairs((bc << 32) | np.asarray(b_start, dtype=np.int64), (bc << 32) | np.asarray(b_end, dtype=np.int64),
+                                 (ac << 32) | np.asarray(a_start, dtype=np.int64), (ac << 32) | np.asarray(a_end, dtype=np.int64))
+
+
+def restrict_mutations_by_bed(df_mut, df_bed, unique=True, remove_X=True, replace_cols=False):
+    """Reference :8-31 (`bed_mut.intersect(bed_bed)`): one row per overlapping (mutation, interval) pair, START / END
+    clipped to the overlap, columns named like pybedtools' to_dataframe(); exact duplicate rows dropped when unique."""
+    if remove_X:
+        df_mut = df_mut[df_mut.iloc[:, 0] != "X"]
+        df_bed = df_bed[df_bed.iloc[:, 0] != "X"]
+    im, ib = _overlap_join(df_mut.iloc[:, 0].astype(str).values, df_mut.iloc[:, 1].values, df_mut.iloc[:, 2].values,
+                           df_bed.iloc[:, 0].astype(str).values, df_bed.iloc[:, 1].values, df_bed.iloc[:, 2].values)
+    df_inter = df_mut.iloc[im].reset_index(drop=True)
+    c1, c2 = df_inter.columns[1], df_inter.columns[2]
+    df_inter[c1] = np.maximum(df_inter[c1].values, df_bed.iloc[ib, 1].values)
+    df_inter[c2] = np.minimum(df_inter[c2].values, df_bed.iloc[ib, 2].values)
+    if df_inter.shape[1] <= len(_BED_FIELDS):
+        df_inter.columns = _BED_FIELDS[:df_inter.shape[1]]
+    if unique:
+        df_inter = df_inter.drop_duplicates()
+    if replace_cols:
+        df_inter.columns = df_mut.columns
+    return df_inter
+
+
+def _raw_rows_to_mutation_frame(raw, drop_duplicates, drop_sex):
+    """read_mutation_file applied to already-parsed rows (what the reference does by re-reading bedtools' temp file)."""
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".tsv", delete=False) as f:
+        raw.to_csv(f, sep="\t", header=False, index=False)
+        name = f.name
+    try:
+        if len(raw) == 0:
+            return pd.DataFrame()
+        return read_mutation_file(name, drop_duplicates=drop_duplicates, drop_sex=drop_sex)
+    finally:
+        os.remove(name)
+
+
+def restrict_mutations_by_bed_efficient(f_mut, f_bed, bed12=False, drop_duplicates=False, drop_sex=False,
+                                        replace_cols=False):
+    """Reference :33-43 (`intersect -wa`): the mutation rows overlapping the bed file (bed12: its blocks), one copy
+    per overlapping interval, then read_mutation_file's clean-up."""
+    mut = _read_raw_mutations(f_mut)
+    blocks = _read_bed_blocks(f_bed, bed12) if bed12 else pd.read_table(f_bed, header=None, low_memory=False,
+                                                                         dtype={0: str}).rename(
+        columns={0: 'CHROM', 1: 'START', 2: 'END'})
+    im, _ = _overlap_join(mut[0].values, mut[1].values, mut[2].values, blocks.CHROM.astype(str).values,
+                          blocks.START.values, blocks.END.values)
+    return _raw_rows_to_mutation_frame(mut.iloc[im], drop_duplicates, drop_sex)
+
+
+def mutations_by_element(f_mut, f_elt_bed, bed12=False, drop_duplicates=False):
+    """Reference :363-381 (`intersect -wa -wb`): every (mutation, element interval) pair with the element's name;
+    expects the 10-column annotated mutation format."""
+    mut = _read_raw_mutations(f_mut)
+    blocks = _read_bed_blocks(f_elt_bed, bed12)
+    im, ib = _overlap_join(mut[0].values, mut[1].values, mut[2].values, blocks.CHROM.values, blocks.START.values,
+                           blocks.END.values)
+    df_hits = mut.iloc[im, :10].reset_index(drop=True)
+    df_hits[13] = blocks.ELT.values[ib]
+    if drop_duplicates:
+        df_hits = df_hits.drop_duplicates([0, 1, 2, 3, 4, 5, 13])
+    df_hits.columns = ['CHROM', 'START', 'END', 'REF', 'ALT', 'SAMPLE', 'GENE', 'ANNOT', 'TYPE', 'CONTEXT', 'ELT']
+    return df_hits
+
+
+def tabulate_nonc_mutations_split(f_nonc_bed, f_mut):
+    """Reference :120-153 (`bed6().intersect(mut, wao=True)` + pivot): per (CHROM, ELT, STRAND) the sorted distinct
+    block starts / ends, the number of distinct samples hitting any block and the overlapping base pairs summed over
+    (block, mutation) pairs.  Returns (None, df_whole) like the reference."""
+    df_nonc = pd.read_table(f_nonc_bed, names=['CHROM', 'START', 'END', "ELT", "SCORE", "STRAND", 'thickStart',
+                                               'thickEnd', 'rgb', 'blockCount', 'blockSizes', 'blockStarts'],
+                            low_memory=False)
+    df_nonc['CHROM'] = df_nonc.CHROM.astype(str)
+    df_nonc = df_nonc[df_nonc.CHROM.isin(AUTOSOMES)].reset_index(drop=True)
+    df_mut = read_mutation_file(f_mut, drop_duplicates=True)
+    assert ('GENE' in df_mut.columns and 'ANNOT' in df_mut.columns and 'MUT_TYPE' in df_mut.columns)
+    rows = []
+    for r in df_nonc.itertuples(index=False):
+        sizes = [int(x) for x in str(r.blockSizes).strip(',').split(',')]
+        starts = [int(x) for x in str(r.blockStarts).strip(',').split(',')]
+        for sz, st in zip(sizes, starts):
+            rows.append((int(r.CHROM), int(r.START) + st, int(r.START) + st + sz, r.ELT, r.STRAND))
+    blk = pd.DataFrame(rows, columns=['CHROM', 'START', 'END', 'ELT', 'STRAND'])
+    im, ib = _overlap_join(df_mut.CHROM.astype(str).values, df_mut.START.values, df_mut.END.values,
+                           blk.CHROM.astype(str).values, blk.START.values, blk.END.values)
+    ov = np.minimum(df_mut.END.values[im], blk.END.values[ib]) - np.maximum(df_mut.START.values[im], blk.START.values[ib])
+    grp = blk.groupby(['CHROM', 'ELT', 'STRAND'], sort=True)
+    gid = grp.ngroup().values
+    hits = pd.DataFrame({'G': gid[ib], 'SAMPLE': df_mut.SAMPLE.values[im], 'OV': ov})
+    n_samp = hits.groupby('G').SAMPLE.nunique()
+    n_bp = hits.groupby('G').OV.sum()
+    df_whole = grp.agg(BLOCK_STARTS=('START', lambda x: sorted(set(x))), BLOCK_ENDS=('END', lambda x: sorted(set(x)))).reset_index()
+    g_of_row = np.arange(len(df_whole))
+    df_whole['OBS_SAMPLES'] = n_samp.reindex(g_of_row).fillna(0).astype(np.int64).values
+    df_whole['OBS_MUT'] = n_bp.reindex(g_of_row).fillna(0).astype(np.int64).values
+    return None, df_whole
+
+
+def _genic_fill_empty_cols(df_gene_counts):
+    """Ensures that every mutation class has a column (reference :282-291)."""
+    for c in {'Essential_Splice', 'Missense', 'Nonsense', 'Stop_loss', 'Synonymous'} - set(df_gene_counts.columns):
+        df_gene_counts[c] = 0

@@ -464,3 +464,128 @@ def selection_coefficient(df_model, mut_type, pvalue=True):
         sel, _ = kernels.selection_coefficient(obs, ex, device=_dev())
         df_model['SEL_{}'.format(mut_type)] = sel.cpu().numpy()
     return df_model
+
+
+# ---------------------------------------------------------------------------------------------
+# remaining building blocks of the reference module (scale factors, log-likelihood terms, row-level LLR tests, the
+# gamma-Poisson selection test, indel burden by transfer)
+# ---------------------------------------------------------------------------------------------
+
+def scale_factor_by_cds(h5_pretrain, df_mut_cds):
+    """Cohort scaling factor from the number of CDS mutations (reference :178-185)."""
+    return len(df_mut_cds) / storage.Store(h5_pretrain, "r").get_attrs()['N_MUT_CDS']
+
+
+def scale_factor_by_samples(h5_pretrain, df_mut):
+    """Cohort scaling factor from the number of samples (reference :187-194)."""
+    return len(df_mut.SAMPLE.unique()) / storage.Store(h5_pretrain, "r").get_attrs()['N_SAMPLES']
+
+
+def element_pvalue_burden_nb_DEPRECATED(df_model):
+    """Reference :458-471: the row loop computes the same value as element_pvalue_burden_nb's vector call."""
+    df_model['PVAL_SNV_BURDEN'] = kernels.nb_burden_test(
+        df_model.OBS_SNV.values.astype(np.float64), df_model.ALPHA.values.astype(np.float64),
+        df_model.THETA.values.astype(np.float64), df_model.Pi_SUM.values.astype(np.float64), _dev(),
+        want_exp=False)[1].cpu().numpy()
+    return df_model
+
+
+def _elementwise_ll(kind, x, a, b=None):
+    args = [np.asarray(v, dtype=np.float64) for v in ((x, a) if b is None else (x, a, b))]
+    bc = np.broadcast_arrays(*args)
+    shape = bc[0].shape
+    flat = [np.ascontiguousarray(v).reshape(-1) for v in bc]
+    out = kernels.loglik(kind, flat[0], flat[1], flat[2] if b is not None else None, _dev()).cpu().numpy()
+    for ref in (x, a, b):
+        if isinstance(ref, pd.Series):
+            return pd.Series(out, index=ref.index)
+    return out.reshape(shape) if shape else float(out[0])
+
+
+def _ll_nb(k, alpha, theta):
+    """scipy.stats.nbinom.logpmf(k, alpha, 1 / (1 + theta)) (reference :1254-1256)."""
+    return _elementwise_ll("nb", k, alpha, theta)
+
+
+def _ll_pois(k, lam):
+    """scipy.stats.poisson.logpmf(k, lam) (reference :1258-1259)."""
+    return _elementwise_ll("pois", k, lam)
+
+
+def _ll_gamma(lam, alpha, theta):
+    """scipy.stats.gamma.logpdf(lam, alpha, scale=theta) (reference :1261-1262)."""
+    return _elementwise_ll("gamma", lam, alpha, theta)
+
+
+def _mle_t(n_neut, exp_rel_neut, alpha, theta):
+    """Maximum-likelihood dN/dS rate of neutral mutations (reference :1264-1272); scalar host arithmetic, the
+    vectorised form runs inside dig_gene_dnds_sel."""
+    tml = (n_neut + alpha - 1) / (exp_rel_neut + (1 / theta))
+    if alpha <= 1:
+        tml = max(alpha * theta, tml)
+    return tml
+
+
+def _mrfold_factor(opt_t, exp_syn):
+    """dN/dS mutation-rate correction factor (reference :1274-1277)."""
+    return max(1e-10, opt_t / exp_syn)
+
+
+def _llr_rows(df, model):
+    third = "TRUNC" if model == "nb" else "NONS"
+    cls = ("SYN", "MIS", third)
+    pi3 = np.stack([np.asarray(df["Pi_%s" % c], dtype=np.float64).reshape(-1) for c in cls], axis=1)
+    obs3 = np.stack([np.asarray(df["OBS_%s" % c], dtype=np.float64).reshape(-1) for c in cls], axis=1)
+    one = lambda c: np.asarray(df[c], dtype=np.float64).reshape(-1)      # noqa: E731
+    t_syn = one("T_SYN") if model != "nb" else None
+    return kernels.gene_llr_test(model, one("ALPHA"), one("THETA"), pi3, obs3, one("MRFOLD"), t_syn, _dev()).cpu().numpy()
+
+
+def _llr_test_nb(row):
+    """NB likelihood-ratio selection tests of one row (reference :1172-1213): (p_syn, p_mis, p_trunc, p_nsyn)."""
+    out = _llr_rows(row, "nb")
+    return tuple(float(v) for v in out[:, 0])
+
+
+def _llr_test_gamma_poiss(row):
+    """Gamma-Poisson likelihood-ratio selection tests of one row (reference :1215-1252): (p_syn, p_mis, p_nons,
+    p_nsyn)."""
+    out = _llr_rows(row, "gamma_poisson")
+    return tuple(float(v) for v in out[:, 0])
+
+
+def gene_pvalue_sel_gamma(df_model):
+    """dN/dS selection p-values from the more aggressive gamma-Poisson model (reference :749-765); needs the T_SYN and
+    MRFOLD columns of gene_expected_muts_dnds."""
+    out = _llr_rows(df_model, "gamma_poisson")
+    for i, c in enumerate(("SYN", "MIS", "NONS", "NONSYN")):
+        df_model['PVAL_%s_SEL_PG' % c] = out[i]
+    return df_model
+
+
+def gene_pvalue_indel_by_transfer(df_model):
+    """Indel burden with the SNV model's parameters and a uniform per-base indel probability (reference :678-707)."""
+    f_cds = None
+    for d in (os.environ.get("DIG_DATA_DIR", ""), DATA_DIR):
+        if d and os.path.exists(os.path.join(d, 'dndscv_gene_cds.bed.gz')):
+            f_cds = os.path.join(d, 'dndscv_gene_cds.bed.gz')
+            break
+    if f_cds is None:
+        raise FileNotFoundError("dndscv_gene_cds.bed.gz (shipped by the reference under DIGDriver/data) not found; "
+                                "set DIG_DATA_DIR")
+    df_cds = pd.read_table(f_cds, names=['CHROM', 'START', 'END', 'GENE'], low_memory=False)
+    df_cds['LENGTH'] = df_cds.END - df_cds.START
+    df_cds_l = df_cds.pivot_table(index='GENE', values='LENGTH', aggfunc="sum")
+    df_model = df_model.merge(df_cds_l['LENGTH'], left_index=True, right_index=True, how='left')
+    df_model['Pi_INDEL'] = df_model.LENGTH / (df_model.R_SIZE)
+    df_model_null = df_model[~df_model.index.isin(_cosmic_genes())]
+    EXP_INDEL_UNIF = (df_model_null.Pi_INDEL * df_model_null.ALPHA * df_model_null.THETA).sum()
+    t_indel = df_model_null.OBS_INDEL.sum() / EXP_INDEL_UNIF
+    df_model['THETA_INDEL'] = df_model.THETA * t_indel
+    exp, pval = kernels.nb_burden_test(df_model.OBS_INDEL.values.astype(np.float64),
+                                       df_model.ALPHA.values.astype(np.float64),
+                                       df_model.THETA_INDEL.values.astype(np.float64),
+                                       df_model.Pi_INDEL.values.astype(np.float64), _dev())
+    df_model['EXP_INDEL'] = exp.cpu().numpy()
+    df_model['PVAL_INDEL_BURDEN'] = pval.cpu().numpy()
+    return df_model

@@ -506,3 +506,97 @@ def site_test(site_chrom, site_start, site_sub, site_k, window, win_map_off, win
         _check_status(status, "dig_site_test", status_sink)
     out["DENOM_PLUS"], out["DENOM_MINUS"] = den_p, den_m
     return {k: v for k, v in out.items() if v is not None}
+
+
+NB_MODES = {"greater": 0, "greater_midp": 1, "less": 2, "less_midp": 3, "exact": 4, "midp": 5}
+
+
+def nb_pvalue_variant(mode, k, alpha, p, mu=None, device="cuda:0", stream=None):
+    """The other tail conventions of nb_model.py (:243-337) element-wise in FP64 on the GPU; mode is a key of
+    NB_MODES.  mu (optional array) is the expectation override of nb_pvalue_exact / nb_pvalue_midp."""
+    dev = torch.device(device)
+    kk, aa, pp = (_dev(x, torch.float64, dev).contiguous() for x in (k, alpha, p))
+    mm = _dev(mu, torch.float64, dev).contiguous() if mu is not None else None
+    out = torch.empty_like(kk)
+    with torch.cuda.device(dev):
+        _lib.call("dig_nb_pvalue_variant", NB_MODES[mode], kk.data_ptr(), aa.data_ptr(), pp.data_ptr(), _ptr(mm),
+                  kk.numel(), out.data_ptr(), _stream(dev, stream))
+    return out
+
+
+LL_KINDS = {"nb": 0, "pois": 1, "gamma": 2}
+
+
+def loglik(kind, x, a, b=None, device="cuda:0", stream=None):
+    """_ll_nb(k, alpha, theta) / _ll_pois(k, lam) / _ll_gamma(lam, alpha, theta) (transfer_tools.py:1254-1262)."""
+    dev = torch.device(device)
+    xx, aa = _dev(x, torch.float64, dev).contiguous(), _dev(a, torch.float64, dev).contiguous()
+    bb = _dev(b, torch.float64, dev).contiguous() if b is not None else None
+    out = torch.empty_like(xx)
+    with torch.cuda.device(dev):
+        _lib.call("dig_loglik", LL_KINDS[kind], xx.data_ptr(), aa.data_ptr(), _ptr(bb), xx.numel(), out.data_ptr(),
+                  _stream(dev, stream))
+    return out
+
+
+def gene_llr_test(model, alpha, theta, pi3, obs3, mrfold, t_syn=None, device="cuda:0", stream=None):
+    """_llr_test_nb (model "nb"; SYN, MIS, TRUNC) / _llr_test_gamma_poiss (model "gamma_poisson"; SYN, MIS, NONS) for
+    every row: float64 [4, n] = p_syn, p_mis, p_third, p_nonsyn."""
+    dev = torch.device(device)
+    a, t, m = (_dev(x, torch.float64, dev).contiguous() for x in (alpha, theta, mrfold))
+    p3, o3 = _dev(pi3, torch.float64, dev).contiguous(), _dev(obs3, torch.float64, dev).contiguous()
+    ts = _dev(t_syn, torch.float64, dev).contiguous() if t_syn is not None else None
+    n = a.numel()
+    assert p3.shape == (n, 3) and o3.shape == (n, 3)
+    out = torch.empty((4, n), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_gene_llr_test", {"nb": 0, "gamma_poisson": 1}[model], a.data_ptr(), t.data_ptr(), p3.data_ptr(),
+                  o3.data_ptr(), m.data_ptr(), _ptr(ts), n, out.data_ptr(), _stream(dev, stream))
+    return out
+
+
+def overlap_pairs(blk_kstart, blk_kend, mut_kstart, mut_kend, device="cuda:0", stream=None):
+    """Overlap join (`bedtools intersect -wa -wb`): int64 arrays (pair_mut, pair_blk) on the host, one entry per
+    overlapping (mutation, block) pair, grouped by mutation in input order; block indices refer to the caller's
+    (unsorted) block order."""
+    dev = torch.device(device)
+    bks = np.asarray(blk_kstart, dtype=np.int64)
+    order = np.argsort(bks, kind="stable")
+    bks = bks[order]
+    bke = np.asarray(blk_kend, dtype=np.int64)[order]
+    pmax = np.maximum.accumulate(bke) if len(bke) else bke
+    b0, b1, b2 = (_dev(x, torch.int64, dev) for x in (bks, bke, pmax))
+    m0, m1 = _dev(mut_kstart, torch.int64, dev), _dev(mut_kend, torch.int64, dev)
+    n_blk, n_mut = len(bks), m0.numel()
+    sptr = _stream(dev, stream)
+    off = torch.zeros(n_mut + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        cnt = torch.zeros(max(n_mut, 1), dtype=torch.int64, device=dev)
+        _lib.call("dig_overlap_count", _ptr(b0), _ptr(b1), _ptr(b2), n_blk, m0.data_ptr(), m1.data_ptr(), n_mut,
+                  cnt.data_ptr(), sptr)
+        off[1:] = torch.cumsum(cnt[:n_mut], 0)
+        total = int(off[-1].item()) if n_mut else 0
+        pm = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        pb = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        if total:
+            _lib.call("dig_overlap_fill", b0.data_ptr(), b1.data_ptr(), b2.data_ptr(), n_blk, m0.data_ptr(),
+                      m1.data_ptr(), n_mut, off.data_ptr(), pm.data_ptr(), pb.data_ptr(), sptr)
+    return pm[:total].cpu().numpy(), order[pb[:total].cpu().numpy()]
+
+
+def overlap_counts(blk_kstart, blk_kend, mut_kstart, mut_kend, device="cuda:0", stream=None):
+    """Number of blocks each mutation overlaps (dig_overlap_count): int64 host array [n_mut]."""
+    dev = torch.device(device)
+    bks = np.asarray(blk_kstart, dtype=np.int64)
+    order = np.argsort(bks, kind="stable")
+    bks = bks[order]
+    bke = np.asarray(blk_kend, dtype=np.int64)[order]
+    pmax = np.maximum.accumulate(bke) if len(bke) else bke
+    b0, b1, b2 = (_dev(x, torch.int64, dev) for x in (bks, bke, pmax))
+    m0, m1 = _dev(mut_kstart, torch.int64, dev), _dev(mut_kend, torch.int64, dev)
+    n_mut = m0.numel()
+    cnt = torch.zeros(max(n_mut, 1), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_overlap_count", _ptr(b0), _ptr(b1), _ptr(b2), len(bks), m0.data_ptr(), m1.data_ptr(), n_mut,
+                  cnt.data_ptr(), _stream(dev, stream))
+    return cnt[:n_mut].cpu().numpy()

@@ -222,12 +222,9 @@ def restrict_mutations_to_regions(df_mut, regions):
         return df_mut.iloc[:0]
     rk_s = (regs[:, 0].astype(np.int64) << 32) | regs[:, 1].astype(np.int64)
     rk_e = (regs[:, 0].astype(np.int64) << 32) | regs[:, 2].astype(np.int64)
-    order = np.argsort(rk_s, kind="stable")
-    rk_s, rk_e = rk_s[order], np.maximum.accumulate(rk_e[order])
     mk_s = (df_mut.CHROM.values.astype(np.int64) << 32) | df_mut.START.values.astype(np.int64)
     mk_e = (df_mut.CHROM.values.astype(np.int64) << 32) | df_mut.END.values.astype(np.int64)
-    hi = np.searchsorted(rk_s, mk_e, side="left")            # regions starting before the mutation ends
-    hit = (hi > 0) & (rk_e[np.maximum(hi - 1, 0)] > mk_s)
+    hit = kernels.overlap_counts(rk_s, rk_e, mk_s, mk_e, default_device()) > 0
     return df_mut[hit].drop_duplicates()
 
 

@@ -316,6 +316,64 @@ int dig_nb_pvalue_exact(const double *k_d, const double *alpha_d, const double *
                         void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * The other p-value conventions of nb_model.py, element-wise like dig_nb_pvalue_greater_midp.  mu_d (may be NULL)
+ * is the optional expectation of nb_pvalue_exact / nb_pvalue_midp; NULL or a 0 entry means alpha (1-p)/p, the
+ * reference's `if not mu`.
+ *   DIG_NB_GREATER       nb_pvalue_greater                  nb_model.py:243-256
+ *   DIG_NB_GREATER_MIDP  nb_pvalue_greater_midp(_DEPRECATED)           :258-278 (the two agree for every k)
+ *   DIG_NB_LESS          nb_pvalue_less                                :280-283 (the value the reference computes
+ *                        but does not return)
+ *   DIG_NB_LESS_MIDP     nb_pvalue_less_midp                           :285-296
+ *   DIG_NB_EXACT         nb_pvalue_exact(k, alpha, p, mu)              :298-314
+ *   DIG_NB_MIDP          nb_pvalue_midp(k, alpha, p, mu)               :316-337
+ */
+#define DIG_NB_GREATER 0
+#define DIG_NB_GREATER_MIDP 1
+#define DIG_NB_LESS 2
+#define DIG_NB_LESS_MIDP 3
+#define DIG_NB_EXACT 4
+#define DIG_NB_MIDP 5
+int dig_nb_pvalue_variant(int mode, const double *k_d, const double *alpha_d, const double *p_d, const double *mu_d,
+                          int64_t n, double *pval_out_d, void *stream);
+
+/* Log-likelihood terms of the selection tests, element-wise (transfer_tools.py:1254-1262):
+ *   DIG_LL_NB     _ll_nb(k = x, alpha = a, theta = b)      scipy.stats.nbinom.logpmf(k, alpha, 1 / (1 + theta))
+ *   DIG_LL_POIS   _ll_pois(k = x, lam = a)                 scipy.stats.poisson.logpmf (b_d unused, may be NULL)
+ *   DIG_LL_GAMMA  _ll_gamma(lam = x, alpha = a, theta = b) scipy.stats.gamma.logpdf(lam, alpha, scale=theta)
+ */
+#define DIG_LL_NB 0
+#define DIG_LL_POIS 1
+#define DIG_LL_GAMMA 2
+int dig_loglik(int kind, const double *x_d, const double *a_d, const double *b_d, int64_t n, double *out_d, void *stream);
+
+/* Row-level likelihood-ratio selection tests with the caller's MRFOLD: _llr_test_nb (transfer_tools.py:1172-1213;
+ * pi3 / obs3 = SYN, MIS, TRUNC) and _llr_test_gamma_poiss (:1215-1252; SYN, MIS, NONS; needs t_syn_d), as called from
+ * gene_pvalue_sel_nb (:657-676) and gene_pvalue_sel_gamma (:749-765).  pi3_d / obs3_d are [n, 3] row-major;
+ * out_d is [4, n]: p_syn, p_mis, p_(trunc|nons), p_nonsyn (chi2.sf with 1, 1, 1, 2 degrees of freedom).
+ */
+#define DIG_LLR_NB 0
+#define DIG_LLR_GAMMA_POISSON 1
+int dig_gene_llr_test(int model, const double *alpha_d, const double *theta_d, const double *pi3_d, const double *obs3_d,
+                      const double *mrfold_d, const double *t_syn_d, int64_t n, double *out_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * Overlap join: every (mutation, block) pair with mut_kstart < blk_kend and blk_kstart < mut_kend, i.e. the rows of
+ * `bedtools intersect -wa -wb` that mutation_tools.restrict_mutations_by_bed (mutation_tools.py:8-31),
+ * restrict_mutations_by_bed_efficient (:33-43), mutations_by_element (:363-381) and tabulate_nonc_mutations_split
+ * (:120-153) post-process with pandas.  Keys are chrom code << 32 | position; blocks sorted by kstart with
+ * blk_pmax_d the running maximum of blk_kend (as for dig_tabulate_elements).
+ *   dig_overlap_count: n_pairs_d[i] = number of blocks mutation i overlaps.
+ *   dig_overlap_fill : pair_off_d [n_mut + 1] = exclusive scan of n_pairs (caller's); writes pair_mut_d / pair_blk_d
+ *                      [pair_off[n_mut]], grouped by mutation in input order, ascending block index inside a group.
+ */
+int dig_overlap_count(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d, int64_t n_blk,
+                      const int64_t *mut_kstart_d, const int64_t *mut_kend_d, int64_t n_mut, int64_t *n_pairs_d,
+                      void *stream);
+int dig_overlap_fill(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d, int64_t n_blk,
+                     const int64_t *mut_kstart_d, const int64_t *mut_kend_d, int64_t n_mut, const int64_t *pair_off_d,
+                     int64_t *pair_mut_d, int64_t *pair_blk_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Synthetic genome generator (BASELINE.json configs are synthetic): position g is a pure
  * function of (seed, g); identical to orc_synth_genome in oracle/dig_oracle.c.
  */

@@ -107,13 +107,8 @@ def test_fasta_reader(tmp_path):
     assert g.lengths.tolist() == [8, 2]
 
 
-def test_restrict_mutations_to_regions_and_qvals():
-    from digdriver_b200.sequence_model import sequence_tools as st
+def test_qvals():
     from digdriver_b200.sequence_model.nb_model import get_q_vals
-    mut = pd.DataFrame({"CHROM": [1, 1, 1, 2, 2], "START": [5, 10, 19, 5, 30], "END": [6, 11, 25, 6, 31],
-                        "REF": list("AAAAA"), "ALT": list("CCCCC")})
-    got = st.restrict_mutations_to_regions(mut, np.array([[1, 10, 20], [2, 0, 10]]))
-    assert got.START.tolist() == [10, 19, 5]
     q = get_q_vals([0.01, 0.04, 0.03, 0.5])
     np.testing.assert_allclose(q, [0.04, 0.04 * 4 / 3, 0.04 * 4 / 3, 0.5])
 
