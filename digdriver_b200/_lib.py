@@ -54,6 +54,8 @@ SIGNATURES = {
     "dig_nb_pvalue_variant": (_I, [_I, _P, _P, _P, _P, _I64, _P, _P]),
     "dig_loglik": (_I, [_I, _P, _P, _P, _I64, _P, _P]),
     "dig_gene_llr_test": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "dig_element_region_counts": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I, _P, _P, _P, _P]),
+    "dig_element_psum": (_I, [_P, _P, _P, _I64, _P, _P, _P]),
     "dig_overlap_count": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "dig_overlap_fill": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
 }
@@ -69,6 +71,7 @@ KERNELS_PER_CALL = {
     "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
     "dig_window_denominators": 1, "dig_site_test": 1, "dig_gene_dnds_sel": 1, "dig_selection_coefficient": 1, "dig_region_prob_norm": 1, "dig_position_obs": 1, "dig_position_test": 1, "dig_nb_pvalue_exact": 1,
     "dig_nb_pvalue_variant": 1, "dig_loglik": 1, "dig_gene_llr_test": 1, "dig_overlap_count": 1, "dig_overlap_fill": 1,
+    "dig_element_region_counts": 1, "dig_element_psum": 1,
 }
 launch_count = 0
 

@@ -31,6 +31,9 @@ __device__ __forceinline__ int revcomp3(int c)
 __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 
+// RC = true (dig_element_region_counts) also writes the strand-flipped 64-context region counts of every element and
+// tolerates n_cohort == 0 with the cohort / result pointers NULL; RC = false is the production K6 instantiation.
+template <bool RC>
 __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
     const int32_t *__restrict__ elt_chrom, const int8_t *__restrict__ elt_strand,
     const int64_t *__restrict__ blk_ptr, const int64_t *__restrict__ blk_start,
@@ -41,7 +44,8 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
     const int32_t *__restrict__ blk_counts, const double *__restrict__ L_elt, int n_col, int span_words,
     double *__restrict__ mu_out, double *__restrict__ sigma_out, double *__restrict__ robs_out,
     uint8_t *__restrict__ flag_out, int64_t *__restrict__ r_size, int64_t *__restrict__ elt_size,
-    double *__restrict__ p_out, int32_t *__restrict__ n_win_out, int32_t *__restrict__ status)
+    double *__restrict__ p_out, int32_t *__restrict__ n_win_out, int32_t *__restrict__ status,
+    int64_t *__restrict__ region_counts_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -210,6 +214,10 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
             for (int o = 16; o > 0; o >>= 1) gene_len += __shfl_xor_sync(0xffffffffu, gene_len, o);
         }
         __syncwarp();
+        if (RC) {
+            region_counts_out[e * 64 + lane] = (int64_t)r64[lane];
+            region_counts_out[e * 64 + lane + 32] = (int64_t)r64[lane + 32];
+        }
         const double rsum = warp_sum(r_lo + r_hi);
         const double lsum = warp_sum(l_lo + l_hi);
 
@@ -282,8 +290,8 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
             }
         }
         if (lane == 0) {
-            r_size[e] = (int64_t)rsum;                       // int(sum(R192)/3) == sum(R64)
-            elt_size[e] = blk_counts != nullptr ? (int64_t)lsum : gene_len;
+            if (!RC || r_size) r_size[e] = (int64_t)rsum;    // int(sum(R192)/3) == sum(R64)
+            if (!RC || elt_size) elt_size[e] = blk_counts != nullptr ? (int64_t)lsum : gene_len;
             n_win_out[e] = nw;
         }
         __syncwarp();
@@ -322,14 +330,101 @@ extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *el
                        max_span_windows, smem);
         return DIG_ERR_UNSUPPORTED;
     }
-    DIG_CUDA(cudaFuncSetAttribute(transfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DIG_CUDA(cudaFuncSetAttribute(transfer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (n_elt + TW - 1) / TW;
     const int64_t cap = (int64_t)dig::sm_count() * 64;      // ~one element per warp: the hardware scheduler balances long genes
     if (blocks > cap) blocks = cap;
-    transfer_kernel<<<(unsigned)blocks, TW * 32, smem, st>>>(
+    transfer_kernel<false><<<(unsigned)blocks, TW * 32, smem, st>>>(
         elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, win_map_off_d, win_map_d,
         win_counts_d, y_pred_d, std_d, y_true_d, flag_d, n_win, n_cohort, d_pr_d, blk_counts_d, L_elt_d, n_col,
-        span_words, mu_d, sigma_d, r_obs_d, flag_out_d, r_size_d, elt_size_d, p_out_d, n_win_out_d, status_d);
+        span_words, mu_d, sigma_d, r_obs_d, flag_out_d, r_size_d, elt_size_d, p_out_d, n_win_out_d, status_d, nullptr);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+// The persisted intermediate of preprocess_nonc / preprocess_sites (sequence_tools.py:596-711): region_counts of every
+// element = sum of the 64 trinucleotide counts of its overlapped windows, reverse-complemented for minus-strand
+// elements (the reference stores it repeated x3 as 192 values).  Same kernel as dig_element_transfer, no cohorts.
+extern "C" int dig_element_region_counts(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
+                                         const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt,
+                                         int64_t window, const int64_t *win_map_off_d, const int32_t *win_map_d,
+                                         const int32_t *win_counts_d, int64_t n_win, int max_span_windows,
+                                         int64_t *region_counts_d, int32_t *n_win_out_d, int32_t *status_d, void *stream)
+{
+    DIG_CHECK_ARG(n_elt >= 0 && n_win >= 0 && window > 0 && max_span_windows >= 1, "bad sizes");
+    DIG_CHECK_ARG(status_d != nullptr, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    DIG_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int32_t), st));
+    if (n_elt == 0) return DIG_OK;
+    DIG_CHECK_ARG(elt_chrom_d && elt_strand_d && blk_ptr_d && blk_start_d && blk_end_d && win_map_off_d && win_map_d &&
+                      win_counts_d && region_counts_d && n_win_out_d,
+                  "null pointer");
+    const int span_words = ((max_span_windows + 31) / 32 + 3) & ~3;
+    const size_t smem = (size_t)TW * (128 * sizeof(double) + (size_t)span_words * sizeof(uint32_t));
+    if (smem > 200 * 1024) {
+        dig::set_error("dig_element_region_counts: window span of %d windows needs %zu B of shared memory",
+                       max_span_windows, smem);
+        return DIG_ERR_UNSUPPORTED;
+    }
+    DIG_CUDA(cudaFuncSetAttribute(transfer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (n_elt + TW - 1) / TW;
+    const int64_t cap = (int64_t)dig::sm_count() * 64;
+    if (blocks > cap) blocks = cap;
+    transfer_kernel<true><<<(unsigned)blocks, TW * 32, smem, st>>>(
+        elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, win_map_off_d, win_map_d,
+        win_counts_d, nullptr, nullptr, nullptr, nullptr, n_win, 0, nullptr, nullptr, nullptr, 0, span_words, nullptr,
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_win_out_d, status_d, region_counts_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+// P_SUM of nonc_model (genic_driver_tools.py:361-369) from the PERSISTED intermediates: prob_sum = region_counts * d_pr,
+// t_pi = d_pr / prob_sum.sum(), p_mut = (t_pi * L).sum().  One warp per element, the same lane assignment and
+// summation order as transfer_kernel, so the result is bit-identical to dig_element_transfer's P for the same counts.
+namespace {
+
+__global__ void __launch_bounds__(128) element_psum_kernel(const double *__restrict__ L, const int64_t *__restrict__ R,
+                                                           const double *__restrict__ d_pr, int64_t n_elt,
+                                                           double *__restrict__ p_out, double *__restrict__ denom_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = gwarp; e < n_elt; e += nwarps) {
+        double part = 0.0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const int j = lane + 32 * t;
+            part += __ldg(d_pr + j) * (double)__ldg(R + e * 192 + j);
+        }
+        const double denom = warp_sum(part);
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const int j = lane + 32 * t;
+            acc += (__ldg(d_pr + j) / denom) * __ldg(L + e * 192 + j);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            p_out[e] = acc;
+            if (denom_out) denom_out[e] = denom;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int dig_element_psum(const double *L_d, const int64_t *region_counts_d, const double *d_pr_d, int64_t n_elt,
+                                double *p_out_d, double *denom_out_d, void *stream)
+{
+    DIG_CHECK_ARG(n_elt >= 0, "negative size");
+    if (n_elt == 0) return DIG_OK;
+    DIG_CHECK_ARG(L_d && region_counts_d && d_pr_d && p_out_d, "null pointer");
+    int64_t blocks = (n_elt + 3) / 4;
+    const int64_t cap = (int64_t)dig::sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    element_psum_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(L_d, region_counts_d, d_pr_d, n_elt, p_out_d,
+                                                                           denom_out_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }

@@ -600,3 +600,42 @@ def overlap_counts(blk_kstart, blk_kend, mut_kstart, mut_kend, device="cuda:0", 
         _lib.call("dig_overlap_count", _ptr(b0), _ptr(b1), _ptr(b2), len(bks), m0.data_ptr(), m1.data_ptr(), n_mut,
                   cnt.data_ptr(), _stream(dev, stream))
     return cnt[:n_mut].cpu().numpy()
+
+
+def element_region_counts(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window, win_map_off, win_map, win_counts,
+                          device="cuda:0", stream=None, status_sink=None):
+    """The `region_counts` intermediate of preprocess_nonc / preprocess_sites: int64 [n_elt, 64] sums of the window
+    trinucleotide counts over each element's overlapped windows (reverse-complemented for minus-strand elements) and
+    the number of windows per element."""
+    dev = torch.device(device)
+    ec, es = _dev(elt_chrom, torch.int32, dev), _dev(elt_strand, torch.int8, dev)
+    bp, bs, be = (_dev(x, torch.int64, dev) for x in (blk_ptr, blk_start, blk_end))
+    wmo, wm = _dev(win_map_off, torch.int64, dev), _dev(win_map, torch.int32, dev)
+    wc = _dev(win_counts, torch.int32, dev).contiguous()
+    n_elt = ec.numel()
+    rc = torch.empty((max(n_elt, 1), 64), dtype=torch.int64, device=dev)
+    nw = torch.empty(max(n_elt, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_element_region_counts", ec.data_ptr(), es.data_ptr(), bp.data_ptr(), bs.data_ptr(), be.data_ptr(),
+                  n_elt, int(window), wmo.data_ptr(), wm.data_ptr(), wc.data_ptr(), wc.shape[0],
+                  element_max_span(bp, bs, be, window), rc.data_ptr(), nw.data_ptr(), status.data_ptr(),
+                  _stream(dev, stream))
+        _check_status(status, "dig_element_region_counts", status_sink)
+    return rc[:n_elt], nw[:n_elt]
+
+
+def element_psum(L, region_counts, d_pr, device="cuda:0", stream=None, want_denom=False):
+    """P_SUM from persisted L_counts / region_counts [n_elt, 192] (dig_element_psum)."""
+    dev = torch.device(device)
+    Ld = _dev(L, torch.float64, dev).contiguous().reshape(-1, 192)
+    Rd = _dev(region_counts, torch.int64, dev).contiguous().reshape(-1, 192)
+    dp = _dev(d_pr, torch.float64, dev).contiguous()
+    n = Ld.shape[0]
+    assert Rd.shape[0] == n and dp.numel() == 192
+    p = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    den = torch.empty(max(n, 1), dtype=torch.float64, device=dev) if want_denom else None
+    with torch.cuda.device(dev):
+        _lib.call("dig_element_psum", Ld.data_ptr(), Rd.data_ptr(), dp.data_ptr(), n, p.data_ptr(), _ptr(den),
+                  _stream(dev, stream))
+    return (p[:n], den[:n]) if want_denom else p[:n]

@@ -173,7 +173,7 @@ def genic_model_arrays(genes, region_model, win_counts64, d_pr):
 
 
 def genic_model_parallel(f_pretrained_str, f_genic_str, N_procs=1, counts_key="window_10kb/counts",
-                         indels_direct=False, f_fasta=None):
+                         indels_direct=False, f_fasta=None, genes_lst=None):
     """Reference :206-226.  f_genic is a store with the f_genic layout flattened to arrays: 'genes' table
     (GENE, CHROM, STRAND), 'cds_ptr', 'cds_start', 'cds_end' (inclusive intervals) and 'L_data' [E,192,4];
     the window trinucleotide counts come from f_pretrained's 'window_counts_64' (written by
@@ -187,6 +187,10 @@ def genic_model_parallel(f_pretrained_str, f_genic_str, N_procs=1, counts_key="w
     keep = ~meta.CHROM.astype(str).isin(['X', 'Y']).values            # reference :89-90
     ptr = gs.read_array('cds_ptr')
     sel = np.flatnonzero(keep)
+    if genes_lst is not None:                                         # genic_model's chunk, in the caller's order
+        row_of = {str(g): i for i, g in enumerate(meta.GENE.values)}
+        rows = np.array([row_of[str(g)] for g in genes_lst], dtype=np.int64)      # KeyError for an unknown gene
+        sel = rows[keep[rows]]
     lens = np.diff(ptr)[sel]
     new_ptr = np.zeros(len(sel) + 1, dtype=np.int64)
     new_ptr[1:] = np.cumsum(lens)
@@ -297,3 +301,117 @@ def tiled_model_parallel(f_pretrained, f_nonc_data, save_key, N_procs=1):
     rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
     L_table = data.read_table("{}/L_counts".format(save_key))
     return tiled_model_arrays(L_table.index, L_table, rm, win_vals[rows].astype(np.int32), d_pr)
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's per-chunk workers (what its multiprocessing.Pool ran on a slice of the element list)
+# --------------------------------------------------------------------------------------------
+
+def genic_model(genes_lst, f_pretrained_str, f_genic_str, counts_key, indels_direct):
+    """Reference :31-203: the genic pretrain rows of the genes in ``genes_lst`` (X / Y genes are dropped)."""
+    return genic_model_parallel(f_pretrained_str, f_genic_str, counts_key=counts_key, indels_direct=indels_direct,
+                                genes_lst=list(genes_lst))
+
+
+def tiled_nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key):
+    """Reference :599-690: the tiled pretrain rows of the tiles in ``elt_lst`` ('chr{c}:{s}-{e}' names)."""
+    pre = storage.Store(f_pretrained, "r")
+    rm = RegionModel(pre.read_table('region_params'))
+    d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
+    data = storage.Store(f_nonc_data, "r")
+    wkey = 'window_{}'.format(rm.window)
+    win_idx = data.read_array('{}/full_window_si_index'.format(wkey))
+    win_vals = data.read_array('{}/full_window_si_values'.format(wkey))
+    key = {tuple(r): i for i, r in enumerate(map(tuple, win_idx))}
+    rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
+    return tiled_model_arrays(list(elt_lst), data.read_table("{}/L_counts".format(save_key)), rm,
+                              win_vals[rows].astype(np.int32), d_pr)
+
+
+def _region_params_of_overlaps(region_model, overlaps):
+    """get_region_params_direct (reference :258-272) for many elements in one K6 launch: every overlapped window is
+    handed to the kernel as a one-base block, so its window set is exactly the persisted overlap list."""
+    E = len(overlaps)
+    ptr = np.zeros(E + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(o) for o in overlaps])
+    chrom = np.array([int(o[0][0]) if len(o) else 1 for o in overlaps], dtype=np.int64)
+    starts = np.array([w[1] for o in overlaps for w in o], dtype=np.int64)
+    n = len(region_model.df)
+    return transfer_elements(region_model, np.zeros((n, 64), dtype=np.int32), np.ones(192), chrom,
+                             np.ones(E, dtype=np.int8), ptr, starts, starts + 1, L_elt=np.zeros((E, 192, 1)))
+
+
+def nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key, indels_direct):
+    """Reference :300-431: element pretrain rows from the intermediates persisted by sequence_tools.preprocess_nonc /
+    preprocess_sites (L_counts, region_counts and the overlap list of every element)."""
+    pre = storage.Store(f_pretrained, "r")
+    rm = RegionModel(pre.read_table('region_params'))
+    d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
+    data = storage.Store(f_nonc_data, "r")
+    names, L, R, overlaps = data.read_element_groups('window_{}/{}'.format(rm.window, save_key), list(elt_lst))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    p_sum = kernels.element_psum(L, R, d_pr, dev).cpu().numpy()
+    res = _region_params_of_overlaps(rm, overlaps)
+    if indels_direct:
+        res_ind = _region_params_of_overlaps(RegionModel(pre.read_table('region_params_indels')), overlaps)
+    else:
+        res_ind = res
+    r_size = (R.sum(axis=1) / 3).astype(np.int64)             # int(region_counts.sum() / 3)
+    elt_size = (L.sum(axis=1) / 3).astype(np.int64)           # int(np.sum(L) / 3)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_indel = elt_size / r_size.astype(np.float64)
+    return pd.DataFrame({
+        'ELT': names, 'ELT_SIZE': elt_size, 'FLAG': res["FLAG"], 'R_SIZE': r_size, 'R_OBS': res["R_OBS"],
+        'R_INDEL': res_ind["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"], 'MU_INDEL': res_ind["MU"],
+        'SIGMA_INDEL': res_ind["SIGMA"], 'P_SUM': p_sum, 'P_INDEL': p_indel})
+
+
+def nonc_model_region(df_nonc, f_pretrained, f_nonc_data, nonc_L_key, f_sites=None, return_intermediates=False):
+    """Reference :518-597 (its own version unpacks three of get_region_params' four return values and cannot run;
+    this one computes what it set out to): R_OBS, MU, SIGMA, P_SUM per row of a bed12_boundaries-style frame, with the
+    block context counts read from the table ``nonc_L_key`` and the window counts from the store's root
+    'full_window_si_index' / 'full_window_si_values'.  With return_intermediates also (L, t_pi) frames."""
+    df_nonc = df_nonc.copy().astype({'CHROM': int, 'ELT': str, 'STRAND': str})
+    pre = storage.Store(f_pretrained, "r")
+    rm = RegionModel(pre.read_table('region_params'))
+    df192 = pre.read_table('sequence_model_192')
+    d_pr = sequence_tools.d_pr_from_model192(df192)
+    data = storage.Store(f_nonc_data, "r")
+    L_contexts = data.read_table(nonc_L_key)
+    win_idx = data.read_array('full_window_si_index')
+    win_vals = data.read_array('full_window_si_values')
+    key = {tuple(r): i for i, r in enumerate(map(tuple, win_idx))}
+    rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
+    win_counts = win_vals[rows].astype(np.int32)
+    out = nonc_model_arrays(df_nonc, L_contexts, rm, win_counts, d_pr)
+    res = df_nonc.drop(['BLOCK_STARTS', 'BLOCK_ENDS'], axis=1)
+    for c in ('R_OBS', 'MU', 'SIGMA', 'P_SUM'):
+        res[c] = out[c].values
+    if not return_intermediates:
+        return res
+    idx = sequence_tools.mk_trans_idx(1, 1)
+    E = len(df_nonc)
+    ptr = np.zeros(E + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(b) for b in df_nonc.BLOCK_STARTS])
+    bs = np.array([x for b in df_nonc.BLOCK_STARTS for x in b], dtype=np.int64)
+    be = np.array([x for b in df_nonc.BLOCK_ENDS for x in b], dtype=np.int64)
+    owner = np.repeat(np.arange(E), np.diff(ptr))
+    chrom = df_nonc.CHROM.values.astype(np.int64)
+    keys = ['chr{}:{}-{}'.format(c, s, e) for c, s, e in zip(chrom[owner], bs, be)]
+    L = np.zeros((E, 192), dtype=np.float64)
+    np.add.at(L, owner, L_contexts.loc[keys].values)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rc, _ = kernels.element_region_counts(chrom.astype(np.int32), _strand_code(df_nonc.STRAND.values), ptr, bs, be,
+                                          rm.window, rm.win_map_off, rm.win_map, win_counts, dev)
+    _, denom = kernels.element_psum(L, np.repeat(rc.cpu().numpy(), 3, axis=1), d_pr, dev, want_denom=True)
+    t_pi = d_pr[None, :] / denom.cpu().numpy()[:, None]
+    return res, pd.DataFrame(L, columns=idx, index=df_nonc.ELT), pd.DataFrame(t_pi, columns=idx, index=df_nonc.ELT)
+
+
+def nonc_model_region_parallel(f_bed, f_pretrained, f_nonc_data, nonc_L_key, N_procs, f_sites=None):
+    """Reference :463-516: nonc_model_region over every autosomal row of a bed12 file."""
+    from ..data_tools import mutation_tools
+    print('Parsing regions bed file')
+    df_nonc = mutation_tools.bed12_boundaries(f_bed)
+    print('Pretraining model')
+    return nonc_model_region(df_nonc, f_pretrained, f_nonc_data, nonc_L_key, f_sites)

@@ -338,3 +338,179 @@ def base_probabilities_by_region(fasta, S_prob, CHROM, START, END, n_up=2, n_dow
                                 np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64), n_up=n_up, n_down=n_down,
                                 binsize=1, normed=normed, want=("pt", "pos"))
     return out["pt"].cpu().numpy(), out["pos"].cpu().numpy().astype(np.int64)
+
+
+# --------------------------------------------------------------------------------------------
+# remaining functions of the reference module: sequence fetch, 192-substitution counts over regions (si_*),
+# and the persisted element / site-set intermediates (initialize_nonc_data, preprocess_nonc, preprocess_sites)
+# --------------------------------------------------------------------------------------------
+
+def fetch_sequence(fasta, CHROM, START, END, n_up=2, n_down=2):
+    """A sequence expanded by the context size on either end (reference :21-29): (seq, START-n_up, END+n_down), with
+    START == 0 silently becoming n_up.  ``fasta`` is a FASTA path or a genome.Genome (host strings; the kernels work
+    on the packed genome and never call this)."""
+    g = fasta if isinstance(fasta, Genome) else Genome.from_fasta(str(fasta))
+    if START == 0:
+        START = n_up
+    if START - n_up < 0:
+        raise ValueError("start out of range (%d)" % (START - n_up))
+    return g.fetch(CHROM, START - n_up, END + n_down).upper(), START - n_up, END + n_down
+
+
+def _parse_region_str(r):
+    left, end = r.rsplit('-', 1)
+    chrom, start = left.rsplit(':', 1)
+    return chrom, int(start), int(end)
+
+
+def si_by_regions(fasta, trans_idx, regions, strand=1, n_up=1, n_down=1, normed=True):
+    """192-substitution context counts summed over a list of 'chr1:100-200' regions (reference :398-431): every
+    counted k-mer adds one to each of its three substitutions; minus strand counts the reverse complement.  Returns a
+    one-column DataFrame indexed by ``trans_idx`` (the reference's row order is that of a Python set)."""
+    g = get_device_genome(fasta)
+    keys = list(trans_idx)
+    if len(regions) == 0:
+        return pd.DataFrame(np.zeros(len(keys), dtype=np.int64), index=keys)
+    parsed = [_parse_region_str(r) for r in regions]
+    minus = strand == -1 or strand == '-'
+    st = np.full(len(parsed), -1 if minus else 1, dtype=np.int8)
+    counts, cols = _count_regions(g, g.chrom_indices([p[0] for p in parsed], prefix=""), [p[1] for p in parsed],
+                                  [p[2] for p in parsed], n_up, n_down, strand=st)
+    tot = counts.sum(axis=0)
+    col_of = {c: i for i, c in enumerate(cols)}
+    return pd.DataFrame(np.array([tot[col_of[k.split('>')[0]]] for k in keys], dtype=np.int64), index=keys)
+
+
+def si_count_pretrain(gene_lst, f_genic_str, f_fasta, window):
+    """192-substitution counts of the windows each gene overlaps (reference :375-396), one row per gene."""
+    from . import genic_driver_tools
+    from .. import storage
+    st = storage.Store(f_genic_str, "r")
+    trans_idx = sorted(np.asarray(st.read_array('substitution_idx')).astype(str))
+    rows = {}
+    for gene in gene_lst:
+        chrom = st.read_array('chr/{}'.format(gene))[0]
+        chrom = chrom.decode("utf-8") if isinstance(chrom, bytes) else str(chrom)
+        strd = st.read_array('strands/{}'.format(gene))[0]
+        intervals = st.read_array('cds_intervals/{}'.format(gene))
+        regions = [genic_driver_tools.trip_to_str(r) for r in genic_driver_tools.get_ideal_overlaps(chrom, intervals, window)]
+        rows[gene] = si_by_regions(f_fasta, trans_idx, regions, strand=strd)[0].values
+    return pd.DataFrame.from_dict(rows, orient='index', columns=trans_idx)
+
+
+def si_count_parallel(f_genic_str, f_fasta, window, n_procs):
+    """Reference :434-449; the process pool is replaced by one pass over all genes."""
+    from .. import storage
+    return si_count_pretrain(storage.Store(f_genic_str, "r").keys('cds_intervals'), f_genic_str, f_fasta, window)
+
+
+def initialize_nonc_data(f_nonc_data_str, f_genome_counts, window, n_up=1, n_down=1):
+    """Copy the substitution index and the per-window trinucleotide counts into the element data store
+    (reference :451-478)."""
+    from .. import storage
+    window_key = 'window_{}'.format(window)
+    dst = storage.Store(f_nonc_data_str, "a")
+    if not dst.has('substitution_idx'):
+        dst.write_array('substitution_idx', np.array(mk_trans_idx(n_up=n_up, n_down=n_down, collapse=False)))
+    if not (dst.has(window_key + '/full_window_si_index') and dst.has(window_key + '/full_window_si_values')):
+        src = storage.Store(f_genome_counts, "r")
+        idx = src.read_array('idx')
+        genome_df = src.read_table('all_window_genome_counts')
+        assert int(str(genome_df.index[0]).split('-')[-1]) == window      # correct genome count window size
+        dst.write_array(window_key + '/full_window_si_values', genome_df.values, dtype=np.int64)
+        dst.write_array(window_key + '/full_window_si_index', idx)
+
+
+def _strand_is_minus(s):
+    return s == '-1' or s == '-' or s == -1
+
+
+def _stored_window_map(store, window_key):
+    """Window index / counts of the element data store as K6 inputs (chromosome number -> dense window map)."""
+    idx = np.asarray(store.read_array(window_key + '/full_window_si_index')).astype(np.int64)
+    vals = np.asarray(store.read_array(window_key + '/full_window_si_values'))
+    window = int(window_key.split('_')[1])
+    n_chrom = int(idx[:, 0].max()) + 1 if len(idx) else 1
+    off, wmap = kernels.build_window_map(idx[:, 0], idx[:, 1], window, n_chrom)
+    return off, wmap, vals.astype(np.int32)
+
+
+def _region_counts_192(store, window_key, window, chrom, strand_minus, blk_ptr, blk_start, blk_end):
+    """np.repeat(sum of window rows, 3) with the minus-strand re-ordering of reference :625-634, from the kernel's
+    64-context sums (all three substitutions of a context share its count, so the x3 expansion commutes)."""
+    off, wmap, vals = _stored_window_map(store, window_key)
+    rc, _ = kernels.element_region_counts(np.asarray(chrom, dtype=np.int32),
+                                          np.where(strand_minus, -1, 1).astype(np.int8), blk_ptr, blk_start, blk_end,
+                                          window, off, wmap, vals, default_device())
+    return np.repeat(rc.cpu().numpy(), 3, axis=1)
+
+
+def preprocess_nonc(f_nonc_bed, f_nonc_data, f_pretrained, L_contexts, save_key, window):
+    """Per element: L_counts (sum of its blocks' 192-substitution counts), region_counts (window counts over its
+    overlapped windows, strand-aware) and the overlap list, stored under window_{W}/<save_key>/<ELT>
+    (reference :596-644).  f_pretrained is only read for its substitution order in the reference; the order here is
+    always the sorted one (mk_trans_idx)."""
+    from . import genic_driver_tools
+    from ..data_tools import mutation_tools
+    from .. import storage
+    window_key = 'window_{}'.format(window)
+    store = storage.Store(f_nonc_data, "a")
+    df_elts = mutation_tools.bed12_boundaries(f_nonc_bed)
+    E = len(df_elts)
+    ptr = np.zeros(E + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(b) for b in df_elts.BLOCK_STARTS])
+    bs = np.array([x for b in df_elts.BLOCK_STARTS for x in b], dtype=np.int64)
+    be = np.array([x for b in df_elts.BLOCK_ENDS for x in b], dtype=np.int64)
+    owner = np.repeat(np.arange(E), np.diff(ptr))
+    chrom = df_elts.CHROM.values.astype(np.int64)
+    keys = ['chr{}:{}-{}'.format(c, s, e) for c, s, e in zip(chrom[owner], bs, be)]
+    L = np.zeros((E, 192), dtype=np.float64)
+    np.add.at(L, owner, L_contexts.loc[keys].values)
+    minus = np.array([_strand_is_minus(s) for s in df_elts.STRAND.values], dtype=bool)
+    R = _region_counts_192(store, window_key, window, chrom, minus, ptr, bs, be)
+    overlaps = [genic_driver_tools.get_ideal_overlaps(c, np.vstack((s, e)), window)
+                for c, s, e in zip(df_elts.CHROM, df_elts.BLOCK_STARTS, df_elts.BLOCK_ENDS)]
+    store.write_element_groups('{}/{}'.format(window_key, save_key), df_elts.ELT.values, L, R, overlaps)
+
+
+def preprocess_sites(f_sites, f_nonc_data, f_pretrained, save_key, window):
+    """Per site set (the SAMPLE column of the sites file): L_counts[j] = number of its sites with substitution j
+    (strand-flipped for minus-strand sets, 'nan' contexts skipped), region_counts and overlaps as preprocess_nonc
+    (reference :647-711)."""
+    from . import genic_driver_tools
+    from ..data_tools import mutation_tools
+    from .. import storage
+    window_key = 'window_{}'.format(window)
+    store = storage.Store(f_nonc_data, "a")
+    subst_idx = mk_trans_idx(1, 1)
+    pos = {s: i for i, s in enumerate(subst_idx)}
+    df_sites = mutation_tools.read_mutation_file(f_sites)
+    df_sites = df_sites.drop(columns=['GENE', 'ANNOT', 'REF', 'ALT']).rename(columns={'SAMPLE': 'GENE'})
+    df_sites['CONTEXT'] = df_sites.CONTEXT.where(df_sites.CONTEXT.notna(), 'nan').astype(str)
+    if 'STRAND' not in df_sites.columns:
+        df_sites['STRAND'] = '.'
+    names, first = np.unique(df_sites.GENE.values.astype(str), return_index=True)      # groupby('GENE'): sorted keys
+    gid = {n: i for i, n in enumerate(names)}
+    owner = np.array([gid[str(g)] for g in df_sites.GENE.values], dtype=np.int64)
+    E = len(names)
+    g_chrom = df_sites.CHROM.values[first].astype(np.int64)                             # list(group['CHROM'])[0]
+    g_minus = np.array([_strand_is_minus(s) for s in df_sites.STRAND.values[first]], dtype=bool)
+    # substitution index of every site, flipped for minus-strand sets; sites whose name contains 'nan' are skipped
+    sub = np.full(len(df_sites), -1, dtype=np.int32)
+    for i, (mt, cx, o) in enumerate(zip(df_sites.MUT_TYPE.values, df_sites.CONTEXT.values, owner)):
+        name = cx + '>' + cx[0] + str(mt)[2] + cx[2] if len(cx) == 3 and len(str(mt)) == 3 else 'nan'
+        if g_minus[o] and 'nan' not in name:
+            a, b = name.split('>')
+            name = reverse_complement(a) + '>' + reverse_complement(b)
+        if 'nan' not in name:
+            sub[i] = pos[name]                        # KeyError for an unknown substitution, like the reference's dict
+    order = np.argsort(owner, kind="stable")
+    keep = order[sub[order] >= 0]
+    L = kernels.site_counts(owner[keep].astype(np.int32), sub[keep], E, 192, default_device()).cpu().numpy()
+    ptr = np.zeros(E + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum(np.bincount(owner, minlength=E))
+    bs, be = df_sites.START.values[order].astype(np.int64), df_sites.END.values[order].astype(np.int64)
+    R = _region_counts_192(store, window_key, window, g_chrom, g_minus, ptr, bs, be)
+    overlaps = [genic_driver_tools.get_ideal_overlaps(int(g_chrom[e]), np.vstack((bs[ptr[e]:ptr[e + 1]], be[ptr[e]:ptr[e + 1]])),
+                                                      window) for e in range(E)]
+    store.write_element_groups('{}/{}'.format(window_key, save_key), names, L.astype(np.float64), R, overlaps)

@@ -86,7 +86,8 @@ class Store:
             with h5py.File(self.path, "r") as h5:
                 return key in h5
         return os.path.exists(_key_path(self.path, key, ".table.npz")) or \
-            os.path.exists(_key_path(self.path, key, ".npy"))
+            os.path.exists(_key_path(self.path, key, ".npy")) or \
+            os.path.exists(_key_path(self.path, key + '/__elements__', ".npz"))
 
     # ---- plain arrays
     def write_array(self, key, arr, dtype=None):
@@ -124,6 +125,55 @@ class Store:
                 base = base[len(pre) + 2:]
             out.add(base.split("__")[0])
         return sorted(out)
+
+    # ---- per-element groups (window_{W}/<key>/<elt>/{L_counts, region_counts} + attr 'overlaps' in the reference)
+    def write_element_groups(self, prefix, names, L_counts, region_counts, overlaps):
+        """HDF5: one group per element exactly as preprocess_nonc / preprocess_sites write them
+        (sequence_tools.py:639-641, :704-706).  Directory store: one .npz per prefix (a file per element would mean
+        hundreds of thousands of files), overlaps as CSR rows of (chrom, start, end)."""
+        names = [str(n) for n in names]
+        if self.hdf5:
+            import h5py
+            with h5py.File(self.path, "a") as h5:
+                for n, L, R, ov in zip(names, L_counts, region_counts, overlaps):
+                    g = '{}/{}'.format(prefix, n)
+                    if g in h5:
+                        del h5[g]
+                    h5.create_dataset(g + '/L_counts', data=L)
+                    h5.create_dataset(g + '/region_counts', data=R)
+                    h5[g].attrs.create('overlaps', np.asarray(ov))
+            return
+        ptr = np.zeros(len(names) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum([len(o) for o in overlaps])
+        flat = np.array([tuple(int(v) for v in w) for o in overlaps for w in o], dtype=np.int64).reshape(-1, 3)
+        np.savez(_key_path(self.path, prefix + '/__elements__', ".npz"), names=np.array(names, dtype=str),
+                 L_counts=np.asarray(L_counts, dtype=np.float64), region_counts=np.asarray(region_counts, dtype=np.int64),
+                 overlaps_ptr=ptr, overlaps=flat)
+
+    def read_element_groups(self, prefix, names=None):
+        """(names, L_counts [E,192], region_counts [E,192], overlaps list) written by write_element_groups; ``names``
+        restricts and orders the rows (KeyError for an unknown element, like h5py)."""
+        if self.hdf5:
+            import h5py
+            with h5py.File(self.path, "r") as h5:
+                grp = h5[prefix]
+                names = [str(n) for n in (names if names is not None else grp.keys())]
+                L = np.array([grp[n]['L_counts'][:] for n in names], dtype=np.float64).reshape(len(names), -1)
+                R = np.array([grp[n]['region_counts'][:] for n in names]).reshape(len(names), -1)
+                ov = [[tuple(int(v) for v in w) for w in grp[n].attrs['overlaps']] for n in names]
+            return names, L, R, ov
+        z = np.load(_key_path(self.path, prefix + '/__elements__', ".npz"), allow_pickle=False)
+        all_names = [str(n) for n in z["names"]]
+        if names is None:
+            rows = np.arange(len(all_names))
+            names = all_names
+        else:
+            pos = {n: i for i, n in enumerate(all_names)}
+            names = [str(n) for n in names]
+            rows = np.array([pos[n] for n in names], dtype=np.int64)
+        ptr, flat = z["overlaps_ptr"], z["overlaps"]
+        ov = [[tuple(int(v) for v in w) for w in flat[ptr[r]:ptr[r + 1]]] for r in rows]
+        return names, z["L_counts"][rows], z["region_counts"][rows], ov
 
     # ---- attributes
     def _attr_file(self):

@@ -374,6 +374,27 @@ int dig_overlap_fill(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, con
                      int64_t *pair_mut_d, int64_t *pair_blk_d, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * dig_element_region_counts: the `region_counts` array that preprocess_nonc (sequence_tools.py:596-644) and
+ * preprocess_sites (:647-711) persist per element -- the sum of the 64 trinucleotide window counts over the element's
+ * overlapped windows (get_ideal_overlaps, genic_driver_tools.py:275-283), new[ctx] = old[revcomp(ctx)] for
+ * minus-strand elements (:633-634).  The reference stores np.repeat(., 3) of it.  Arguments as dig_element_transfer;
+ * region_counts_d is int64 [n_elt, 64], n_win_out_d int32 [n_elt]; status as dig_element_transfer.
+ */
+int dig_element_region_counts(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
+                              const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt, int64_t window,
+                              const int64_t *win_map_off_d, const int32_t *win_map_d, const int32_t *win_counts_d,
+                              int64_t n_win, int max_span_windows, int64_t *region_counts_d, int32_t *n_win_out_d,
+                              int32_t *status_d, void *stream);
+
+/* dig_element_psum: P_SUM of nonc_model (genic_driver_tools.py:361-369) from the persisted per-element arrays:
+ * p[e] = sum_j (d_pr[j] / sum_i d_pr[i] R[e,i]) L[e,j]; L_d float64 [n_elt, 192], region_counts_d int64 [n_elt, 192]
+ * (already strand-ordered), denom_out_d (may be NULL) = sum_i d_pr[i] R[e,i].  Bit-identical to the P of
+ * dig_element_transfer for the same counts.
+ */
+int dig_element_psum(const double *L_d, const int64_t *region_counts_d, const double *d_pr_d, int64_t n_elt,
+                     double *p_out_d, double *denom_out_d, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Synthetic genome generator (BASELINE.json configs are synthetic): position g is a pure
  * function of (seed, g); identical to orc_synth_genome in oracle/dig_oracle.c.
  */

@@ -96,6 +96,7 @@ def preprocess_nonc_contexts(args):
     if args.f_sites:
         print("preprocessing sites data")
         st.write_table('{}/{}/sites'.format(wkey, args.save_key), mutation_tools.read_mutation_file(args.f_sites))
+        sequence_tools.preprocess_sites(args.f_sites, args.f_element_data, args.f_pretrained, args.save_key, args.window)
         return
     print("Preprocessing elements")
     L = sequence_tools.precount_region_contexts_parallel(args.f_element_bed, args.f_fasta, args.N_procs, args.window,
@@ -105,6 +106,9 @@ def preprocess_nonc_contexts(args):
     df_elts['BLOCK_ENDS'] = [','.join(map(str, b)) for b in df_elts.BLOCK_ENDS]
     st.write_table('{}/{}/elements'.format(wkey, args.save_key), df_elts.reset_index(drop=True))
     st.write_table('{}/{}/L_contexts'.format(wkey, args.save_key), L)
+    # the reference's persisted per-element intermediates (L_counts, region_counts, overlaps), read by nonc_model
+    sequence_tools.preprocess_nonc(args.f_element_bed, args.f_element_data, args.f_pretrained, L, args.save_key,
+                                   args.window)
 
 
 def preprocess_tiled(args):

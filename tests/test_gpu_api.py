@@ -485,3 +485,140 @@ def test_tiled_model_cli(workdir, oracle):
     # the window really is the one containing the tile's start
     r = wc[[win_index[(c, s // W10 * W10)] for c, s in zip(chrom, start)]].sum(axis=1)
     assert np.array_equal(got.R_SIZE.values, r)
+
+
+def _ref_region_counts_192(win_counts, overlaps, win_index, minus):
+    """The reference's own expressions for region_counts (sequence_tools.py:625-634), restated: np.repeat of every
+    overlapped window's 64 counts summed, re-ordered through the reverse-complement substitution names for '-'."""
+    from digdriver_b200.sequence_model import sequence_tools as st
+    subst_idx = st.mk_trans_idx(1, 1)
+    revc = {s: st.reverse_complement(s.split('>')[0]) + '>' + st.reverse_complement(s.split('>')[-1]) for s in subst_idx}
+    rc = np.array([np.repeat(win_counts[win_index[(int(c), int(s))]], 3) for c, s, e in overlaps]).sum(axis=0)
+    if minus:
+        rc = np.array([r[1] for r in sorted(enumerate(rc), key=lambda k: revc[subst_idx[k[0]]])])
+    return rc
+
+
+def test_persisted_intermediates_and_chunk_workers(workdir, oracle, tmp_path):
+    """preprocess_nonc / preprocess_sites persist L_counts, region_counts and overlaps per element; nonc_model,
+    genic_model and tiled_nonc_model (the reference's pool workers) read them back for a chunk of names."""
+    from digdriver_b200 import storage
+    from digdriver_b200.data_tools import mutation_tools
+    from digdriver_b200.sequence_model import genic_driver_tools as gd, sequence_tools as st
+    d = workdir["dir"]
+    p = lambda x: str(d / x)
+    if not storage.Store(p("pretrained"), "r").has("K1"):
+        test_cli_flow_matches_oracle(workdir, oracle)
+    pre = storage.Store(p("pretrained"), "r")
+    em = pre.read_table("K1")
+    genes, wins = workdir["genes"], workdir["wins"]
+    # ---- preprocess_nonc with the reference's signature, into the same element data store
+    L_contexts = st.precount_region_contexts_parallel(p("elements.bed"), p("genome.fa"), 1, W)
+    st.preprocess_nonc(p("elements.bed"), p("eltdata"), p("pretrained"), L_contexts, "K2", W)
+    data = storage.Store(p("eltdata"), "r")
+    names, L, R, overlaps = data.read_element_groups("window_%d/K2" % W)
+    assert names == [g[0] for g in genes]
+    win_counts = data.read_array("window_%d/full_window_si_values" % W)
+    win_index = {(int(c), int(s)): i for i, (c, s, e) in enumerate(data.read_array("window_%d/full_window_si_index" % W))}
+    for i, g in enumerate(genes):
+        ov = gd.get_ideal_overlaps(g[1], np.vstack((g[3], g[4])), W)
+        assert overlaps[i] == [(int(c), int(s), int(e)) for c, s, e in ov]
+        assert np.array_equal(R[i], _ref_region_counts_192(win_counts, ov, win_index, g[2] == "-")), g[0]
+        want_L = sum(L_contexts.loc["chr%d:%d-%d" % (g[1], s, e)].values for s, e in zip(g[3], g[4]))
+        assert np.array_equal(L[i], want_L)
+    # ---- nonc_model on a chunk (reversed order) == the rows of the all-in-one element model, bit for bit
+    chunk = [g[0] for g in genes][::-1][:17]
+    got = gd.nonc_model(chunk, p("pretrained"), p("eltdata"), "K2", False)
+    want = em.set_index("ELT").loc[chunk]
+    assert list(got.ELT) == chunk and list(got.columns) == list(em.columns)
+    for col in got.columns[1:]:
+        assert np.array_equal(got[col].values, want[col].values, equal_nan=True), col
+    with pytest.raises(KeyError):
+        gd.nonc_model(["no_such_element"], p("pretrained"), p("eltdata"), "K2", False)
+    # ---- indels_direct: a second region-parameter table for the indel columns
+    rp2 = workdir["rp"].copy()
+    rp2["Y_PRED"] = rp2.Y_PRED * 0.25
+    rp2["Y_TRUE"] = rp2.Y_TRUE + 3
+    pre_dir = tmp_path / "pre2"
+    st2 = storage.Store(str(pre_dir), "w")
+    st2.write_table("region_params", workdir["rp"])
+    st2.write_table("region_params_indels", rp2)
+    st2.write_table("sequence_model_192", pre.read_table("sequence_model_192"))
+    gi = gd.nonc_model(chunk, str(pre_dir), p("eltdata"), "K2", True)
+    np.testing.assert_allclose(gi.MU_INDEL.values, 0.25 * gi.MU.values, rtol=1e-12)
+    assert np.array_equal(gi.R_INDEL.values, gi.R_OBS.values + 3 * np.array([len(overlaps[names.index(n)]) for n in chunk]))
+    assert np.array_equal(gi.SIGMA_INDEL.values, gi.SIGMA.values)
+    # ---- preprocess_sites + nonc_model == sites_model_arrays
+    ann = pd.read_table(p("annot.tsv"), header=None)
+    ann = ann[ann[7] != "INDEL"].iloc[:600].copy()
+    rng = np.random.default_rng(8)
+    ann[5] = ["SET%02d" % s for s in rng.integers(0, 23, len(ann))]
+    set_chrom = {s: int(c) for s, c in zip(ann[5], ann[0])}                        # one chromosome / strand per set
+    ann = ann[[set_chrom[s] == int(c) for s, c in zip(ann[5], ann[0])]]
+    ann[10] = ["-" if int(s[3:]) % 3 == 0 else "+" for s in ann[5]]
+    ann.to_csv(p("sites.tsv"), sep="\t", header=False, index=False)
+    st.preprocess_sites(p("sites.tsv"), p("eltdata"), p("pretrained"), "S1", W)
+    set_names = sorted(set(ann[5]))
+    got_s = gd.nonc_model(set_names, p("pretrained"), p("eltdata"), "S1", False)
+    rm = gd.RegionModel(pre.read_table("region_params"))
+    d_pr = st.d_pr_from_model192(pre.read_table("sequence_model_192"))
+    key = {tuple(r): i for i, r in enumerate(map(tuple, data.read_array("window_%d/full_window_si_index" % W)))}
+    rows = np.array([key[(int(c), int(s), int(e))] for c, s, e in zip(rm.df.CHROM, rm.df.START, rm.df.END)])
+    want_s = gd.sites_model_arrays(mutation_tools.read_mutation_file(p("sites.tsv")), rm,
+                                   win_counts[rows].astype(np.int32), d_pr)
+    assert list(got_s.ELT) == list(want_s.ELT)
+    for col in got_s.columns[1:]:
+        assert np.array_equal(got_s[col].values, want_s[col].values, equal_nan=True), col
+    # ---- genic_model on a chunk == rows of genic_model_parallel
+    gm = pre.read_table("genic_model")
+    gchunk = [g[0] for g in genes][5:25:3]
+    gg = gd.genic_model(gchunk, p("pretrained"), p("genic"), "window_10kb/counts", False)
+    wantg = gm.set_index("GENE").loc[gchunk]
+    assert list(gg.GENE) == gchunk
+    for col in ("MU", "SIGMA", "R_OBS", "R_SIZE", "GENE_LENGTH", "P_MIS", "P_NONS", "P_SILENT", "P_SPLICE", "P_INDEL"):
+        assert np.array_equal(gg[col].values, wantg[col].values), col
+    # ---- nonc_model_region on bed12 rows == the element model (root-level window keys, as the reference reads them)
+    rdir = tmp_path / "regiondata"
+    rs = storage.Store(str(rdir), "w")
+    rs.write_array("full_window_si_index", data.read_array("window_%d/full_window_si_index" % W))
+    rs.write_array("full_window_si_values", win_counts)
+    rs.write_table("Lkey", L_contexts)
+    res, df_L, df_pi = gd.nonc_model_region(mutation_tools.bed12_boundaries(p("elements.bed")), p("pretrained"), str(rdir),
+                                            "Lkey", return_intermediates=True)
+    for col in ("R_OBS", "MU", "SIGMA", "P_SUM"):
+        assert np.array_equal(res[col].values, em[col].values), col
+    assert np.array_equal(df_L.values, L)
+    np.testing.assert_allclose((df_pi.values * df_L.values).sum(axis=1), em.P_SUM.values, rtol=1e-12)
+    par = gd.nonc_model_region_parallel(p("elements.bed"), p("pretrained"), str(rdir), "Lkey", 2)
+    assert np.array_equal(par.P_SUM.values, em.P_SUM.values)
+
+
+def test_si_by_regions_and_fetch_sequence(workdir, oracle):
+    from digdriver_b200.genome import Genome
+    from digdriver_b200.sequence_model import sequence_tools as st
+    d = workdir["dir"]
+    fa = str(d / "genome.fa")
+    trans_idx = st.mk_trans_idx(1, 1)
+    regions = ["chr1:0-1000", "chr1:3000-4000", "chr2:44000-45500"]
+    off2 = 60_032
+    seq = np.full(off2 + 45_500, ord("N"), dtype=np.uint8)
+    seq[:60_000] = workdir["seqs"]["chr1"]
+    seq[off2:] = workdir["seqs"]["chr2"]
+    off, ln = np.array([0, off2]), np.array([60_000, 45_500])
+    names = oracle.context_names(1, 1)
+    for strand in (1, -1, '-'):
+        got = st.si_by_regions(fa, trans_idx, regions, strand=strand)
+        sc = np.full(3, -1 if strand in (-1, '-') else 1, dtype=np.int8)
+        c64, _ = oracle.count_regions(seq, off, ln, np.array([0, 0, 1]), np.array([0, 3000, 44000]),
+                                      np.array([1000, 4000, 45500]), 1, 1, strand=sc)
+        tot = c64.sum(axis=0)
+        assert list(got.index) == trans_idx
+        assert np.array_equal(got[0].values, [tot[names.index(t.split('>')[0])] for t in trans_idx])
+    assert st.si_by_regions(fa, trans_idx, []).values.sum() == 0
+    g = Genome.from_fasta(fa)
+    s, a, b = st.fetch_sequence(g, "chr1", 0, 10, n_up=2, n_down=2)
+    assert (a, b) == (0, 12) and s == g.fetch("chr1", 0, 12).upper()
+    s, a, b = st.fetch_sequence(fa, "chr2", 100, 110, n_up=1, n_down=1)
+    assert (a, b) == (99, 111) and s == g.fetch("chr2", 99, 111).upper() and len(s) == 12
+    with pytest.raises(ValueError):
+        st.fetch_sequence(g, "chr1", 1, 10, n_up=2, n_down=2)

@@ -150,3 +150,33 @@ def test_window_tiling_rule_and_tile_names():
     assert idx.tolist() == [[1, 0, 10_000], [1, 10_000, 20_000], [3, 0, 10_000]]      # the last partial window is dropped
     assert objectives.tile_windows({7: 100}, 30, overlap=10).tolist() == [[7, 0, 30], [7, 20, 50], [7, 40, 70], [7, 60, 90]]
     assert _index_transform("chr12:100-250") == "region_12_100_250"
+
+
+def test_store_element_groups_round_trip(tmp_path):
+    from digdriver_b200 import storage
+    st = storage.Store(str(tmp_path / "s"), "w")
+    names = ["e1", "e2", "e3"]
+    L = np.arange(3 * 192, dtype=np.float64).reshape(3, 192)
+    R = (np.arange(3 * 192, dtype=np.int64) * 7).reshape(3, 192)
+    ov = [[(1, 0, 1000), (1, 1000, 2000)], [], [(2, 5000, 6000)]]
+    st.write_element_groups("window_1000/K", names, L, R, ov)
+    assert st.has("window_1000/K")
+    n2, L2, R2, ov2 = storage.Store(str(tmp_path / "s"), "r").read_element_groups("window_1000/K")
+    assert n2 == names and np.array_equal(L2, L) and np.array_equal(R2, R) and ov2 == ov
+    n3, L3, R3, ov3 = st.read_element_groups("window_1000/K", ["e3", "e1"])
+    assert n3 == ["e3", "e1"] and np.array_equal(L3, L[[2, 0]]) and ov3 == [ov[2], ov[0]]
+    with pytest.raises(KeyError):
+        st.read_element_groups("window_1000/K", ["nope"])
+
+
+def test_fetch_sequence_and_host_helpers():
+    from digdriver_b200.genome import Genome
+    from digdriver_b200.sequence_model import sequence_tools as st
+    from digdriver_b200.driver_model import transfer_tools as tt
+    g = Genome.from_dict({"chr1": "acgtNNacgtACGT"})
+    assert st.fetch_sequence(g, "chr1", 0, 4, n_up=2, n_down=2) == ("ACGTNN", 0, 6)        # START 0 -> n_up
+    assert st.fetch_sequence(g, "chr1", 3, 5, n_up=1, n_down=1) == ("GTNN", 2, 6)
+    assert st._parse_region_str("chr12:100-250") == ("chr12", 100, 250)
+    assert tt._mle_t(3, 1, 0.5, 2.0) == max(0.5 * 2.0, (3 + 0.5 - 1) / (1 + 0.5))
+    assert tt._mle_t(0, 1, 2.0, 0.1) == (0 + 2.0 - 1) / (1 + 10.0)
+    assert tt._mrfold_factor(0.0, 5.0) == 1e-10 and tt._mrfold_factor(2.0, 4.0) == 0.5
