@@ -386,13 +386,24 @@ def si_count_pretrain(gene_lst, f_genic_str, f_fasta, window):
     from . import genic_driver_tools
     from .. import storage
     st = storage.Store(f_genic_str, "r")
-    trans_idx = sorted(np.asarray(st.read_array('substitution_idx')).astype(str))
+    trans_idx = (sorted(np.asarray(st.read_array('substitution_idx')).astype(str)) if st.has('substitution_idx')
+                 else mk_trans_idx(1, 1))
+    flat = None
+    if st.has('genes') and st.has('cds_ptr'):        # this package's flattened f_genic (genic_model_parallel)
+        meta = st.read_table('genes')
+        flat = ({str(g): i for i, g in enumerate(meta.GENE.values)}, meta, st.read_array('cds_ptr'),
+                st.read_array('cds_start'), st.read_array('cds_end'))
     rows = {}
     for gene in gene_lst:
-        chrom = st.read_array('chr/{}'.format(gene))[0]
-        chrom = chrom.decode("utf-8") if isinstance(chrom, bytes) else str(chrom)
-        strd = st.read_array('strands/{}'.format(gene))[0]
-        intervals = st.read_array('cds_intervals/{}'.format(gene))
+        if flat is not None:
+            i = flat[0][str(gene)]
+            chrom, strd = str(flat[1].CHROM.values[i]), flat[1].STRAND.values[i]
+            intervals = np.vstack((flat[3][flat[2][i]:flat[2][i + 1]], flat[4][flat[2][i]:flat[2][i + 1]]))
+        else:
+            chrom = st.read_array('chr/{}'.format(gene))[0]
+            chrom = chrom.decode("utf-8") if isinstance(chrom, bytes) else str(chrom)
+            strd = st.read_array('strands/{}'.format(gene))[0]
+            intervals = st.read_array('cds_intervals/{}'.format(gene))
         regions = [genic_driver_tools.trip_to_str(r) for r in genic_driver_tools.get_ideal_overlaps(chrom, intervals, window)]
         rows[gene] = si_by_regions(f_fasta, trans_idx, regions, strand=strd)[0].values
     return pd.DataFrame.from_dict(rows, orient='index', columns=trans_idx)
@@ -401,7 +412,9 @@ def si_count_pretrain(gene_lst, f_genic_str, f_fasta, window):
 def si_count_parallel(f_genic_str, f_fasta, window, n_procs):
     """Reference :434-449; the process pool is replaced by one pass over all genes."""
     from .. import storage
-    return si_count_pretrain(storage.Store(f_genic_str, "r").keys('cds_intervals'), f_genic_str, f_fasta, window)
+    st = storage.Store(f_genic_str, "r")
+    genes = list(st.read_table('genes').GENE.values) if st.has('genes') else st.keys('cds_intervals')
+    return si_count_pretrain(genes, f_genic_str, f_fasta, window)
 
 
 def initialize_nonc_data(f_nonc_data_str, f_genome_counts, window, n_up=1, n_down=1):

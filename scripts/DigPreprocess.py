@@ -118,6 +118,15 @@ def preprocess_tiled(args):
     storage.Store(args.f_nonc_data, "a").write_table("{}/L_counts".format(args.save_key), L)
 
 
+def preprocess_cds_contexts(args):
+    """Reference DigPreprocess.py:118-127: 192-substitution counts of the windows every gene overlaps."""
+    gs = storage.Store(args.f_genic, "r")
+    assert (gs.has('genes') and gs.has('cds_ptr')) or gs.has('substitution_idx'), \
+        "f_genic file does not contain necessary groups. Please check that the correct file is passed"
+    results = sequence_tools.si_count_parallel(args.f_genic, args.f_fasta, args.window, args.N_procs)
+    storage.Store(args.out_file, "a").write_table(args.out_key, results)
+
+
 def parse_args(text=None):
     parser = argparse.ArgumentParser(description='Preprocess genome and mutation files for use with Dig (B200).')
     sub = parser.add_subparsers()
@@ -140,6 +149,14 @@ def parse_args(text=None):
     b.add_argument('--down', type=int, default=1)
     b.add_argument('--n-procs', type=int, default=get_cpus())
     b.set_defaults(func=addMutationContext)
+    c1 = sub.add_parser('preprocess_genic_model', help='pre-count the contexts of the windows that overlap each gene')
+    c1.add_argument('f_genic')
+    c1.add_argument('f_fasta')
+    c1.add_argument('out_file')
+    c1.add_argument('--out-key', default='cds/window_10kb')
+    c1.add_argument('--n-procs', default=get_cpus(), type=int, dest='N_procs')
+    c1.add_argument('--window', type=int, default=10000)
+    c1.set_defaults(func=preprocess_cds_contexts)
     e = sub.add_parser('preprocess_element_model', help='precount element contexts')
     e.add_argument('f_element_data')
     e.add_argument('f_pretrained')

@@ -622,3 +622,42 @@ def test_si_by_regions_and_fetch_sequence(workdir, oracle):
     assert (a, b) == (99, 111) and s == g.fetch("chr2", 99, 111).upper() and len(s) == 12
     with pytest.raises(ValueError):
         st.fetch_sequence(g, "chr1", 1, 10, n_up=2, n_down=2)
+
+
+def test_count_mutations_and_genic_precount_cli(workdir, oracle, tmp_path, monkeypatch):
+    """DigPretrain.py countMutations (cohort-size attributes) and DigPreprocess.py preprocess_genic_model
+    (si_count_parallel: 192-substitution counts of the windows each gene overlaps)."""
+    from digdriver_b200 import storage
+    from digdriver_b200.sequence_model import genic_driver_tools as gd, sequence_tools as st
+    d = workdir["dir"]
+    p = lambda x: str(d / x)
+    if not os.path.exists(p("annot.tsv")):
+        test_cli_flow_matches_oracle(workdir, oracle)
+    genes = workdir["genes"]
+    (tmp_path / "genes_MSK_230.txt").write_text("\n".join(g[0] for g in genes[:12]) + "\n")
+    monkeypatch.setenv("DIG_DATA_DIR", str(tmp_path))
+    _cli("DigPretrain", "countMutations --outputFile %s --mutation-file %s" % (p("pretrained"), p("annot.tsv")))
+    attrs = storage.Store(p("pretrained"), "r").get_attrs()
+    ann = pd.read_table(p("annot.tsv"), header=None).drop_duplicates([0, 1, 2, 3, 4, 5])
+    snv, ind = ann[ann[7] != "INDEL"], ann[ann[7] == "INDEL"].drop_duplicates([0, 1, 2, 3, 4, 6])
+    dd = pd.concat([snv, ind])
+    cds = dd[dd[7] != "Noncoding"]
+    rp = workdir["rp"]
+    assert attrs["N_SAMPLES"] == dd[5].nunique() and attrs["N_MUT_CDS"] == len(cds) == attrs["N_MUT_SAMPLE_CDS"]
+    assert attrs["N_MUT_TOTAL"] == rp.Y_TRUE.sum() and attrs["N_MUT_TRAIN"] == rp.Y_TRUE[~rp.FLAG].sum()
+    sel = cds[cds[6].isin([g[0] for g in genes[:12]]) & ~cds[7].isin(["Synonymous", "Essential_Splice", "Noncoding"])]
+    assert attrs["N_MUT_MSK_230"] == len(sel) > 0
+    assert attrs["N_MUT_SAMPLE_MSK_230"] == len(sel.drop_duplicates([5, 6])) and attrs["N_SAMPLE_MSK_230"] == sel[5].nunique()
+    assert "N_MUT_MSK_341" not in attrs                                   # list not shipped -> skipped with a warning
+    # ---- preprocess_genic_model
+    _cli("DigPreprocess", "preprocess_genic_model %s %s %s --out-key cds/w --window %d" % (p("genic"), p("genome.fa"), p("si"), W))
+    si = storage.Store(p("si"), "r").read_table("cds/w")
+    assert list(si.index) == [g[0] for g in genes] and list(si.columns) == st.mk_trans_idx(1, 1)
+    cs = storage.Store(p("counts"), "r")
+    wc = cs.read_table("all_window_genome_counts")
+    for g in genes[:8]:
+        ov = gd.get_ideal_overlaps(str(g[1]), np.vstack((g[3], g[4] - 1)), W)
+        tot = wc.loc[[gd.trip_to_str(r) for r in ov]].values.sum(axis=0)
+        if g[2] == "-":
+            tot = tot[[list(wc.columns).index(st.reverse_complement(c)) for c in wc.columns]]
+        assert np.array_equal(si.loc[g[0]].values, np.repeat(tot, 3)), g[0]

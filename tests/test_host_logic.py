@@ -121,6 +121,10 @@ def test_cli_parsers_accept_the_reference_arguments():
         spec = importlib.util.spec_from_file_location("cli_" + name, os.path.join(root, "scripts", name + ".py"))
         mods[name] = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mods[name])
+    a = mods["DigPretrain"].parse_args("countMutations --outputFile m --mutation-file f.tsv")
+    assert a.fmut == "f.tsv" and a.func.__name__ == "count_training_mutations"
+    a = mods["DigPreprocess"].parse_args("preprocess_genic_model g.h5 g.fa out --window 1000")
+    assert a.out_key == "cds/window_10kb" and a.window == 1000 and a.func.__name__ == "preprocess_cds_contexts"
     a = mods["DigPreprocess"].parse_args("countGenomeContext g.fa out --bed w.bed --up 2 --down 2 --n-procs 4")
     assert a.up == 2 and a.bed == "w.bed" and a.func.__name__ == "countGenomeContext"
     a = mods["DigPretrain"].parse_args("elementModel pre.h5 data.h5 KEY --n-procs 3")
