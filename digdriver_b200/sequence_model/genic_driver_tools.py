@@ -307,10 +307,11 @@ def tiled_model_parallel(f_pretrained, f_nonc_data, save_key, N_procs=1):
 # the reference's per-chunk workers (what its multiprocessing.Pool ran on a slice of the element list)
 # --------------------------------------------------------------------------------------------
 
-def genic_model(genes_lst, f_pretrained_str, f_genic_str, counts_key, indels_direct):
-    """Reference :31-203: the genic pretrain rows of the genes in ``genes_lst`` (X / Y genes are dropped)."""
+def genic_model(genes_lst, f_pretrained_str, f_genic_str, counts_key, indels_direct, f_fasta=None):
+    """Reference :31-203: the genic pretrain rows of the genes in ``genes_lst`` (X / Y genes are dropped).  f_fasta
+    is only needed when f_pretrained holds no 'window_counts_64' (see genic_model_parallel)."""
     return genic_model_parallel(f_pretrained_str, f_genic_str, counts_key=counts_key, indels_direct=indels_direct,
-                                genes_lst=list(genes_lst))
+                                f_fasta=f_fasta, genes_lst=list(genes_lst))
 
 
 def tiled_nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key):

@@ -572,7 +572,7 @@ def test_persisted_intermediates_and_chunk_workers(workdir, oracle, tmp_path):
     # ---- genic_model on a chunk == rows of genic_model_parallel
     gm = pre.read_table("genic_model")
     gchunk = [g[0] for g in genes][5:25:3]
-    gg = gd.genic_model(gchunk, p("pretrained"), p("genic"), "window_10kb/counts", False)
+    gg = gd.genic_model(gchunk, p("pretrained"), p("genic"), "window_10kb/counts", False, f_fasta=p("genome.fa"))
     wantg = gm.set_index("GENE").loc[gchunk]
     assert list(gg.GENE) == gchunk
     for col in ("MU", "SIGMA", "R_OBS", "R_SIZE", "GENE_LENGTH", "P_MIS", "P_NONS", "P_SILENT", "P_SPLICE", "P_INDEL"):
@@ -648,7 +648,6 @@ def test_count_mutations_and_genic_precount_cli(workdir, oracle, tmp_path, monke
     sel = cds[cds[6].isin([g[0] for g in genes[:12]]) & ~cds[7].isin(["Synonymous", "Essential_Splice", "Noncoding"])]
     assert attrs["N_MUT_MSK_230"] == len(sel) > 0
     assert attrs["N_MUT_SAMPLE_MSK_230"] == len(sel.drop_duplicates([5, 6])) and attrs["N_SAMPLE_MSK_230"] == sel[5].nunique()
-    assert "N_MUT_MSK_341" not in attrs                                   # list not shipped -> skipped with a warning
     # ---- preprocess_genic_model
     _cli("DigPreprocess", "preprocess_genic_model %s %s %s --out-key cds/w --window %d" % (p("genic"), p("genome.fa"), p("si"), W))
     si = storage.Store(p("si"), "r").read_table("cds/w")
