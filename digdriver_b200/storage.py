@@ -5,8 +5,10 @@ The reference hands data between its CLI stages through HDF5 files written with 
 mappability, window_{W}/..., pretrained tables; DigPreprocess.py:63-73, DigPretrain.py:82-96,156-177,
 207-208).  Neither h5py nor PyTables exists in this image, so the same key layout is served by a
 directory store (``<path>`` is a directory holding ``<key>.npy`` / ``<key>.table.npz`` files and
-``attrs.json``).  When h5py AND tables are importable and the path is an existing HDF5 file, the real
-file is read instead, so pretrained models produced by the reference can be dropped in.
+``attrs.json``).  An existing HDF5 file is read through h5py + PyTables when they are importable and otherwise
+through ``hdf5_lite`` (a pure-Python reader of the classic HDF5 structures and the pandas fixed format; read-only),
+so pretrained models produced by the reference can be dropped in.  ``export_hdf5`` writes a directory store out as
+an HDF5 file with the reference's key layout.
 """
 import json
 import os
@@ -41,10 +43,15 @@ class Store:
     def __init__(self, path, mode="a"):
         self.path = str(path)
         self.hdf5 = _is_hdf5_file(self.path)
+        self.lite = None
         if self.hdf5 and not _have_hdf5():
-            raise RuntimeError("%s is an HDF5 file but h5py/PyTables are not installed in this environment; "
-                               "convert it with the reference's environment or install them" % self.path)
-        if not self.hdf5:
+            if mode != "r":
+                raise RuntimeError("%s is an HDF5 file and h5py/PyTables are not installed: it can only be opened "
+                                   "read-only (mode 'r') through the built-in reader" % self.path)
+            from . import hdf5_lite
+            self.lite = hdf5_lite.File(self.path)
+            self.hdf5 = False
+        if not self.hdf5 and self.lite is None:
             if mode == "r" and not os.path.isdir(self.path):
                 raise FileNotFoundError(self.path)
             if mode == "w" and os.path.isdir(self.path):
@@ -53,7 +60,12 @@ class Store:
             os.makedirs(self.path, exist_ok=True)
 
     # ---- tables (pandas objects)
+    def _writable(self):
+        if self.lite is not None:
+            raise RuntimeError("%s was opened through the built-in read-only HDF5 reader" % self.path)
+
     def write_table(self, key, df):
+        self._writable()
         if self.hdf5:
             df.to_hdf(self.path, key=key, mode="a")
             return
@@ -69,6 +81,8 @@ class Store:
                  __index__=plain(df.index), __index_name__=np.array([str(df.index.name or "")]), **cols)
 
     def read_table(self, key):
+        if self.lite is not None:
+            return self.lite.read_pandas(key)
         if self.hdf5:
             return pd.read_hdf(self.path, key)
         z = np.load(_key_path(self.path, key, ".table.npz"), allow_pickle=False)
@@ -81,6 +95,8 @@ class Store:
         return df
 
     def has(self, key):
+        if self.lite is not None:
+            return key in self.lite
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "r") as h5:
@@ -91,6 +107,7 @@ class Store:
 
     # ---- plain arrays
     def write_array(self, key, arr, dtype=None):
+        self._writable()
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "a") as h5:
@@ -101,6 +118,8 @@ class Store:
         np.save(_key_path(self.path, key, ".npy"), np.asarray(arr, dtype=dtype))
 
     def read_array(self, key):
+        if self.lite is not None:
+            return self.lite.read(key)
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "r") as h5:
@@ -108,6 +127,8 @@ class Store:
         return np.load(_key_path(self.path, key, ".npy"), allow_pickle=False)
 
     def keys(self, prefix=""):
+        if self.lite is not None:
+            return self.lite.keys(prefix or "/")
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "r") as h5:
@@ -131,6 +152,7 @@ class Store:
         """HDF5: one group per element exactly as preprocess_nonc / preprocess_sites write them
         (sequence_tools.py:639-641, :704-706).  Directory store: one .npz per prefix (a file per element would mean
         hundreds of thousands of files), overlaps as CSR rows of (chrom, start, end)."""
+        self._writable()
         names = [str(n) for n in names]
         if self.hdf5:
             import h5py
@@ -153,6 +175,14 @@ class Store:
     def read_element_groups(self, prefix, names=None):
         """(names, L_counts [E,192], region_counts [E,192], overlaps list) written by write_element_groups; ``names``
         restricts and orders the rows (KeyError for an unknown element, like h5py)."""
+        if self.lite is not None:
+            f = self.lite
+            names = [str(n) for n in (names if names is not None else f.keys(prefix))]
+            L = np.array([f.read('{}/{}/L_counts'.format(prefix, n)) for n in names], dtype=np.float64).reshape(len(names), -1)
+            R = np.array([f.read('{}/{}/region_counts'.format(prefix, n)) for n in names]).reshape(len(names), -1)
+            ov = [[tuple(int(v) for v in w) for w in np.asarray(f.attrs('{}/{}'.format(prefix, n))['overlaps']).reshape(-1, 3)]
+                  for n in names]
+            return names, L, R, ov
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "r") as h5:
@@ -180,6 +210,9 @@ class Store:
         return os.path.join(self.path, "attrs.json")
 
     def get_attrs(self):
+        if self.lite is not None:
+            return {k: (v.item() if hasattr(v, "item") and getattr(v, "ndim", 1) == 0 else v)
+                    for k, v in self.lite.attrs("/").items()}
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "r") as h5:
@@ -189,6 +222,7 @@ class Store:
         return {}
 
     def set_attrs(self, **kw):
+        self._writable()
         if self.hdf5:
             import h5py
             with h5py.File(self.path, "a") as h5:
@@ -203,3 +237,67 @@ class Store:
 def read_hdf(path, key):
     """Drop-in for the reference's ``pd.read_hdf(path, key)`` call sites."""
     return Store(path, "r").read_table(key)
+
+
+def _pandas_node(obj):
+    """The group pandas' fixed format writes for a DataFrame / Series (pandas/io/pytables.py, BlockManagerFixed /
+    SeriesFixed): axis*/block*_items index arrays with a 'kind' attribute, block*_values stored transposed.  String
+    (object) blocks are written as fixed-length byte arrays, not as PyTables' pickled VLArrays."""
+    def index_ds(values, name=None):
+        v = np.asarray(values)
+        kind = "string" if v.dtype.kind in "OUS" else ("integer" if v.dtype.kind in "iu" else "float")
+        return ('data', v, {"kind": kind, "name": "N." if name is None else str(name), "transposed": np.bool_(True)})
+    common = {"CLASS": "GROUP", "TITLE": "", "VERSION": "1.0", "encoding": "UTF-8", "errors": "strict",
+              "pandas_version": "0.15.2"}
+    if isinstance(obj, pd.Series):
+        return {"attrs": dict(common, pandas_type="series", name="N." if obj.name is None else str(obj.name)),
+                "children": {"index": index_ds(obj.index.values, obj.index.name),
+                             "values": ('data', np.asarray(obj.values), {"transposed": np.bool_(True)})}}
+    children = {"axis0": index_ds([str(c) for c in obj.columns], obj.columns.name),
+                "axis1": index_ds(obj.index.values, obj.index.name)}
+    blocks = {}
+    for c in obj.columns:
+        v = np.asarray(obj[c].values)
+        k = "str" if v.dtype.kind in "OUS" else str(v.dtype)
+        blocks.setdefault(k, []).append(c)
+    attrs = dict(common, pandas_type="frame", ndim=np.int64(2), nblocks=np.int64(len(blocks)),
+                 axis0_variety="regular", axis1_variety="regular")
+    for i, (k, cols) in enumerate(blocks.items()):
+        vals = np.stack([np.asarray(obj[c].values) if k != "str" else np.array([str(x) for x in obj[c].values])
+                         for c in cols], axis=1) if len(obj) else np.zeros((0, len(cols)))
+        children["block%d_items" % i] = index_ds([str(c) for c in cols])
+        children["block%d_values" % i] = ('data', vals, {"transposed": np.bool_(True)})
+        attrs["block%d_items_variety" % i] = "regular"
+    return {"attrs": attrs, "children": children}
+
+
+def export_hdf5(store_path, out_path):
+    """Write a directory store as ONE HDF5 file with the reference's key layout (datasets for arrays, pandas
+    fixed-format groups for tables, root attributes, per-element groups with L_counts / region_counts / overlaps).
+    The file is produced by hdf5_lite's classic-format writer; it has been read back with hdf5_lite only (libhdf5 is
+    not available in this image), see hdf5_lite's module docstring."""
+    from . import hdf5_lite
+    st = Store(store_path, "r")
+    root = {"attrs": st.get_attrs(), "children": {}}
+
+    def node_for(parts):
+        node = root
+        for part in parts:
+            node = node["children"].setdefault(part, {"attrs": {}, "children": {}})
+        return node
+    for f in sorted(os.listdir(st.path)):
+        if f.endswith(".table.npz"):
+            parts = f[:-len(".table.npz")].split("__")
+            node_for(parts[:-1])["children"][parts[-1]] = _pandas_node(st.read_table("/".join(parts)))
+        elif f.endswith(".npy"):
+            parts = f[:-4].split("__")
+            node_for(parts[:-1])["children"][parts[-1]] = ('data', st.read_array("/".join(parts)), {})
+        elif f.endswith("____elements__.npz"):
+            parts = [x for x in f[:-len("____elements__.npz")].split("__")]
+            names, L, R, ov = st.read_element_groups("/".join(parts))
+            grp = node_for(parts)
+            for n, l_, r_, o_ in zip(names, L, R, ov):
+                grp["children"][n] = {"attrs": {"overlaps": np.asarray(o_, dtype=np.int64).reshape(-1, 3)},
+                                      "children": {"L_counts": ('data', l_, {}), "region_counts": ('data', r_, {})}}
+    hdf5_lite.hdf5_write(out_path, root)
+    return out_path
