@@ -28,8 +28,18 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in rows]
-    marks = [i for i, (n, _) in enumerate(names) if "scan_fused53_kernel" in n or "scan_sym_kernel<2" in n or "scan_hex_kernel" in n]
-    step = names[marks[-1]:] if marks else names
+    is_scan = lambda n: "scan_fused53_kernel" in n or "scan_sym_kernel<2" in n or "scan_hex_kernel" in n   # noqa: E731
+    big = max([v for n, v in names if is_scan(n)] or [0.0])
+    # a step = one whole-genome scan (the per-chromosome scans of the e2e leg are much shorter) and what follows it,
+    # up to the next scan or pack launch; the last COMPLETE one is reported (-c may cut the run anywhere)
+    marks = [i for i, (n, v) in enumerate(names) if is_scan(n) and v >= 0.5 * big]
+    step = names
+    for m in reversed(marks):
+        end = next((j for j in range(m + 1, len(names)) if is_scan(names[j][0]) or "pack_kernel" in names[j][0]), None)
+        if end is not None or m == marks[-1]:
+            step = names[m:end]
+            if end is not None:
+                break
     tot = sum(v for _, v in step)
     agg = collections.OrderedDict()
     for n, v in step:
