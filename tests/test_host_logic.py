@@ -184,3 +184,25 @@ def test_fetch_sequence_and_host_helpers():
     assert tt._mle_t(3, 1, 0.5, 2.0) == max(0.5 * 2.0, (3 + 0.5 - 1) / (1 + 0.5))
     assert tt._mle_t(0, 1, 2.0, 0.1) == (0 + 2.0 - 1) / (1 + 10.0)
     assert tt._mrfold_factor(0.0, 5.0) == 1e-10 and tt._mrfold_factor(2.0, 4.0) == 0.5
+
+
+def test_filter_hypermut_script(tmp_path):
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("cli_filter_hypermut", os.path.join(root, "scripts", "filter_hypermut.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = []
+    for i in range(30):                                            # sample H: 30 coding rows, sample L: 3
+        rows.append((1, 100 + i, 101 + i, "A", "C", "H", "G%d" % i, "Missense", "A>C", "AAA"))
+    for i in range(3):
+        rows.append((2, 500 + i, 501 + i, "C", "T", "L", "G1", "Synonymous", "C>T", "ACA"))
+    for i in range(50):                                            # non-coding rows never count
+        rows.append((3, 900 + i, 901 + i, "G", "T", "L", ".", "Noncoding", "G>T", "AGA"))
+    pd.DataFrame(rows).to_csv(tmp_path / "cohort.annot.txt", sep="\t", header=False, index=False)
+    out = tmp_path / "out"
+    mod.main("--input-dir %s --output-dir %s" % (tmp_path, out))               # reference behaviour: limit 3000
+    assert len(pd.read_table(out / "cohort.no_hypermut.annot.txt", header=None)) == 83
+    mod.main("--input-dir %s --output-dir %s --max-muts-per-sample 10 --honour-threshold" % (tmp_path, out))
+    kept = pd.read_table(out / "cohort.no_hypermut.annot.txt", header=None)
+    assert set(kept[5]) == {"L"} and len(kept) == 53
