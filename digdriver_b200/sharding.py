@@ -93,3 +93,40 @@ class Collectives:
         if self.rank != 0:
             return None
         return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def partition_elements(elt_chrom, elt_first_start, win_chrom, win_start, win_end, parts):
+    """Owner rank of every element: the rank whose window slice holds the window that contains the element's FIRST
+    block start (multi-exon elements may straddle a shard boundary, so they are assigned by
+    their first block and resolved against the all-gathered window-count table).  `parts` = partition_windows(...)
+    over windows sorted by (chromosome, start); chromosome labels are compared as given.  Elements whose first block
+    lies in no window get rank -1 (the single-process path raises KeyError for them, K6 status 2)."""
+    wc = np.asarray(win_chrom).astype(np.int64)
+    ws = np.asarray(win_start, dtype=np.int64)
+    we = np.asarray(win_end, dtype=np.int64)
+    key = (wc << 40) | ws                                     # windows are sorted by (chromosome, start)
+    ek = (np.asarray(elt_chrom).astype(np.int64) << 40) | np.asarray(elt_first_start, dtype=np.int64)
+    w = np.searchsorted(key, ek, side="right") - 1
+    ok = (w >= 0)
+    wi = np.clip(w, 0, max(len(ws) - 1, 0))
+    if len(ws):
+        ok &= (wc[wi] == np.asarray(elt_chrom).astype(np.int64)) & (np.asarray(elt_first_start) < we[wi])
+    else:
+        ok &= False
+    bounds = np.array([hi for _, hi in parts], dtype=np.int64)
+    owner = np.searchsorted(bounds, wi, side="right").astype(np.int64)
+    owner[~ok] = -1
+    return owner
+
+
+def all_gather_rows(coll, t, sizes):
+    """Every rank's row block concatenated on EVERY rank (the all-gather of the [Nw_local, 64] window-count table:
+    79 MB for hg19 at 10 kb, so any rank can resolve any element).  `sizes` = rows per rank."""
+    if not coll.on or coll.world == 1:
+        return t
+    m = max(sizes)
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(coll.world)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
