@@ -125,8 +125,13 @@ def all_gather_rows(coll, t, sizes):
     if not coll.on or coll.world == 1:
         return t
     m = max(sizes)
-    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    pad[: t.shape[0]] = t
-    bufs = [torch.empty_like(pad) for _ in range(coll.world)]
-    dist.all_gather(bufs, pad)
-    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    if t.shape[0] != m:                                   # ragged last slice: pad to the common block size
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        t = pad
+    out = torch.empty((coll.world * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())      # one collective straight into the final buffer
+    if all(s_ == m for s_ in sizes):
+        return out
+    keep = torch.cat([torch.arange(r * m, r * m + s_, device=t.device) for r, s_ in enumerate(sizes)])
+    return out.index_select(0, keep)

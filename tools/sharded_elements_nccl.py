@@ -19,24 +19,39 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def element_rows(dg, wins_t, table, elts, sel, rp, d_pr, W, wmap):
-    """K4 + K6 + K7 for the elements `sel`: float64 [len(sel), 6] = id, MU, SIGMA, P_SUM, R_SIZE, PVAL."""
+class ElementShard:
+    """Device-resident CSR of the elements one rank owns (built once, outside the timed job)."""
+
+    def __init__(self, elts, sel, dev, W):
+        from digdriver_b200 import kernels
+        e_chrom, e_strand, ptr, bs, be, obs = elts
+        nb = np.diff(ptr)[sel]
+        sp = np.concatenate([[0], np.cumsum(nb)])
+        take = (np.repeat(ptr[:-1][sel] - sp[:-1], nb) + np.arange(sp[-1])) if len(sel) else np.zeros(0, dtype=np.int64)
+        owner = np.repeat(np.arange(len(sel)), nb)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)     # noqa: E731
+        self.chrom, self.strand = t(e_chrom[sel], torch.int32), t(e_strand[sel], torch.int8)
+        self.ptr, self.bs, self.be = t(sp, torch.int64), t(bs[take], torch.int64), t(be[take], torch.int64)
+        self.blk_chrom, self.blk_strand = t(e_chrom[sel][owner], torch.int32), t(e_strand[sel][owner], torch.int8)
+        self.obs, self.ids = t(obs[sel], torch.float64), t(sel, torch.float64)
+        self.max_span = kernels.element_max_span(sp, bs[take], be[take], W)
+
+
+def element_rows(dg, table, sh, rp, d_pr, W, wmap, sink=None):
+    """K4 + K6 + K7 for one shard's elements: float64 [n, 6] = id, MU, SIGMA, P_SUM, R_SIZE, PVAL."""
     from digdriver_b200 import kernels
-    e_chrom, e_strand, ptr, bs, be, obs = elts
     dev = dg.device
-    nb = np.diff(ptr)[sel]
-    sp = np.concatenate([[0], np.cumsum(nb)])
-    take = np.concatenate([np.arange(ptr[i], ptr[i + 1]) for i in sel]) if len(sel) else np.zeros(0, dtype=np.int64)
-    owner = np.repeat(np.arange(len(sel)), nb)
-    blk, _ = kernels.count_contexts(dg, e_chrom[sel][owner], bs[take], be[take], 1, 1, strand=e_strand[sel][owner])
-    pre = kernels.element_transfer(e_chrom[sel].astype(np.int32), e_strand[sel], sp, bs[take], be[take], W, wmap[0], wmap[1],
-                                   table, rp["y_pred"], rp["std"], rp["y_true"], rp["flag"], d_pr, blk_counts=blk,
-                                   device=dev)
+    blk, _ = kernels.count_contexts(dg, sh.blk_chrom, sh.bs, sh.be, 1, 1, strand=sh.blk_strand)
+    pre = kernels.element_transfer(sh.chrom, sh.strand, sh.ptr, sh.bs, sh.be, W, wmap[0], wmap[1], table, rp["y_pred"],
+                                   rp["std"], rp["y_true"], rp["flag"], d_pr, blk_counts=blk, device=dev,
+                                   max_span=sh.max_span, status_sink=sink)
     mu, sigma, p = pre["MU"][0], pre["SIGMA"][0], pre["P"][0][:, 0]
     alpha, theta = mu ** 2 / sigma ** 2, sigma ** 2 / mu
-    _, pval = kernels.nb_burden_test(torch.from_numpy(obs[sel]).to(dev), alpha, theta, p, dev, want_exp=False)
-    ids = torch.from_numpy(sel.astype(np.float64)).to(dev)
-    return torch.stack([ids, mu, sigma, p, pre["R_SIZE"].to(torch.float64), pval], dim=1)
+    _, pval = kernels.nb_burden_test(sh.obs, alpha, theta, p, dev, want_exp=False)
+    return torch.stack([sh.ids, mu, sigma, p, pre["R_SIZE"].to(torch.float64), pval], dim=1)
+
+
+_ALL = []
 
 
 def main():
@@ -85,12 +100,23 @@ def main():
     owner = sharding.partition_elements(e_chrom, bs[ptr[:-1]], wins[:, 0], wins[:, 1], wins[:, 2], parts)
     assert np.all(owner >= 0)
     sel = np.flatnonzero(owner == rank)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)         # noqa: E731
+    rp = {k: t(v.astype(np.uint8) if v.dtype == bool else v, torch.uint8 if v.dtype == bool else torch.float64)
+          for k, v in rp.items()}
+    d_pr = t(d_pr, torch.float64)
+    wmap = (t(wmap[0], torch.int64), t(wmap[1], torch.int32))
+    w_dev = (t(wins[:, 0], torch.int32), t(wins[:, 1], torch.int64), t(wins[:, 2], torch.int64))
+    mine = ElementShard(elts, sel, dev, W)
+    sizes = [b - a for a, b in parts]
+
+    sink = []                                             # device status words, read once after the timed job
+    n_own = [int((owner == r).sum()) for r in range(world)]
 
     def sharded():
-        local_counts, _ = kernels.count_contexts(dg, wins[lo:hi, 0], wins[lo:hi, 1], wins[lo:hi, 2], 1, 1)
-        table = sharding.all_gather_rows(coll, local_counts, [b - a for a, b in parts])
-        rows = element_rows(dg, wins, table, elts, sel, rp, d_pr, W, wmap)
-        return table, coll.gather_rows(rows)
+        local_counts, _ = kernels.count_contexts(dg, w_dev[0][lo:hi], w_dev[1][lo:hi], w_dev[2][lo:hi], 1, 1)
+        table = sharding.all_gather_rows(coll, local_counts, sizes)
+        rows = element_rows(dg, table, mine, rp, d_pr, W, wmap, sink)
+        return table, coll.gather_rows(rows, sizes=n_own)
 
     for _ in range(2):
         sharded()
@@ -102,17 +128,32 @@ def main():
     table, got = sharded()
     e1.record()
     torch.cuda.synchronize()
+    kernels.check_deferred(sink)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     coll.all_reduce_max(ms)
     ok = None
     if rank == 0:
-        full, _ = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], 1, 1)
-        want = element_rows(dg, wins, full, elts, np.arange(E), rp, d_pr, W, wmap)
+        full, _ = kernels.count_contexts(dg, w_dev[0], w_dev[1], w_dev[2], 1, 1)
+        _ALL.append(ElementShard(elts, np.arange(E), dev, W))
+        want = element_rows(dg, full, _ALL[0], rp, d_pr, W, wmap)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        kernels.count_contexts(dg, w_dev[0], w_dev[1], w_dev[2], 1, 1)
+        element_rows(dg, full, _ALL[0], rp, d_pr, W, wmap)
+        s1.record()
+        torch.cuda.synchronize()
+        ms_single = s0.elapsed_time(s1)
         got = got[torch.argsort(got[:, 0])]
-        ok = bool(torch.equal(table, full) and torch.equal(got, want))
+        same = lambda a, b: bool(torch.equal(torch.isnan(a), torch.isnan(b)) and   # noqa: E731
+                                 torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)))
+        table_ok, rows_ok = bool(torch.equal(table, full)), same(got, want)
+        ok = table_ok and rows_ok
+        n_nan = int(torch.isnan(want).any(dim=1).sum().item())       # elements whose windows hold no countable base
         print(json.dumps({"workload": "config 4: %d elements (1-3 blocks of 200-2000 bp) on a %.0f Mb genome, %d kb windows, "
                                       "range-sharded x%d" % (E, args.bases / 1e6, W // 1000, world),
-                          "n_gpus": world, "bit_identical_to_single_gpu": ok, "ms_sharded_job": float(ms.item()),
+                          "n_gpus": world, "bit_identical_to_single_gpu": ok, "window_table_identical": table_ok,
+                          "element_rows_identical": rows_ok, "elements_with_nan_rows": n_nan, "ms_sharded_job": float(ms.item()), "ms_same_job_one_gpu": ms_single,
                           "elements_per_s": E / (float(ms.item()) / 1e3), "elements_per_rank": [int((owner == r).sum()) for r in range(world)]}))
     if world > 1:
         dist.barrier()
