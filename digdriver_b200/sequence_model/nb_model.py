@@ -149,7 +149,6 @@ def mutation_freq_joint(S_mut, S_gen, N):
 def train_sequence_model(train_idx, f_model, N, key_prefix=None):
     """Context model from the pre-tabulated `mutation_counts` / `genome_counts` tables of f_model restricted to the
     training windows (reference :79-107): (Series of Pr(b | context), {context: sum over b})."""
-    import pandas as pd
     from .. import storage
     rows = ['chr{}:{}-{}'.format(r[0], r[1], r[2]) for r in train_idx]
     key_mut = 'mutation_counts' if not key_prefix else key_prefix + "_mutation_counts"

@@ -206,3 +206,26 @@ def test_filter_hypermut_script(tmp_path):
     mod.main("--input-dir %s --output-dir %s --max-muts-per-sample 10 --honour-threshold" % (tmp_path, out))
     kept = pd.read_table(out / "cohort.no_hypermut.annot.txt", header=None)
     assert set(kept[5]) == {"L"} and len(kept) == 53
+
+
+def test_nb_model_sequence_helpers(tmp_path):
+    """nb_model.mutation_freq_conditional / _joint / tabix_to_dataframe (reference nb_model.py:13-77)."""
+    from digdriver_b200.sequence_model import nb_model
+    idx = pd.MultiIndex.from_tuples([("A>C", "AAA"), ("A>G", "AAA"), ("C>T", "ACG")])
+    S_mut = pd.Series([4, 6, 9], index=idx)
+    S_gen = pd.Series({"AAA": 100, "ACG": 30})
+    got = nb_model.mutation_freq_conditional(S_mut, S_gen, 2)
+    assert got.dtype == float and list(got.index) == list(idx)
+    assert got.tolist() == [4 / (2 * 100), 6 / (2 * 100), 9 / (2 * 30)]
+    assert nb_model.mutation_freq_joint(S_mut, S_gen, 2).equals(got)
+
+    class Tbx:
+        def fetch(self, chrom, start, end):
+            return ["1\t5\t6\tA\tC\tS1\tMissense", "1\t9\t10\tG\tT\tS2\tNoncoding"]
+    df = nb_model.tabix_to_dataframe(Tbx(), "1", 0, 100)
+    assert list(df.columns) == ['CHROM', 'START', 'END', 'REF', 'ALT', 'ID', 'ANNOT'] and df.START.tolist() == [5, 9]
+
+    class Empty:
+        def fetch(self, *a):
+            return []
+    assert list(nb_model.tabix_to_dataframe(Empty(), "1", 0, 1).columns) == ['CHROM', 'START', 'END', 'REF', 'ALT', 'ID']
