@@ -203,3 +203,51 @@ def test_variable_length_data_through_the_global_heap(tmp_path):
         assert f.attrs("block1_values") == {"title": "UTF-8 text é"}
         got = f._pandas_values("block1_values")
     assert got.dtype == object and got.tolist() == obj.tolist()
+
+
+def test_new_style_structures(tmp_path):
+    """Superblock v2, version-2 object headers ('OHDR', with a continuation chunk 'OCHK'), compact groups made of link
+    messages, version-3 attributes and a version-2 dataspace: what libhdf5 writes with libver='latest' as long as a
+    group stays compact.  Hand-assembled, read back."""
+    U = hdf5_lite.UNDEF
+    buf = bytearray(b"\x00" * 48)                                   # superblock v2: 8 + 4 + 4*8 + 4 = 48 bytes
+
+    def alloc(b):
+        buf.extend(b"\x00" * (-len(buf) % 8))
+        a = len(buf)
+        buf.extend(b)
+        return a
+
+    def msg(mtype, data):
+        return struct.pack("<BHB", mtype, len(data), 0) + data
+
+    def ohdr(messages, cont=None):
+        body = b"".join(messages)
+        if cont is not None:
+            body += msg(0x10, struct.pack("<QQ", cont[0], cont[1]))
+        return alloc(b"OHDR" + struct.pack("<BBH", 2, 0x01, len(body)) + body + b"\x00" * 4)
+
+    arr = np.arange(12, dtype=np.float64).reshape(3, 4) * 0.5
+    data = alloc(arr.tobytes())
+    ds2 = struct.pack("<BBBB", 2, 2, 0, 1) + struct.pack("<QQ", 3, 4)             # dataspace v2, simple, rank 2
+    layout = struct.pack("<BBQQ", 3, 1, data, arr.nbytes)
+    note = np.array(b"new style")
+    a_dt, a_ds = hdf5_lite._dt_message(note.dtype), struct.pack("<BBBB", 2, 0, 0, 0)  # scalar dataspace v2
+    attr3 = struct.pack("<BBHHHB", 3, 0, 5, len(a_dt), len(a_ds), 0) + b"note\x00" + a_dt + a_ds + note.tobytes()
+    # the attribute lives in a continuation chunk of the dataset's header
+    och_body = msg(0x0C, attr3)
+    och = alloc(b"OCHK" + och_body + b"\x00" * 4)
+    dset = ohdr([msg(0x01, ds2), msg(0x03, hdf5_lite._dt_message(arr.dtype)), msg(0x08, layout)],
+                cont=(och, 4 + len(och_body) + 4))
+    link = lambda name, addr: msg(0x06, struct.pack("<BBB", 1, 0, len(name)) + name.encode() + struct.pack("<Q", addr))  # noqa: E731
+    linfo = msg(0x02, struct.pack("<BBQQ", 0, 0, U, U))                          # link info: no dense storage
+    sub = ohdr([linfo, link("values", dset)])
+    root = ohdr([linfo, link("grp", sub), link("also_values", dset)])
+    sb = hdf5_lite.SIGNATURE + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", 0, U, len(buf), root) + b"\x00" * 4
+    buf[0:48] = sb
+    path = str(tmp_path / "n.h5")
+    open(path, "wb").write(bytes(buf))
+    with hdf5_lite.File(path) as f:
+        assert f.keys("/") == ["also_values", "grp"] and f.keys("grp") == ["values"] and f.is_group("grp")
+        assert np.array_equal(f["grp/values"], arr) and np.array_equal(f["also_values"], arr)
+        assert f.attrs("grp/values") == {"note": "new style"}
