@@ -327,3 +327,20 @@ def test_region_counts_and_psum_match_k6_at_scale():
     a, b = rc.cpu().numpy(), rc_plus.cpu().numpy()
     minus = es < 0
     assert np.array_equal(a[~minus], b[~minus]) and np.array_equal(a[minus], b[minus][:, comp])
+
+
+def test_new_entry_points_accept_empty_inputs():
+    from digdriver_b200 import kernels
+    z = np.zeros(0)
+    zi = np.zeros(0, dtype=np.int64)
+    assert kernels.loglik("pois", z, z).numel() == 0 and kernels.loglik("gamma", z, z, z).numel() == 0
+    assert kernels.gene_llr_test("nb", z, z, np.zeros((0, 3)), np.zeros((0, 3)), z).shape == (4, 0)
+    assert kernels.gene_llr_test("gamma_poisson", z, z, np.zeros((0, 3)), np.zeros((0, 3)), z, z).shape == (4, 0)
+    assert kernels.element_psum(np.zeros((0, 192)), np.zeros((0, 192), dtype=np.int64), np.ones(192)).numel() == 0
+    off, wmap = kernels.build_window_map(np.array([0]), np.array([0]), 1000, 1)
+    rc, nw = kernels.element_region_counts(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int8), np.zeros(1, dtype=np.int64),
+                                           zi, zi, 1000, off, wmap, np.zeros((1, 64), dtype=np.int32))
+    assert rc.shape == (0, 64) and nw.numel() == 0
+    assert kernels.overlap_counts(zi, zi, zi, zi).size == 0
+    with pytest.raises(Exception):
+        kernels.gene_llr_test("gamma_poisson", np.ones(2), np.ones(2), np.ones((2, 3)), np.ones((2, 3)), np.ones(2))   # no T_SYN
