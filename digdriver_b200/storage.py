@@ -77,8 +77,11 @@ class Store:
                 v = np.array([str(e) for e in v], dtype=str) if len(v) else np.zeros(0, dtype="U1")
             return v
         cols = {"col%d" % i: plain(df[c]) for i, c in enumerate(df.columns)}
+        # tuple column labels (the (MUT_TYPE, CONTEXT) columns of the reference's mutation-count tables) survive as JSON
+        tuples = json.dumps([list(map(str, c)) for c in df.columns]) if any(isinstance(c, tuple) for c in df.columns) else ""
         np.savez(_key_path(self.path, key, ".table.npz"), __columns__=np.array([str(c) for c in df.columns]),
-                 __index__=plain(df.index), __index_name__=np.array([str(df.index.name or "")]), **cols)
+                 __index__=plain(df.index), __index_name__=np.array([str(df.index.name or "")]),
+                 __column_tuples__=np.array([tuples]), **cols)
 
     def read_table(self, key):
         if self.lite is not None:
@@ -90,6 +93,9 @@ class Store:
         df = pd.DataFrame({c: z["col%d" % i] for i, c in enumerate(cols)}, index=z["__index__"])
         name = str(z["__index_name__"][0])
         df.index.name = name or None
+        tuples = str(z["__column_tuples__"][0]) if "__column_tuples__" in z.files else ""
+        if tuples:
+            df.columns = pd.MultiIndex.from_tuples([tuple(c) for c in json.loads(tuples)])
         if cols == ["__series__"]:
             return df["__series__"].rename(None)
         return df

@@ -229,3 +229,26 @@ def test_nb_model_sequence_helpers(tmp_path):
         def fetch(self, *a):
             return []
     assert list(nb_model.tabix_to_dataframe(Empty(), "1", 0, 1).columns) == ['CHROM', 'START', 'END', 'REF', 'ALT', 'ID']
+
+
+def test_nb_model_train_sequence_model_from_store(tmp_path):
+    """nb_model.train_sequence_model / expected_mutations_by_context (reference nb_model.py:79-124) on a store that
+    holds per-window mutation counts with (mutation, context) tuple columns."""
+    from digdriver_b200 import storage
+    from digdriver_b200.sequence_model import nb_model
+    rows = ["chr1:0-1000", "chr1:1000-2000", "chr2:0-1000"]
+    cols = pd.MultiIndex.from_tuples([("A>C", "AAA"), ("A>G", "AAA"), ("C>T", "ACG")])
+    df_mut = pd.DataFrame([[1, 2, 3], [4, 0, 1], [7, 7, 7]], index=rows, columns=cols)
+    df_gen = pd.DataFrame({"AAA": [100, 50, 10], "ACG": [30, 20, 5]}, index=rows)
+    st = storage.Store(str(tmp_path / "m"), "w")
+    st.write_table("mutation_counts", df_mut)
+    st.write_table("genome_counts", df_gen)
+    back = storage.Store(str(tmp_path / "m"), "r").read_table("mutation_counts")
+    assert list(back.columns) == list(cols) and np.array_equal(back.values, df_mut.values)
+    train = [(1, 0, 1000), (1, 1000, 2000)]
+    Pr, d = nb_model.train_sequence_model(train, str(tmp_path / "m"), N=2)
+    assert Pr.tolist() == [5 / (2 * 150), 2 / (2 * 150), 4 / (2 * 50)]
+    assert d == {"AAA": 5 / 300 + 2 / 300, "ACG": 4 / 100}
+    exp_train, exp_test = nb_model.expected_mutations_by_context(train, [(2, 0, 1000)], str(tmp_path / "m"), N=2)
+    np.testing.assert_allclose(exp_train.values, [100 * d["AAA"] + 30 * d["ACG"], 50 * d["AAA"] + 20 * d["ACG"]], rtol=1e-15)
+    np.testing.assert_allclose(exp_test.values, [10 * d["AAA"] + 5 * d["ACG"]], rtol=1e-15)
