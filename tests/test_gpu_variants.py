@@ -235,6 +235,13 @@ def test_bedtools_front_ends(tmp_path):
     assert len(eff) == len(snv) + len(ind)
     assert set(zip(eff.CHROM.astype(str), eff.START, eff.SAMPLE)) == \
         set(zip(snv[0], snv[1], snv[5])) | set(zip(ind[0], ind[1], ind[5]))
+    f_bed3 = str(tmp_path / "blocks.bed")                                  # the same blocks as a plain 3-column bed
+    blk[["CHROM", "START", "END"]].to_csv(f_bed3, sep="\t", header=False, index=False)
+    eff3 = mt.restrict_mutations_by_bed_efficient(f_mut, f_bed3, bed12=False, drop_duplicates=True)
+    assert len(eff3) == len(eff) and set(zip(eff3.CHROM.astype(str), eff3.START, eff3.SAMPLE)) == \
+        set(zip(eff.CHROM.astype(str), eff.START, eff.SAMPLE))
+    nodrop = mt.restrict_mutations_by_bed_efficient(f_mut, f_bed, bed12=True, drop_duplicates=False, drop_sex=False)
+    assert len(nodrop[nodrop.ANNOT != "INDEL"]) == sum(1 for i, _ in pairs if mut[7][i] != "INDEL")   # one copy per pair
     # restrict_mutations_by_bed: clipped coordinates, pybedtools column names, duplicates dropped
     df_bed = blk[["CHROM", "START", "END"]]
     cl = mt.restrict_mutations_by_bed(mut, df_bed, unique=False)
