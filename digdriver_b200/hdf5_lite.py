@@ -592,6 +592,10 @@ class File:
         if ptype != "frame":
             raise Hdf5Error("%s: %r is not a fixed-format pandas object (pandas_type=%r; table format is not "
                             "supported)" % (self.path, path, ptype))
+        for ax in ("axis0", "axis1"):
+            if a.get(ax + "_variety", "regular") != "regular":
+                raise Hdf5Error("%s: %r has a MultiIndex on %s, which the built-in reader does not support" %
+                                (self.path, path, ax))
         cols, cname = self._pandas_index(path + "/axis0")
         idx, iname = self._pandas_index(path + "/axis1")
         data = {}
