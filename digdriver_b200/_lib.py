@@ -24,8 +24,9 @@ SIGNATURES = {
     "dig_packed_words": (_I64, [_I64]),
     "dig_nmask_words": (_I64, [_I64]),
     "dig_pack_genome": (_I, [_P, _I64, _P, _P, _P, _P]),
-    "dig_count_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P]),
-    "dig_count_contexts_fused53": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "dig_scan_workspace_bytes": (_I64, [_I64]),
+    "dig_count_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P, _P]),
+    "dig_count_contexts_fused53": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "dig_synth_genome": (_I, [_P, _I64, _I64, _U64, _I, _P]),
     "dig_mutation_contexts": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P]),
     "dig_substitution_counts": (_I, [_P, _P, _I64, _I, _I, _P, _P]),
@@ -34,7 +35,7 @@ SIGNATURES = {
                                    _I64, _I64, _I64, _P, _P, _I, _P]),
     "dig_site_counts": (_I, [_P, _P, _I64, _I64, _I, _P, _P]),
     "dig_tabulate_genes": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P]),
-    "dig_element_transfer": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P,
+    "dig_element_transfer": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P,
                                   _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dig_nb_pvalue_greater_midp": (_I, [_P, _P, _P, _I64, _P, _P]),
     "dig_nb_burden_test": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P]),
@@ -45,7 +46,7 @@ SIGNATURES = {
     "dig_gene_dnds_sel": (_I, [_P, _P, _P, _P, _I64, _P, _P]),
     "dig_selection_coefficient": (_I, [_P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "dig_window_denominators": (_I, [_P, _P, _I64, _P, _P, _P]),
-    "dig_site_test": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
+    "dig_site_test": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "dig_region_prob_norm": (_I, [_P, _P, _I64, _I, _P, _P]),
     "dig_position_obs": (_I, [_P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _P, _I64, _P, _P]),
     "dig_position_test": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P,
@@ -54,11 +55,21 @@ SIGNATURES = {
     "dig_nb_pvalue_variant": (_I, [_I, _P, _P, _P, _P, _I64, _P, _P]),
     "dig_loglik": (_I, [_I, _P, _P, _P, _I64, _P, _P]),
     "dig_gene_llr_test": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
-    "dig_element_region_counts": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I, _P, _P, _P, _P]),
+    "dig_element_region_counts": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P, _I64, _I, _P, _P, _P, _P]),
     "dig_element_psum": (_I, [_P, _P, _P, _I64, _P, _P, _P]),
     "dig_overlap_count": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "dig_overlap_fill": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
 }
+
+
+
+class ScanOpts(ctypes.Structure):
+    """dig_scan_opts of include/dig_b200.h."""
+    _fields_ = [("workspace_d", _c.c_void_p), ("workspace_bytes", _c.c_int64), ("variant", _c.c_int32),
+                ("totals_limit_kb", _c.c_uint32)]
+
+
+SCAN_AUTO, SCAN_PER_BASE, SCAN_HEX_PLAIN, SCAN_HEX = 0, 1, 2, 3
 
 _lib = None
 

@@ -28,8 +28,25 @@ using namespace digscan;
 
 namespace {
 
-unsigned int g_tot_limit_kb = 1u << 20;   // kilobases a CTA may fold into int32 totals before it goes global
-int g_scan_variant = 0;   // 0 = hexamer-pair kernel for (2,2) plus-strand scans, 1 = per-base kernels only, 2 = hexamer, plain flush
+// per-call options (dig_scan_opts, dig_b200.h); a null pointer means all defaults
+struct ScanOpts {
+    void *workspace = nullptr;
+    size_t workspace_bytes = 0;
+    int variant = DIG_SCAN_AUTO;
+    unsigned int tot_limit_kb = 1u << 20;   // kilobases a CTA may fold into 32-bit partial totals before it goes global
+};
+
+ScanOpts scan_opts(const dig_scan_opts *o)
+{
+    ScanOpts r;
+    if (o != nullptr) {
+        r.workspace = o->workspace_d;
+        r.workspace_bytes = o->workspace_bytes > 0 ? (size_t)o->workspace_bytes : 0;
+        r.variant = o->variant;
+        if (o->totals_limit_kb != 0u) r.tot_limit_kb = o->totals_limit_kb;
+    }
+    return r;
+}
 
 // ---------------------------------------------------------------------------------------
 // fast kernel: symmetric context (U == D).  PRIVATE selects the lane-private layout.
@@ -474,7 +491,7 @@ template <int U, bool PRIVATE>
 int launch_sym(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start,
                const int64_t *reg_end, const int8_t *reg_strand, int64_t n_reg, int32_t *counts,
-               unsigned long long *totals, cudaStream_t stream)
+               unsigned long long *totals, unsigned int tot_limit_kb, cudaStream_t stream)
 {
     constexpr int K = 1 << (2 * (2 * U + 1));
     constexpr size_t HIST_BYTES = (size_t)K << (PRIVATE ? 7 : 2);
@@ -493,7 +510,7 @@ int launch_sym(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const in
     kern<<<(unsigned)blocks, THREADS, smem, stream>>>(reinterpret_cast<const uint2 *>(p2), p2, nm,
                                                       (n_bases + 31) >> 5, chrom_off, chrom_len, reg_chrom,
                                                       reg_start, reg_end, reg_strand, n_reg, counts, totals,
-                                                      g_tot_limit_kb);
+                                                      tot_limit_kb);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
@@ -505,8 +522,9 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
                                          const int32_t *reg_chrom_d, const int64_t *reg_start_d,
                                          const int64_t *reg_end_d, int64_t n_reg, int32_t *counts5_d,
                                          int32_t *counts3_d, unsigned long long *totals5_d,
-                                         unsigned long long *totals3_d, void *stream)
+                                         unsigned long long *totals3_d, const dig_scan_opts *opts, void *stream)
 {
+    const ScanOpts so = scan_opts(opts);
     DIG_CHECK_ARG(n_reg >= 0 && n_bases >= 0, "negative size");
     if (n_reg == 0) return DIG_OK;
     DIG_CHECK_ARG(packed2_d && nmask_d && chrom_off_d && chrom_len_d && reg_chrom_d && reg_start_d && reg_end_d &&
@@ -515,10 +533,16 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
     DIG_CHECK_ARG((totals5_d == nullptr) == (totals3_d == nullptr), "pass both totals or neither");
     DIG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed2_d) & 7u) == 0 && (reinterpret_cast<uintptr_t>(counts5_d) & 15u) == 0,
                   "packed2_d must be 8-byte and counts5_d 16-byte aligned");
-    if (g_scan_variant != 1)
+    DIG_CHECK_ARG(so.variant >= DIG_SCAN_AUTO && so.variant <= DIG_SCAN_HEX, "unknown scan variant");
+    if (so.variant == DIG_SCAN_AUTO &&
+        scan_lb_usable(packed2_d, nmask_d, n_bases, counts5_d, so.workspace, so.workspace_bytes, n_reg))
+        return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
+                              n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb, so.workspace,
+                              (cudaStream_t)stream);
+    if (so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
-                               n_reg, counts5_d, counts3_d, totals5_d, totals3_d, g_tot_limit_kb, g_scan_variant == 2,
-                               (cudaStream_t)stream);
+                               n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb,
+                               so.variant == DIG_SCAN_HEX_PLAIN, nullptr, nullptr, (cudaStream_t)stream);
     const size_t smem = 1024 * 4 + 4096 + (size_t)WARPS_PER_BLOCK * 4096;
     static thread_local int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -530,22 +554,21 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
     if (blocks > need) blocks = need;
     scan_fused53_kernel<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint2 *>(packed2_d), packed2_d, nmask_d, (n_bases + 31) >> 5, chrom_off_d, chrom_len_d,
-        reg_chrom_d, reg_start_d, reg_end_d, n_reg, counts5_d, counts3_d, totals5_d, totals3_d, g_tot_limit_kb);
+        reg_chrom_d, reg_start_d, reg_end_d, n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
 
-// test hook (not part of the public header): lowers the int32-totals guard so tests can reach it
-extern "C" void dig_debug_set_totals_limit_kb(unsigned int kb) { g_tot_limit_kb = kb; }
-// test / A-B hook: 1 forces the per-base kernels (scan_sym_kernel, scan_fused53_kernel) for (2,2) scans
-extern "C" void dig_debug_set_scan_variant(int v) { g_scan_variant = v; }
+extern "C" int64_t dig_scan_workspace_bytes(int64_t n_reg) { return (int64_t)scan_lb_workspace_bytes(n_reg); }
 
 extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
                                   const int64_t *chrom_off_d, const int64_t *chrom_len_d,
                                   const int32_t *reg_chrom_d, const int64_t *reg_start_d,
                                   const int64_t *reg_end_d, const int8_t *reg_strand_d, int64_t n_reg, int n_up,
-                                  int n_down, int32_t *counts_d, unsigned long long *totals_d, void *stream)
+                                  int n_down, int32_t *counts_d, unsigned long long *totals_d,
+                                  const dig_scan_opts *opts, void *stream)
 {
+    const ScanOpts so = scan_opts(opts);
     DIG_CHECK_ARG(n_reg >= 0 && n_bases >= 0, "negative size");
     DIG_CHECK_ARG(n_up >= 0 && n_down >= 0 && n_up + n_down <= 5, "need 0 <= n_up, n_down and n_up + n_down <= 5");
     if (n_reg == 0) return DIG_OK;
@@ -554,21 +577,27 @@ extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nma
                   "null pointer");
     DIG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed2_d) & 7u) == 0 && (reinterpret_cast<uintptr_t>(counts_d) & 15u) == 0,
                   "packed2_d must be 8-byte and counts_d 16-byte aligned");
+    DIG_CHECK_ARG(so.variant >= DIG_SCAN_AUTO && so.variant <= DIG_SCAN_HEX, "unknown scan variant");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && g_scan_variant != 1)
+    if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && so.variant == DIG_SCAN_AUTO &&
+        scan_lb_usable(packed2_d, nmask_d, n_bases, counts_d, so.workspace, so.workspace_bytes, n_reg))
+        return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
+                              n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb, so.workspace, st);
+    if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
-                               n_reg, counts_d, nullptr, totals_d, nullptr, g_tot_limit_kb, g_scan_variant == 2, st);
+                               n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb,
+                               so.variant == DIG_SCAN_HEX_PLAIN, nullptr, nullptr, st);
     if (n_up == n_down && n_up <= 2) {
         switch (n_up) {
         case 0:
             return launch_sym<0, true>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d,
-                                       reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
+                                       reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, so.tot_limit_kb, st);
         case 1:
             return launch_sym<1, true>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d,
-                                       reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
+                                       reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, so.tot_limit_kb, st);
         default:
             return launch_sym<2, false>(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d,
-                                        reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, st);
+                                        reg_start_d, reg_end_d, reg_strand_d, n_reg, counts_d, totals_d, so.tot_limit_kb, st);
         }
     }
     const int K = 1 << (2 * (n_up + n_down + 1));

@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(HEX_WARPS * 32, MIN_CTAS) scan_hex_kernel(
     const int32_t *__restrict__ reg_chrom, const int64_t *__restrict__ reg_start,
     const int64_t *__restrict__ reg_end, int64_t n_reg, int32_t *__restrict__ counts5,
     int32_t *__restrict__ counts3, unsigned long long *__restrict__ totals5,
-    unsigned long long *__restrict__ totals3, unsigned int tot_limit_kb, uint32_t one)
+    unsigned long long *__restrict__ totals3, unsigned int tot_limit_kb, uint32_t one,
+    const int32_t *__restrict__ rlist, const int32_t *__restrict__ rlist_n)
 {
     constexpr int HEX_THREADS = HEX_WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -255,18 +256,22 @@ __global__ void __launch_bounds__(HEX_WARPS * 32, MIN_CTAS) scan_hex_kernel(
 
     const int64_t gwarp = (int64_t)blockIdx.x * HEX_WARPS + warp;
     const int64_t nwarps = (int64_t)gridDim.x * HEX_WARPS;
+    // rlist != null: only the regions listed (the lane-bank kernel's redo list, scan_lb.cu); n_items is read on the device
+    const int64_t n_items = rlist != nullptr ? (int64_t)__ldg(rlist_n) : n_reg;
+    auto region_of = [&](int64_t idx) -> int64_t { return rlist != nullptr ? (int64_t)__ldg(rlist + idx) : idx; };
 
     HexRegion g;
     g.nw = 0;
-    if (gwarp < n_reg)
-        g = hex_setup<TRI>(hex_load_raw(reg_chrom, reg_start, reg_end, gwarp), p2v, p2, nmask, n_words32, chrom_off,
-                           chrom_len, lane);
-    for (int64_t r = gwarp; r < n_reg; r += nwarps) {
+    if (gwarp < n_items)
+        g = hex_setup<TRI>(hex_load_raw(reg_chrom, reg_start, reg_end, region_of(gwarp)), p2v, p2, nmask, n_words32,
+                           chrom_off, chrom_len, lane);
+    for (int64_t idx = gwarp; idx < n_items; idx += nwarps) {
+        const int64_t r = region_of(idx);
         // the next region's descriptor is requested now and its first words just before this region's flush, so
         // neither latency is exposed
-        const bool more = r + nwarps < n_reg;
+        const bool more = idx + nwarps < n_items;
         HexRaw raw_n;
-        if (more) raw_n = hex_load_raw(reg_chrom, reg_start, reg_end, r + nwarps);
+        if (more) raw_n = hex_load_raw(reg_chrom, reg_start, reg_end, region_of(idx + nwarps));
         HexRegion gn;
         gn.nw = 0;
         int32_t *const row5 = counts5 + r * (int64_t)1024;
@@ -446,7 +451,8 @@ template <int HEX_WARPS, int MIN_CTAS, bool TRI, bool TOT, bool EXCH>
 int launch_hex_cfg(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
-               unsigned long long *totals3, unsigned int tot_limit_kb, cudaStream_t stream)
+               unsigned long long *totals3, unsigned int tot_limit_kb, const int32_t *rlist, const int32_t *rlist_n,
+               cudaStream_t stream)
 {
     constexpr int HEX_THREADS = HEX_WARPS * 32;
     constexpr size_t HEX_SMEM = H6_BYTES + (size_t)HEX_WARPS * (H6_BYTES + C5_BYTES + C3_BYTES);
@@ -463,7 +469,7 @@ int launch_hex_cfg(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
     kern<<<(unsigned)blocks, HEX_THREADS, HEX_SMEM, stream>>>(reinterpret_cast<const uint2 *>(p2), p2, nm,
                                                               (n_bases + 31) >> 5, chrom_off, chrom_len, reg_chrom,
                                                               reg_start, reg_end, n_reg, counts5, counts3, totals5,
-                                                              totals3, tot_limit_kb, 1u);
+                                                              totals3, tot_limit_kb, 1u, rlist, rlist_n);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
@@ -472,10 +478,12 @@ template <bool TRI, bool TOT, bool EXCH>
 int launch_hex(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
-               unsigned long long *totals3, unsigned int tot_limit_kb, cudaStream_t stream)
+               unsigned long long *totals3, unsigned int tot_limit_kb, const int32_t *rlist, const int32_t *rlist_n,
+               cudaStream_t stream)
 {
     return launch_hex_cfg<8, 2, TRI, TOT, EXCH>(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end,
-                                                n_reg, counts5, counts3, totals5, totals3, tot_limit_kb, stream);
+                                                n_reg, counts5, counts3, totals5, totals3, tot_limit_kb, rlist, rlist_n,
+                                                stream);
 }
 
 }  // namespace
@@ -488,11 +496,11 @@ int launch_scan_hex(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, con
                     const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start,
                     const int64_t *reg_end, int64_t n_reg, int32_t *counts5, int32_t *counts3,
                     unsigned long long *totals5, unsigned long long *totals3, unsigned int tot_limit_kb,
-                    bool plain_flush, cudaStream_t stream)
+                    bool plain_flush, const int32_t *rlist, const int32_t *rlist_n, cudaStream_t stream)
 {
 #define DIG_HEX_CALL(TRI, TOT, EXCH)                                                                                   \
     return launch_hex<TRI, TOT, EXCH>(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg,    \
-                                      counts5, counts3, totals5, totals3, tot_limit_kb, stream)
+                                      counts5, counts3, totals5, totals3, tot_limit_kb, rlist, rlist_n, stream)
     const int sel = (counts3 != nullptr ? 4 : 0) | (totals5 != nullptr ? 2 : 0) | (plain_flush ? 0 : 1);
     switch (sel) {
     case 0: DIG_HEX_CALL(false, false, false);

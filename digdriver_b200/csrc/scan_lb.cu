@@ -1,0 +1,730 @@
+// K2 "lane-bank" scan: pentanucleotide (+ optional trinucleotide) tables of window-sized plus-strand regions.
+//
+// Why.  The per-warp hexamer-pair kernel (scan_hex.cu) is bound by the shared-memory atomic pipe: 32 lanes of one
+// warp hit a 2048-word table at random, and the 32 banks serve such an instruction in ~3.56 passes
+// (tools/micro_atoms.cu).  A table that lives in ONE bank cannot conflict with a table that lives in another, so
+// here the roles are transposed: LANE l of every warp of the CTA works on window l of a batch of 32 windows, and
+// window l's hexamer table is the column "bank l" of a [1024 rows][32 lanes] word array.  Every atomic instruction
+// then touches 32 different banks: one pass, whatever the k-mers are (1.2 cycles measured against 3.56).
+//
+//   * table: 4096 hexamer bins per window as 8-bit fields, four to a word: row = first pentanucleotide of the
+//     hexamer (abcde), byte 3 - f for the sixth base f.  4 KB per window, 128 KB per batch.  The increment
+//     1 << 8 (3 - f) is ONE instruction (PRMT.F4E only looks at the two low bits of its selector).
+//   * 8-bit fields can overflow in low-complexity windows (>= 256 copies of one hexamer at even positions of one
+//     window).  That is detected EXACTLY: a carry out of a field lowers the sum of all bytes of the table by 255
+//     (or drops the count altogether out of the top byte), so "sum of bytes == number of pairs counted" holds
+//     iff no field overflowed.  A batch that fails the check is appended to a device-side list and redone by the
+//     per-warp kernel (16-bit fields, flushed as needed) right after this one; so are regions longer than
+//     LB_MAX_CHUNKS chunks.
+//   * genome staging: the 16 consumer warps split each 2048-base chunk of every window into 128-base spans; the
+//     chunk (+ one 16-byte granule of halo) of each of the 32 windows is brought into shared memory by TMA bulk
+//     copies (cp.async.bulk, mbarrier completion), two stages deep; consumer warp w issues the copies of windows
+//     2w and 2w+1 (ptxas serialises per-lane bulk copies, so they are spread over the warps).  Window strides of
+//     33 / 17 granules keep the 128-bit shared-memory reads of a quarter-warp on distinct banks.
+//   * write-out: pentanucleotide m gets dp4a(row m) (hexamers that START with m) plus byte f of the rows
+//     a.bcde over a (hexamers that END with m = bcdef).  Thread (warp w, lane l) produces four consecutive bins
+//     of window l per 64-bin slice, rotated by lane so the 128-bit stores into the slice buffer are conflict-free;
+//     a 17th warp applies the rare single-centre corrections, folds the slice into the genome-wide totals
+//     (column sums, two bins per lane in registers) and ships the [32 windows][64 bins] slice with ONE 2-D TMA
+//     tensor store (rows past n_reg are clipped by the tensor map).
+//   * pairs with ONE valid centre (an N three bases away, odd region boundaries, chromosome ends) and
+//     trinucleotide centres whose 5-mer is invalid are not hexamers: they go through a small per-batch list that
+//     the producer applies to the slice buffers / the trinucleotide block.  A list overflow fails the batch.
+//
+// Replaces the per-base Python loop of count_sequence_context (sequence_tools.py:65-78) for
+// count_contexts_in_bed(..., n_up=2, n_down=2) (sequence_tools.py:96-128) and, fused, the (1,1) run; bit-exact.
+#include <cuda.h>
+
+#include "scan_common.cuh"
+
+using namespace digscan;
+
+namespace {
+
+constexpr int LB_CW = 16;                          // consumer warps
+constexpr int LB_THREADS = (LB_CW + 1) * 32;       // + the producer warp
+constexpr int LB_CONS = LB_CW * 32;
+constexpr int LB_SPAN = 128;                       // bases per consumer thread per chunk
+constexpr int LB_CHUNK = LB_CW * LB_SPAN;          // 2048
+constexpr uint32_t LB_DSTRIDE = (LB_CHUNK + 64) / 4;     // 528 B of packed bases per window and stage (33 granules)
+constexpr uint32_t LB_MSTRIDE = (LB_CHUNK + 128) / 8;    // 272 B of N mask (17 granules)
+constexpr uint32_t LB_STAGE_BYTES = 32u * (LB_DSTRIDE + LB_MSTRIDE);
+constexpr int LB_MAX_CHUNKS = 16;                  // regions up to ~32 kb; longer ones go to the per-warp kernel
+constexpr int LB_EXC_CAP = 508;
+
+constexpr uint32_t OFF_TAB = 0u;                                   // [1024 rows][32 lanes] words
+constexpr uint32_t OFF_STG = 131072u;
+constexpr uint32_t OUT_BYTES = 32u * 64u * 4u;                     // one 64-bin slice of 32 windows
+constexpr uint32_t OFF_OUT = OFF_STG + 2u * LB_STAGE_BYTES;
+constexpr int LB_NOUT = 4;                                         // slice buffers in flight
+constexpr uint32_t OFF_TRI = OFF_OUT + LB_NOUT * OUT_BYTES;        // [64 bins][33] ints (padded: transposable)
+constexpr uint32_t TRI_BYTES = 64u * 33u * 4u;
+constexpr uint32_t OFF_EXC = OFF_TRI + TRI_BYTES;                  // two lists: [0] = count, [4..] entries
+constexpr uint32_t EXC_BYTES = 2048u;
+constexpr uint32_t OFF_CNT = OFF_EXC + 2u * EXC_BYTES;             // pairs counted per window, two parities
+constexpr uint32_t OFF_CHK = OFF_CNT + 256u;                       // sum of table bytes per window
+constexpr uint32_t OFF_BAR = OFF_CHK + 128u;
+constexpr uint32_t LB_SMEM = OFF_BAR + 128u;
+static_assert(OFF_BAR % 16u == 0u, "barrier block alignment");
+static_assert(LB_SMEM <= 232448u, "shared memory budget");
+
+enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_OUTFULL = 4, BAR_OUTEMPTY = 8, BAR_DONE = 12 };
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t a, uint32_t tx)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(tx) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+    return ok != 0u;
+}
+// bounded wait: a protocol error must abort the kernel, never hang the device
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
+{
+    uint32_t spins = 0u;
+    while (!mbar_try(a, parity))
+        if (++spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_s2g(const CUtensorMap *tmap, uint32_t src, int x, int y)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(x),
+                 "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LB_CONS) : "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void red_add(uint32_t a, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add(uint32_t a, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+// 1 << 8 (3 - (sel & 3)): the byte of the sixth base.  F4E extracts bytes sel .. sel + 3 of {0, 0x01000000}.
+// (top = 0x01000000 comes from the kernel arguments so that it stays in ONE register instead of being rematerialised)
+__device__ __forceinline__ uint32_t field_inc(uint32_t sel, uint32_t top)
+{
+    uint32_t v;
+    asm("prmt.b32.f4e %0, %1, %2, %3;" : "=r"(v) : "r"(top), "r"(0u), "r"(sel));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- geometry of one region, exactly as hex_setup() of scan_hex.cu walks it ---------------------------
+struct LbGeom {
+    int64_t O;                // origin: multiple of 128 (may be -128), first possible centre is O + 2
+    int lo5, hi5, lo3, hi3;   // centre ranges relative to O
+    int nch;                  // chunks to scan (0: nothing)
+    bool active, too_long;
+};
+
+template <bool TRI>
+__device__ __forceinline__ LbGeom lb_geom(int64_t r, int64_t n_reg, const int64_t *__restrict__ chrom_off,
+                                          const int64_t *__restrict__ chrom_len,
+                                          const int32_t *__restrict__ reg_chrom,
+                                          const int64_t *__restrict__ reg_start,
+                                          const int64_t *__restrict__ reg_end)
+{
+    LbGeom g;
+    g.O = 0;
+    g.lo5 = g.hi5 = g.lo3 = g.hi3 = 0;
+    g.nch = 0;
+    g.active = r < n_reg;
+    g.too_long = false;
+    if (g.active) {
+        const int32_t c = __ldg(reg_chrom + r);
+        const int64_t rs = __ldg(reg_start + r), re = __ldg(reg_end + r);
+        const int64_t L = __ldg(chrom_len + c), off = __ldg(chrom_off + c);
+        int64_t gs[2], ge[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int n = 2 - t;                  // t = 0: pentanucleotide, t = 1: trinucleotide
+            int64_t s = rs < n ? n : rs;          // START == 0 -> n_up (sequence_tools.py:25-26)
+            int64_t f0 = s - n, f1 = re + n;
+            if (f1 > L) f1 = L;                   // faidx clips at the chromosome end
+            if (f0 > L) f0 = L;
+            gs[t] = off + f0 + n;
+            ge[t] = off + f1 - n;
+            if (ge[t] < gs[t]) ge[t] = gs[t];
+        }
+        int64_t lowc = gs[0], hic = ge[0];
+        if (TRI) {
+            if (ge[1] > gs[1]) {
+                if (ge[0] > gs[0]) {
+                    lowc = gs[1] < gs[0] ? gs[1] : gs[0];
+                    hic = ge[1] > ge[0] ? ge[1] : ge[0];
+                } else {
+                    lowc = gs[1];
+                    hic = ge[1];
+                }
+            }
+        }
+        if (hic > lowc) {
+            const int64_t O = ((lowc - 2) >> 7) << 7;       // arithmetic shift: floor
+            const int64_t nch = (hic - O - 2 + (LB_CHUNK - 1)) / LB_CHUNK;
+            if (nch > LB_MAX_CHUNKS) {
+                g.too_long = true;
+            } else {
+                g.O = O;
+                g.nch = (int)nch;
+                g.lo5 = (int)(gs[0] - O);
+                g.hi5 = (int)(ge[0] - O);
+                g.lo3 = (int)(gs[1] - O);
+                g.hi3 = (int)(ge[1] - O);
+            }
+        }
+    }
+    return g;
+}
+
+// word idx (0..8) of the thread's nine 16-base words without dynamic register indexing
+__device__ __forceinline__ uint32_t lb_sel(const uint32_t (&D)[9], int idx)
+{
+    uint32_t v = 0u;
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+        if (q == idx) v = D[q];
+    return v;
+}
+// nbits starting at base `b` (local index) of the thread's 144-base string
+__device__ __forceinline__ uint32_t lb_bits(const uint32_t (&D)[9], int b, int nbits)
+{
+    const int q = b >> 4, o = (b & 15) * 2;
+    const unsigned long long v = ((unsigned long long)lb_sel(D, q) << 32) | lb_sel(D, q + 1 > 8 ? 8 : q + 1);
+    return (uint32_t)(v >> (64 - o - nbits)) & ((1u << nbits) - 1u);
+}
+
+// the 64 hexamers of a 128-base span: hexamer i = local bases 2i .. 2i+5 (centres 2i+2, 2i+3)
+// k32 is the constant 32 read from the kernel arguments: ptxas cannot turn the multiply-add into a second shift, so the
+// address costs one LOP3 (integer pipe) + one IMAD (FMA pipe) instead of SHF + LOP3 + IADD on the busier integer pipe
+template <bool PRED>
+__device__ __forceinline__ void lb_pairs(const uint32_t (&D)[9], uint32_t tabl, uint32_t k32, uint32_t top,
+                                         const uint32_t (&PV)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const int q = i >> 3, off = 4 * (i & 7);
+        uint32_t r;
+        if (off <= 20) r = D[q] >> (20 - off);
+        else r = __funnelshift_r(D[q + 1], D[q], 52 - off);
+        const bool go = !PRED || ((PV[i >> 4] >> (31 - 2 * (i & 15))) & 1u);
+        if (go) {
+            uint32_t addr;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(r & 0xFFCu), "r"(k32), "r"(tabl));
+            red_add(addr, field_inc(r, top));
+        }
+    }
+}
+
+struct LbArgs {
+    const uint32_t *p2;
+    const uint32_t *nmask;
+    int64_t n_bases;
+    const int64_t *chrom_off;
+    const int64_t *chrom_len;
+    const int32_t *reg_chrom;
+    const int64_t *reg_start;
+    const int64_t *reg_end;
+    int64_t n_reg;
+    int32_t *counts5;
+    int32_t *counts3;
+    unsigned long long *totals5;
+    unsigned long long *totals3;
+    int32_t *fb_count;
+    int32_t *fb_list;
+    unsigned int tot_limit_kb;
+    uint32_t k32;             // = 32 (see lb_pairs)
+    uint32_t top;             // = 0x01000000 (see field_inc)
+    uint32_t zero;            // = 0
+};
+
+// ---- genome staging: issued by the consumer warps, two lanes (= two windows) per warp ---------------------
+// The chunk sequence of a CTA is the concatenation of the chunks of its batches; chunk number ci lands in stage
+// ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by all sixteen warps.
+struct LbIssuer {
+    int64_t b;        // batch of the next chunk to issue
+    int k;            // chunk inside that batch
+    int nch;          // chunks of batch b (warp maximum)
+    uint32_t ci;      // chunks issued so far
+    LbGeom g;         // this lane's window of batch b
+};
+
+template <bool TRI>
+__device__ __forceinline__ void lb_issue_next(LbIssuer &I, const LbArgs &A, int64_t n_batches, uint32_t sbase, int warp,
+                                              int lane)
+{
+    while (I.b < n_batches && I.k >= I.nch) {            // next batch that has something to scan
+        I.b += gridDim.x;
+        I.k = 0;
+        I.nch = 0;
+        if (I.b < n_batches) {
+            I.g = lb_geom<TRI>(I.b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+            I.nch = warp_max(I.g.nch);
+        }
+    }
+    if (I.b >= n_batches) return;
+    const uint32_t bar = sbase + OFF_BAR;
+    const uint32_t stage = I.ci & 1u;
+    mbar_wait(bar + 8u * (BAR_EMPTY + stage), ((I.ci >> 1) & 1u) ^ 1u);
+    if ((lane >> 1) == warp) {
+        const uint32_t full = bar + 8u * (BAR_FULL + stage);
+        if (I.k < I.g.nch) {
+            const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
+            const int64_t G0 = I.g.O + (int64_t)I.k * LB_CHUNK;              // first staged base: multiple of 128, >= -128
+            int64_t dsrc = G0 >> 2, msrc = G0 >> 3;
+            uint32_t ddst = stg + (uint32_t)lane * LB_DSTRIDE, mdst = stg + 32u * LB_DSTRIDE + (uint32_t)lane * LB_MSTRIDE;
+            int64_t dbytes = LB_DSTRIDE, mbytes = LB_MSTRIDE;
+            if (G0 < 0) {                                                    // no base before the genome is ever needed
+                dsrc = 0; ddst += 32u; dbytes -= 32;
+                msrc = 0; mdst += 16u; mbytes -= 16;
+            }
+            const int64_t davail = (A.n_bases >> 2) - dsrc, mavail = (A.n_bases >> 3) - msrc;
+            if (dbytes > davail) dbytes = davail;
+            if (mbytes > mavail) mbytes = mavail;
+            mbar_arrive_tx(full, (uint32_t)(dbytes + mbytes));
+            bulk_g2s(ddst, reinterpret_cast<const unsigned char *>(A.p2) + dsrc, (uint32_t)dbytes, full);
+            bulk_g2s(mdst, reinterpret_cast<const unsigned char *>(A.nmask) + msrc, (uint32_t)mbytes, full);
+        } else {
+            mbar_arrive(full);
+        }
+    }
+    __syncwarp();
+    ++I.k;
+    ++I.ci;
+}
+
+// ---- consumer warps ----------------------------------------------------------------------------------
+template <bool TRI>
+__device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int warp, int lane)
+{
+    const uint32_t bar = sbase + OFF_BAR;
+    const uint32_t tabl = sbase + OFF_TAB + (uint32_t)lane * 4u;
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    const int ctid = warp * 32 + lane;
+    uint32_t cit = 0u, sit = 0u, bi = 0u;
+    // one VECTOR-register copy of the PRMT constant: made formally lane-dependent (A.zero = 0), otherwise ptxas keeps it
+    // in a uniform register and copies it into a fresh vector register for every PRMT
+    const uint32_t top_r = A.top | (tabl & A.zero);
+
+    LbIssuer I;
+    I.b = blockIdx.x;
+    I.k = 0;
+    I.ci = 0u;
+    I.g = lb_geom<TRI>(I.b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+    I.nch = warp_max(I.g.nch);
+    lb_issue_next<TRI>(I, A, n_batches, sbase, warp, lane);
+    lb_issue_next<TRI>(I, A, n_batches, sbase, warp, lane);
+
+    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
+        const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const int nch = warp_max(g.nch);
+        const uint32_t par = bi & 1u;
+        const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
+        uint32_t npairs = 0u;
+        for (int k = 0; k < nch; ++k, ++cit) {
+            const uint32_t stage = cit & 1u;
+            mbar_wait(bar + 8u * (BAR_FULL + stage), (cit >> 1) & 1u);
+            const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
+            const uint32_t dptr = stg + (uint32_t)lane * LB_DSTRIDE + (uint32_t)warp * 32u;
+            const uint32_t mptr = stg + 32u * LB_DSTRIDE + (uint32_t)lane * LB_MSTRIDE + (uint32_t)warp * 16u;
+            uint32_t D[9], M[5];
+            {
+                const uint4 a = lds128(dptr), c = lds128(dptr + 16u), m = lds128(mptr);
+                D[0] = a.x; D[1] = a.y; D[2] = a.z; D[3] = a.w;
+                D[4] = c.x; D[5] = c.y; D[6] = c.z; D[7] = c.w;
+                D[8] = lds32(dptr + 32u);
+                M[0] = m.x; M[1] = m.y; M[2] = m.z; M[3] = m.w;
+                M[4] = lds32(mptr + 16u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + 8u * (BAR_EMPTY + stage));      // the stage is in registers now
+            const int base = k * LB_CHUNK + warp * LB_SPAN;                  // local base 0 relative to the origin
+            const int lo5 = g.lo5 - base, hi5 = g.hi5 - base;                // centre c (local base index) valid: lo5 <= c < hi5
+            const uint32_t any_n = M[0] | M[1] | M[2] | M[3] | (M[4] & 0xF0000000u);
+            uint32_t PV[4] = {0u, 0u, 0u, 0u};
+            if (any_n == 0u && lo5 <= 2 && hi5 >= 130) {
+                lb_pairs<false>(D, tabl, A.k32, top_r, PV);
+                npairs += 64u;
+            } else if (k < g.nch) {
+                const int lo3 = g.lo3 - base, hi3 = g.hi3 - base;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // bit 31 - t of word j <-> centre c' = 32 j + t = (local base index of the centre) - 2
+                    const uint32_t s1 = __funnelshift_l(M[j + 1], M[j], 1), s2 = __funnelshift_l(M[j + 1], M[j], 2);
+                    const uint32_t s3 = __funnelshift_l(M[j + 1], M[j], 3), s4 = __funnelshift_l(M[j + 1], M[j], 4);
+                    const uint32_t b3 = s1 | s2 | s3;                        // N in bases c'+1 .. c'+3
+                    const uint32_t b5 = b3 | M[j] | s4;                      // N in bases c' .. c'+4
+                    const uint32_t v5 = range_mask(lo5 - 2 - 32 * j, hi5 - 2 - 32 * j) & ~b5;
+                    const uint32_t pv = v5 & (v5 << 1) & 0xAAAAAAAAu;        // both centres of the pair valid
+                    PV[j] = pv;
+                    npairs += (uint32_t)__popc(pv);
+                    uint32_t single = v5 & ~(pv | (pv >> 1));
+                    uint32_t x3 = 0u;
+                    if constexpr (TRI) x3 = range_mask(lo3 - 2 - 32 * j, hi3 - 2 - 32 * j) & ~b3 & ~v5;
+                    while (single) {
+                        const int t = __clz(single);
+                        single &= ~(0x80000000u >> t);
+                        const uint32_t key = lb_bits(D, 32 * j + t, 10);
+                        const uint32_t pos = atom_add(exc, 1u);
+                        if (pos < (uint32_t)LB_EXC_CAP) sts32(exc + 16u + 4u * pos, ((uint32_t)lane << 16) | key);
+                    }
+                    while (x3) {
+                        const int t = __clz(x3);
+                        x3 &= ~(0x80000000u >> t);
+                        const uint32_t key = lb_bits(D, 32 * j + t + 1, 6);
+                        const uint32_t pos = atom_add(exc, 1u);
+                        if (pos < (uint32_t)LB_EXC_CAP) sts32(exc + 16u + 4u * pos, ((uint32_t)lane << 16) | 0x8000u | key);
+                    }
+                }
+                if ((PV[0] | PV[1] | PV[2] | PV[3]) != 0u) lb_pairs<true>(D, tabl, A.k32, top_r, PV);
+            }
+            __syncwarp();
+            lb_issue_next<TRI>(I, A, n_batches, sbase, warp, lane);          // chunk cit + 2
+        }
+        if (npairs) red_add(sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, npairs);
+        cons_sync();                                                         // every hexamer of the batch is in the tables
+        mbar_wait(bar + 8u * BAR_DONE, (bi & 1u) ^ 1u);                      // the writer warp finished the previous batch
+
+        uint32_t chk = 0u;
+#pragma unroll 1
+        for (int sg = 0; sg < 16; ++sg, ++sit) {
+            const uint32_t buf = sit & (LB_NOUT - 1);
+            mbar_wait(bar + 8u * (BAR_OUTEMPTY + buf), ((sit / LB_NOUT) & 1u) ^ 1u);
+            const int jl = (warp + lane) & 15;
+            const int j = 16 * sg + jl;                                      // bins 4j .. 4j+3 of window `lane`
+            const uint32_t k0 = lds32(tabl + (uint32_t)(4 * j + 0) * 128u), k1 = lds32(tabl + (uint32_t)(4 * j + 1) * 128u);
+            const uint32_t k2 = lds32(tabl + (uint32_t)(4 * j + 2) * 128u), k3 = lds32(tabl + (uint32_t)(4 * j + 3) * 128u);
+            const uint32_t w0 = lds32(tabl + (uint32_t)(j)*128u), w1 = lds32(tabl + (uint32_t)(256 + j) * 128u);
+            const uint32_t w2 = lds32(tabl + (uint32_t)(512 + j) * 128u), w3 = lds32(tabl + (uint32_t)(768 + j) * 128u);
+            // hexamers STARTING with pentanucleotide m: all four fields of row m
+            const uint32_t a0 = __dp4a(k0, 0x01010101u, 0u), a1 = __dp4a(k1, 0x01010101u, 0u);
+            const uint32_t a2 = __dp4a(k2, 0x01010101u, 0u), a3 = __dp4a(k3, 0x01010101u, 0u);
+            chk += (a0 + a1) + (a2 + a3);
+            // hexamers ENDING with m = (bcde f): byte 3 - f of rows (a bcde), summed over a (<= 4 x 255 per half)
+            const uint32_t ev = (w0 & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + (w2 & 0x00FF00FFu) + (w3 & 0x00FF00FFu);
+            const uint32_t od = ((w0 >> 8) & 0x00FF00FFu) + ((w1 >> 8) & 0x00FF00FFu) + ((w2 >> 8) & 0x00FF00FFu) +
+                                ((w3 >> 8) & 0x00FF00FFu);
+            const uint32_t o0 = a0 + (od >> 16), o1 = a1 + (ev >> 16), o2 = a2 + (od & 0xFFFFu), o3 = a3 + (ev & 0xFFFFu);
+            sts128(sbase + OFF_OUT + buf * OUT_BYTES + (uint32_t)lane * 256u + (uint32_t)jl * 16u, o0, o1, o2, o3);
+            if constexpr (TRI)
+                red_add(sbase + OFF_TRI + ((uint32_t)(j & 63) * 33u + (uint32_t)lane) * 4u, (o0 + o1) + (o2 + o3));
+            if (sg == 15 && chk) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, chk);
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + 8u * (BAR_OUTFULL + buf));
+        }
+        cons_sync();                                                         // all table reads done
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sts128(sbase + OFF_TAB + (uint32_t)(ctid + LB_CONS * i) * 16u, 0u, 0u, 0u, 0u);
+        cons_sync();
+    }
+}
+
+// ---- writer warp: corrections, genome-wide totals, TMA stores, per-batch bookkeeping ------------------------
+template <bool TRI, bool TOT>
+__device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tmap, uint32_t sbase, int lane)
+{
+    const uint32_t bar = sbase + OFF_BAR;
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    uint32_t sit = 0u, bi = 0u;
+    unsigned int tot5[TOT ? 32 : 1], tot3[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < (TOT ? 32 : 1); ++i) tot5[i] = 0u;
+    unsigned int acc_kb = 0u;
+
+    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
+        const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const uint32_t par = bi & 1u;
+        const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
+        const int64_t r = b * 32 + lane;
+        unsigned int tmp5[TOT ? 32 : 1], tmp3[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < (TOT ? 32 : 1); ++i) tmp5[i] = 0u;
+        uint32_t n_exc_raw = 0u;
+#pragma unroll
+        for (int sg = 0; sg < 16; ++sg, ++sit) {
+            const uint32_t buf = sit & (LB_NOUT - 1);
+            mbar_wait(bar + 8u * (BAR_OUTFULL + buf), (sit / LB_NOUT) & 1u);
+            const uint32_t out = sbase + OFF_OUT + buf * OUT_BYTES;
+            if (sg == 0) n_exc_raw = lds32(exc);                             // final: every consumer is past the scan
+            const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
+            for (uint32_t e = lane; e < n_exc; e += 32u) {
+                const uint32_t ent = lds32(exc + 16u + 4u * e);
+                if (!(ent & 0x8000u) && ((ent & 1023u) >> 6) == (uint32_t)sg)
+                    red_add(out + (ent >> 16) * 256u + (ent & 63u) * 4u, 1u);
+            }
+            __syncwarp();
+            if constexpr (TOT) {
+#pragma unroll 8
+                for (int l2 = 0; l2 < 32; ++l2) {
+                    const uint2 v = lds64(out + (uint32_t)l2 * 256u + (uint32_t)lane * 8u);
+                    tmp5[2 * sg] += v.x;
+                    tmp5[2 * sg + 1] += v.y;
+                }
+            }
+            fence_async();
+            __syncwarp();
+            if (lane == 0) {
+                tensor_s2g(tmap, out, 64 * sg, (int)(b * 32));
+                bulk_commit();
+                bulk_wait_read<LB_NOUT - 1>();                               // the store issued LB_NOUT - 1 slices ago has left its buffer
+                if (sit >= (uint32_t)(LB_NOUT - 1)) mbar_arrive(bar + 8u * (BAR_OUTEMPTY + ((sit - (LB_NOUT - 1)) & (LB_NOUT - 1))));
+            }
+            __syncwarp();
+        }
+        const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
+        if constexpr (TRI) {
+            const uint32_t tri = sbase + OFF_TRI;
+            for (uint32_t e = lane; e < n_exc; e += 32u) {
+                const uint32_t ent = lds32(exc + 16u + 4u * e);
+                const uint32_t bin = (ent & 0x8000u) ? (ent & 63u) : ((ent >> 2) & 63u);
+                red_add(tri + (bin * 33u + (ent >> 16)) * 4u, 1u);
+            }
+            __syncwarp();
+            for (int l2 = 0; l2 < 32; ++l2) {
+                const int64_t r2 = b * 32 + l2;
+                const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
+                const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
+                if (r2 < A.n_reg) {
+                    __stcs(A.counts3 + r2 * 64 + lane, (int)v0);
+                    __stcs(A.counts3 + r2 * 64 + 32 + lane, (int)v1);
+                }
+                tmp3[0] += v0;
+                tmp3[1] += v1;
+            }
+            __syncwarp();
+            for (int i = 0; i < 66; ++i) sts32(tri + (uint32_t)(lane + 32 * i) * 4u, 0u);
+        }
+        // exact overflow check: sum of all table bytes == hexamers counted
+        const uint32_t cnt_a = sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, chk_a = sbase + OFF_CHK + (uint32_t)lane * 4u;
+        const bool bad = lds32(cnt_a) != lds32(chk_a);
+        const bool fail = __any_sync(0xffffffffu, bad) || n_exc_raw > (uint32_t)LB_EXC_CAP;
+        sts32(cnt_a, 0u);
+        sts32(chk_a, 0u);
+        if (lane == 0) sts32(exc, 0u);
+        if (g.too_long || (fail && g.active)) {
+            const int pos = atomicAdd(A.fb_count, 1);
+            A.fb_list[pos] = (int32_t)r;
+        }
+        if constexpr (TOT) {
+            if (!fail) {
+                // 32-bit register totals: move them out before 2^31 bases have been folded in
+                unsigned int kb = g.nch > 0 ? (unsigned int)(g.nch * (LB_CHUNK >> 10)) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) kb += __shfl_xor_sync(0xffffffffu, kb, o);
+                if (acc_kb + kb > A.tot_limit_kb || acc_kb + kb < acc_kb) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (tot5[i]) atomicAdd(A.totals5 + 64 * (i >> 1) + 2 * lane + (i & 1), (unsigned long long)tot5[i]);
+                        tot5[i] = 0u;
+                    }
+                    if constexpr (TRI) {
+                        if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
+                        if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
+                        tot3[0] = tot3[1] = 0u;
+                    }
+                    acc_kb = 0u;
+                }
+                acc_kb += kb;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tot5[i] += tmp5[i];
+                tot3[0] += tmp3[0];
+                tot3[1] += tmp3[1];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8u * BAR_DONE);
+    }
+    if constexpr (TOT) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (tot5[i]) atomicAdd(A.totals5 + 64 * (i >> 1) + 2 * lane + (i & 1), (unsigned long long)tot5[i]);
+        if constexpr (TRI) {
+            if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
+            if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
+        }
+    }
+    bulk_wait_all();
+}
+
+template <bool TRI, bool TOT>
+__global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if ((sbase & 127u) != 0u) __trap();                  // bank = lane and the TMA tile both need a 128-byte aligned base
+
+    for (uint32_t i = threadIdx.x; i < OFF_BAR / 16u; i += LB_THREADS) sts128(sbase + i * 16u, 0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) {
+        const uint32_t bar = sbase + OFF_BAR;
+        mbar_init(bar + 8u * (BAR_FULL + 0), 32u);
+        mbar_init(bar + 8u * (BAR_FULL + 1), 32u);
+        mbar_init(bar + 8u * (BAR_EMPTY + 0), LB_CW);
+        mbar_init(bar + 8u * (BAR_EMPTY + 1), LB_CW);
+#pragma unroll
+        for (int i = 0; i < LB_NOUT; ++i) {
+            mbar_init(bar + 8u * (BAR_OUTFULL + i), LB_CW);
+            mbar_init(bar + 8u * (BAR_OUTEMPTY + i), 1u);
+        }
+        mbar_init(bar + 8u * BAR_DONE, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async();
+    }
+    __syncthreads();
+    if (warp == LB_CW) lb_writer<TRI, TOT>(A, &tmap, sbase, lane);
+    else lb_consumer<TRI>(A, sbase, warp, lane);
+}
+
+typedef CUresult (*LbEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// counts5 as a 2-D int32 tensor [n_reg][1024] with a [32 rows][64 columns] box: one slice of one batch per store
+int lb_tensor_map(CUtensorMap *tmap, int32_t *counts5, int64_t n_reg)
+{
+    static LbEncodeFn encode = nullptr;                  // driver entry point, resolved once (no libcuda link dependency)
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DIG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (fn == nullptr || q != cudaDriverEntryPointSuccess) {
+            dig::set_error("%s: cuTensorMapEncodeTiled is not available", __func__);
+            return DIG_ERR_CUDA;
+        }
+        encode = reinterpret_cast<LbEncodeFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {1024u, (cuuint64_t)n_reg};
+    const cuuint64_t gstride[1] = {4096u};
+    const cuuint32_t box[2] = {64u, 32u};
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult rc = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2u, counts5, gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        dig::set_error("%s: cuTensorMapEncodeTiled failed (%d)", __func__, (int)rc);
+        return DIG_ERR_CUDA;
+    }
+    return DIG_OK;
+}
+
+template <bool TRI, bool TOT>
+int launch_lb(const LbArgs &A, const CUtensorMap &tmap, cudaStream_t stream)
+{
+    auto kern = scan_lb_kernel<TRI, TOT>;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_SMEM));
+        attr_set = true;
+    }
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    int64_t blocks = dig::sm_count();
+    if (blocks > n_batches) blocks = n_batches;
+    kern<<<(unsigned)blocks, LB_THREADS, LB_SMEM, stream>>>(A, tmap);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
+}  // namespace
+
+namespace digscan {
+
+size_t scan_lb_workspace_bytes(int64_t n_reg) { return 16 + (size_t)(n_reg > 0 ? n_reg : 0) * sizeof(int32_t); }
+
+bool scan_lb_usable(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int32_t *counts5, const void *workspace,
+                    size_t workspace_bytes, int64_t n_reg)
+{
+    return workspace != nullptr && workspace_bytes >= scan_lb_workspace_bytes(n_reg) && (n_bases & 127) == 0 &&
+           (reinterpret_cast<uintptr_t>(p2) & 15u) == 0 && (reinterpret_cast<uintptr_t>(nm) & 15u) == 0 &&
+           (reinterpret_cast<uintptr_t>(counts5) & 15u) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
+           n_reg > 0 && n_reg < (int64_t)0x7fffffe0;
+}
+
+// Lane-bank scan of all regions, then the per-warp hexamer kernel over the regions it listed (overflowed batches,
+// regions longer than LB_MAX_CHUNKS chunks).  The list lives in the caller's workspace; no host synchronisation.
+int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
+                   const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
+                   int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
+                   unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, cudaStream_t stream)
+{
+    int32_t *fb_count = reinterpret_cast<int32_t *>(workspace);
+    int32_t *fb_list = fb_count + 4;
+    CUtensorMap tmap;
+    const int trc = lb_tensor_map(&tmap, counts5, n_reg);
+    if (trc != DIG_OK) return trc;
+    DIG_CUDA(cudaMemsetAsync(fb_count, 0, 16, stream));
+    LbArgs A;
+    A.p2 = p2; A.nmask = nm; A.n_bases = n_bases; A.chrom_off = chrom_off; A.chrom_len = chrom_len;
+    A.reg_chrom = reg_chrom; A.reg_start = reg_start; A.reg_end = reg_end; A.n_reg = n_reg;
+    A.counts5 = counts5; A.counts3 = counts3; A.totals5 = totals5; A.totals3 = totals3;
+    A.k32 = 32u; A.top = 0x01000000u; A.zero = 0u;
+    A.fb_count = fb_count; A.fb_list = fb_list; A.tot_limit_kb = tot_limit_kb < (1u << 21) ? tot_limit_kb : (1u << 21);
+    int rc;
+    if (counts3 != nullptr) rc = totals5 != nullptr ? launch_lb<true, true>(A, tmap, stream) : launch_lb<true, false>(A, tmap, stream);
+    else rc = totals5 != nullptr ? launch_lb<false, true>(A, tmap, stream) : launch_lb<false, false>(A, tmap, stream);
+    if (rc != DIG_OK) return rc;
+    return launch_scan_hex(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts5, counts3,
+                           totals5, totals3, tot_limit_kb, false, fb_list, fb_count, stream);
+}
+
+}  // namespace digscan

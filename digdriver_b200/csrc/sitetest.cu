@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) window_denominators_kernel(const int32_t 
 
 __global__ void __launch_bounds__(256) site_test_kernel(
     const int32_t *__restrict__ site_chrom, const int64_t *__restrict__ site_start, const uint8_t *__restrict__ site_sub,
-    const int8_t *__restrict__ site_strand, const double *__restrict__ site_k, int64_t n_site, int64_t window,
+    const int8_t *__restrict__ site_strand, const double *__restrict__ site_k, int64_t n_site, int64_t window, int n_chrom,
     const int64_t *__restrict__ win_map_off, const int32_t *__restrict__ win_map, const double *__restrict__ y_pred,
     const double *__restrict__ stdv, const double *__restrict__ denom_plus, const double *__restrict__ denom_minus,
     const double *__restrict__ d_pr, double cj, double *__restrict__ p_out, double *__restrict__ exp_out,
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) site_test_kernel(
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_site; i += stride) {
         const int32_t c = site_chrom[i];
         const int64_t wi = site_start[i] / window;                         // START >= 0
-        const int64_t m0 = __ldg(win_map_off + c), mn = __ldg(win_map_off + c + 1) - m0;
+        const bool chrom_ok = c >= 0 && c < n_chrom;                       // outside the window map: KeyError below
+        const int64_t m0 = chrom_ok ? __ldg(win_map_off + c) : 0, mn = chrom_ok ? __ldg(win_map_off + c + 1) - m0 : 0;
         const int32_t row = wi < mn ? __ldg(win_map + m0 + wi) : -1;
         if (row < 0) {                                                     // the reference raises KeyError here
             atomicMax(status, 2);
@@ -115,12 +116,12 @@ int dig_window_denominators(const int32_t *win_counts_d, const double *d_pr_d, i
 }
 
 int dig_site_test(const int32_t *site_chrom_d, const int64_t *site_start_d, const uint8_t *site_sub_d,
-                  const int8_t *site_strand_d, const double *site_k_d, int64_t n_site, int64_t window,
+                  const int8_t *site_strand_d, const double *site_k_d, int64_t n_site, int64_t window, int n_chrom,
                   const int64_t *win_map_off_d, const int32_t *win_map_d, const double *y_pred_d, const double *std_d,
                   const double *denom_plus_d, const double *denom_minus_d, const double *d_pr_d, double cj,
                   double *p_out_d, double *exp_out_d, double *pval_out_d, int32_t *status_d, void *stream)
 {
-    DIG_CHECK_ARG(n_site >= 0 && window > 0, "bad sizes");
+    DIG_CHECK_ARG(n_site >= 0 && window > 0 && n_chrom >= 0, "bad sizes");
     DIG_CHECK_ARG(status_d != nullptr, "null pointer");
     DIG_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int32_t), (cudaStream_t)stream));
     if (n_site == 0) return DIG_OK;
@@ -131,7 +132,7 @@ int dig_site_test(const int32_t *site_chrom_d, const int64_t *site_start_d, cons
     const int64_t cap = (int64_t)dig::sm_count() * 16;
     if (blocks > cap) blocks = cap;
     site_test_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        site_chrom_d, site_start_d, site_sub_d, site_strand_d, site_k_d, n_site, window, win_map_off_d, win_map_d,
+        site_chrom_d, site_start_d, site_sub_d, site_strand_d, site_k_d, n_site, window, n_chrom, win_map_off_d, win_map_d,
         y_pred_d, std_d, denom_plus_d, denom_minus_d, d_pr_d, cj, p_out_d, exp_out_d, pval_out_d, status_d);
     DIG_CHECK_LAUNCH();
     return DIG_OK;

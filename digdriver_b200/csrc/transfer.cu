@@ -37,8 +37,8 @@ template <bool RC>
 __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
     const int32_t *__restrict__ elt_chrom, const int8_t *__restrict__ elt_strand,
     const int64_t *__restrict__ blk_ptr, const int64_t *__restrict__ blk_start,
-    const int64_t *__restrict__ blk_end, int64_t n_elt, int64_t window, const int64_t *__restrict__ win_map_off,
-    const int32_t *__restrict__ win_map, const int32_t *__restrict__ win_counts,
+    const int64_t *__restrict__ blk_end, int64_t n_elt, int64_t window, int n_chrom,
+    const int64_t *__restrict__ win_map_off, const int32_t *__restrict__ win_map, const int32_t *__restrict__ win_counts,
     const double *__restrict__ y_pred, const double *__restrict__ stdv, const double *__restrict__ y_true,
     const uint8_t *__restrict__ flag, int64_t n_win, int n_cohort, const double *__restrict__ d_pr,
     const int32_t *__restrict__ blk_counts, const double *__restrict__ L_elt, int n_col, int span_words,
@@ -114,8 +114,11 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
 #pragma unroll
         for (int q = 0; q < MAX_COHORT_PER_LANE; ++q) mu[q] = var[q] = ro[q] = 0.0, fl[q] = 0;
         int nw = 0;
-        const int64_t map0 = win_map_off[c];
-        const int64_t map_n = win_map_off[c + 1] - map0;
+        // a chromosome outside the window map has no window at all: every lookup below misses and the element gets
+        // status 2 (the reference raises KeyError for it)
+        const bool chrom_ok = c >= 0 && c < n_chrom;
+        const int64_t map0 = chrom_ok ? win_map_off[c] : 0;
+        const int64_t map_n = chrom_ok ? win_map_off[c + 1] - map0 : 0;
         for (int w = 0; ok && w < words; ++w) {
             const uint32_t bits = bitmap[w];
             const int cnt = __popc(bits);
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(TW * 32, 8) transfer_kernel(
 
 extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
                                     const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt,
-                                    int64_t window, const int64_t *win_map_off_d, const int32_t *win_map_d,
+                                    int64_t window, int n_chrom, const int64_t *win_map_off_d, const int32_t *win_map_d,
                                     const int32_t *win_counts_d, const double *y_pred_d, const double *std_d,
                                     const double *y_true_d, const uint8_t *flag_d, int64_t n_win, int n_cohort,
                                     const double *d_pr_d, const int32_t *blk_counts_d, const double *L_elt_d,
@@ -310,7 +313,7 @@ extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *el
                                     uint8_t *flag_out_d, int64_t *r_size_d, int64_t *elt_size_d, double *p_out_d,
                                     int32_t *n_win_out_d, int32_t *status_d, void *stream)
 {
-    DIG_CHECK_ARG(n_elt >= 0 && n_win >= 0 && window > 0, "bad sizes");
+    DIG_CHECK_ARG(n_elt >= 0 && n_win >= 0 && window > 0 && n_chrom >= 0, "bad sizes");
     DIG_CHECK_ARG(n_cohort >= 1 && n_cohort <= 32 * MAX_COHORT_PER_LANE, "n_cohort must be in [1, 64] per call");
     DIG_CHECK_ARG((blk_counts_d != nullptr) != (L_elt_d != nullptr), "pass exactly one of blk_counts_d / L_elt_d");
     DIG_CHECK_ARG(blk_counts_d == nullptr || n_col == 1, "n_col must be 1 with blk_counts_d");
@@ -335,7 +338,7 @@ extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *el
     const int64_t cap = (int64_t)dig::sm_count() * 64;      // ~one element per warp: the hardware scheduler balances long genes
     if (blocks > cap) blocks = cap;
     transfer_kernel<false><<<(unsigned)blocks, TW * 32, smem, st>>>(
-        elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, win_map_off_d, win_map_d,
+        elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, n_chrom, win_map_off_d, win_map_d,
         win_counts_d, y_pred_d, std_d, y_true_d, flag_d, n_win, n_cohort, d_pr_d, blk_counts_d, L_elt_d, n_col,
         span_words, mu_d, sigma_d, r_obs_d, flag_out_d, r_size_d, elt_size_d, p_out_d, n_win_out_d, status_d, nullptr);
     DIG_CHECK_LAUNCH();
@@ -347,11 +350,11 @@ extern "C" int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *el
 // elements (the reference stores it repeated x3 as 192 values).  Same kernel as dig_element_transfer, no cohorts.
 extern "C" int dig_element_region_counts(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
                                          const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt,
-                                         int64_t window, const int64_t *win_map_off_d, const int32_t *win_map_d,
+                                         int64_t window, int n_chrom, const int64_t *win_map_off_d, const int32_t *win_map_d,
                                          const int32_t *win_counts_d, int64_t n_win, int max_span_windows,
                                          int64_t *region_counts_d, int32_t *n_win_out_d, int32_t *status_d, void *stream)
 {
-    DIG_CHECK_ARG(n_elt >= 0 && n_win >= 0 && window > 0 && max_span_windows >= 1, "bad sizes");
+    DIG_CHECK_ARG(n_elt >= 0 && n_win >= 0 && window > 0 && max_span_windows >= 1 && n_chrom >= 0, "bad sizes");
     DIG_CHECK_ARG(status_d != nullptr, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     DIG_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int32_t), st));
@@ -371,7 +374,7 @@ extern "C" int dig_element_region_counts(const int32_t *elt_chrom_d, const int8_
     const int64_t cap = (int64_t)dig::sm_count() * 64;
     if (blocks > cap) blocks = cap;
     transfer_kernel<true><<<(unsigned)blocks, TW * 32, smem, st>>>(
-        elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, win_map_off_d, win_map_d,
+        elt_chrom_d, elt_strand_d, blk_ptr_d, blk_start_d, blk_end_d, n_elt, window, n_chrom, win_map_off_d, win_map_d,
         win_counts_d, nullptr, nullptr, nullptr, nullptr, n_win, 0, nullptr, nullptr, nullptr, 0, span_words, nullptr,
         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_win_out_d, status_d, region_counts_d);
     DIG_CHECK_LAUNCH();

@@ -24,8 +24,27 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace):
+    """dig_scan_opts for one scan call: the device scratch the lane-bank kernel needs (caller-owned, sized by
+    dig_scan_workspace_bytes) plus the A/B knobs.  Returns (struct, workspace tensor to keep alive)."""
+    import ctypes
+    if workspace is None and n_reg > 0:
+        nbytes = int(_lib.load().dig_scan_workspace_bytes(int(n_reg)))
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    opts = _lib.ScanOpts(workspace.data_ptr() if workspace is not None else None,
+                         workspace.numel() if workspace is not None else 0, int(variant), int(totals_limit_kb))
+    return opts, ctypes.byref(opts), workspace
+
+
+def scan_workspace(genome_or_device, n_reg):
+    """Scratch tensor for count_contexts / count_contexts_fused53 (reuse it across calls on one stream)."""
+    dev = getattr(genome_or_device, "device", genome_or_device)
+    return torch.empty(int(_lib.load().dig_scan_workspace_bytes(int(n_reg))), dtype=torch.uint8, device=dev)
+
+
 def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, strand=None,
-                   want_totals=False, out=None, totals=None, stream=None):
+                   want_totals=False, out=None, totals=None, stream=None, variant=_lib.SCAN_AUTO,
+                   totals_limit_kb=0, workspace=None):
     """K2/K4: per-region context histogram.
 
     genome: DeviceGenome.  reg_chrom: chromosome indices into the genome (int32).
@@ -41,16 +60,22 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
         out = torch.empty((n, K), dtype=torch.int32, device=dev)
     if want_totals and totals is None:
         totals = torch.zeros(K, dtype=torch.int64, device=dev)
+    lane_bank = n_up == 2 and n_down == 2 and st is None and variant == _lib.SCAN_AUTO
+    opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
+                                           workspace if lane_bank else None)
     with torch.cuda.device(dev):
         _lib.call("dig_count_contexts", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
                   genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),
-                  re.data_ptr(), _ptr(st), n, int(n_up), int(n_down), out.data_ptr(), _ptr(totals),
+                  re.data_ptr(), _ptr(st), n, int(n_up), int(n_down), out.data_ptr(), _ptr(totals), opts_ref,
                   _stream(dev, stream))
+    if lane_bank and n > 0:
+        _lib.launch_count += 1          # lane-bank kernel + the per-warp kernel over its redo list
     return out, totals
 
 
 def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=False, out5=None, out3=None,
-                           totals5=None, totals3=None, stream=None):
+                           totals5=None, totals3=None, stream=None, variant=_lib.SCAN_AUTO, totals_limit_kb=0,
+                           workspace=None):
     """K2 fused: pentanucleotide and trinucleotide tables (+ totals) of the same regions in one pass.
     Returns (counts5 [n,1024], counts3 [n,64], totals5, totals3)."""
     dev = genome.device
@@ -65,11 +90,16 @@ def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=Fa
     if want_totals and totals5 is None:
         totals5 = torch.zeros(1024, dtype=torch.int64, device=dev)
         totals3 = torch.zeros(64, dtype=torch.int64, device=dev)
+    lane_bank = variant == _lib.SCAN_AUTO
+    opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
+                                           workspace if lane_bank else None)
     with torch.cuda.device(dev):
         _lib.call("dig_count_contexts_fused53", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
                   genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),
-                  re.data_ptr(), n, out5.data_ptr(), out3.data_ptr(), _ptr(totals5), _ptr(totals3),
+                  re.data_ptr(), n, out5.data_ptr(), out3.data_ptr(), _ptr(totals5), _ptr(totals3), opts_ref,
                   _stream(dev, stream))
+    if lane_bank and n > 0:
+        _lib.launch_count += 1
     return out5, out3, totals5, totals3
 
 
@@ -254,8 +284,8 @@ def element_transfer(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, window,
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dig_element_transfer", ec.data_ptr(), es.data_ptr(), bp.data_ptr(), bs.data_ptr(), be.data_ptr(),
-                  n_elt, int(window), wmo.data_ptr(), wm.data_ptr(), wc.data_ptr(), yp.data_ptr(), sd.data_ptr(),
-                  yt.data_ptr(), fl.data_ptr(), n_win, n_cohort, dp.data_ptr(), _ptr(bc), _ptr(Le), n_col, max_span,
+                  n_elt, int(window), int(wmo.numel()) - 1, wmo.data_ptr(), wm.data_ptr(), wc.data_ptr(), yp.data_ptr(),
+                  sd.data_ptr(), yt.data_ptr(), fl.data_ptr(), n_win, n_cohort, dp.data_ptr(), _ptr(bc), _ptr(Le), n_col, max_span,
                   out["MU"].data_ptr(), out["SIGMA"].data_ptr(), out["R_OBS"].data_ptr(), out["FLAG"].data_ptr(),
                   out["R_SIZE"].data_ptr(), out["ELT_SIZE"].data_ptr(), out["P"].data_ptr(),
                   out["N_WIN"].data_ptr(), status.data_ptr(), _stream(dev, stream))
@@ -500,7 +530,7 @@ def site_test(site_chrom, site_start, site_sub, site_k, window, win_map_off, win
     with torch.cuda.device(dev):
         _lib.call("dig_window_denominators", wc.data_ptr(), dp.data_ptr(), n_win, den_p.data_ptr(), den_m.data_ptr(), sptr)
         _lib.call("dig_site_test", sc.data_ptr(), ss.data_ptr(), sb.data_ptr(), _ptr(st), sk.data_ptr(), n, int(window),
-                  wmo.data_ptr(), wm.data_ptr(), yp.data_ptr(), sd.data_ptr(), den_p.data_ptr(), den_m.data_ptr(),
+                  int(wmo.numel()) - 1, wmo.data_ptr(), wm.data_ptr(), yp.data_ptr(), sd.data_ptr(), den_p.data_ptr(), den_m.data_ptr(),
                   dp.data_ptr(), float(cj), _ptr(out["P"]), _ptr(out["EXP"]), out["PVAL"].data_ptr(),
                   status.data_ptr(), sptr)
         _check_status(status, "dig_site_test", status_sink)
@@ -618,7 +648,7 @@ def element_region_counts(elt_chrom, elt_strand, blk_ptr, blk_start, blk_end, wi
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dig_element_region_counts", ec.data_ptr(), es.data_ptr(), bp.data_ptr(), bs.data_ptr(), be.data_ptr(),
-                  n_elt, int(window), wmo.data_ptr(), wm.data_ptr(), wc.data_ptr(), wc.shape[0],
+                  n_elt, int(window), int(wmo.numel()) - 1, wmo.data_ptr(), wm.data_ptr(), wc.data_ptr(), wc.shape[0],
                   element_max_span(bp, bs, be, window), rc.data_ptr(), nw.data_ptr(), status.data_ptr(),
                   _stream(dev, stream))
         _check_status(status, "dig_element_region_counts", status_sink)

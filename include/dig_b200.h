@@ -72,12 +72,35 @@ int dig_pack_genome(const uint8_t *ascii_d, int64_t n_bases, uint32_t *packed2_d
  *                genome-wide totals of DigPreprocess.py:59 fused into the scan
  * Supported: n_up + n_down <= 5 (K <= 4096).  A region with 0 < START < n_up is counted
  * from n_up (the reference raises inside pysam); hosts should reject it beforehand.
+ *
+ * opts (nullable = all defaults) carries the per-call knobs; the library keeps no scan state between calls:
+ *   workspace_d / workspace_bytes  caller-owned device scratch of dig_scan_workspace_bytes(n_reg) bytes, 16-byte
+ *        aligned, contents irrelevant.  With it, pentanucleotide plus-strand scans (this call with n_up = n_down = 2
+ *        and no strands, and dig_count_contexts_fused53) run the lane-bank kernel (csrc/scan_lb.cu: one window per
+ *        lane, conflict-free shared-memory atomics, TMA staging); the scratch holds the device-side list of regions
+ *        that kernel hands to the per-warp kernel (regions longer than ~32 kb, batches whose 8-bit counters
+ *        overflowed).  Without it (or when n_bases is not a multiple of 128 / the arrays are not 16-byte aligned)
+ *        the per-warp kernels run; results are identical.
+ *   variant          DIG_SCAN_AUTO, or one specific kernel family for A/B measurements and tests
+ *   totals_limit_kb  0 = default; kilobases folded into 32-bit partial totals before they move to totals_d
  */
+#define DIG_SCAN_AUTO 0        /* lane-bank kernel when usable, else per-warp hexamer pairs, else per-base */
+#define DIG_SCAN_PER_BASE 1    /* one shared-memory atomic per base (scan.cu) */
+#define DIG_SCAN_HEX_PLAIN 2   /* per-warp hexamer pairs, LDS/STS flush */
+#define DIG_SCAN_HEX 3         /* per-warp hexamer pairs, ATOMS.EXCH.128 flush (scan_hex.cu) */
+typedef struct dig_scan_opts {
+    void *workspace_d;
+    int64_t workspace_bytes;
+    int32_t variant;
+    uint32_t totals_limit_kb;
+} dig_scan_opts;
+int64_t dig_scan_workspace_bytes(int64_t n_reg);
+
 int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
                        const int64_t *chrom_off_d, const int64_t *chrom_len_d,
                        const int32_t *reg_chrom_d, const int64_t *reg_start_d, const int64_t *reg_end_d,
                        const int8_t *reg_strand_d, int64_t n_reg, int n_up, int n_down,
-                       int32_t *counts_d, unsigned long long *totals_d, void *stream);
+                       int32_t *counts_d, unsigned long long *totals_d, const dig_scan_opts *opts, void *stream);
 
 /* Pentanucleotide (n_up = n_down = 2) AND trinucleotide (1, 1) tables of the same regions in ONE pass: what
  * two countGenomeContext runs of the reference produce (DigPreprocess.py:19-73 with --up/--down 2 and 1).  The
@@ -89,7 +112,8 @@ int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint32_t *nmask_
                                const int64_t *chrom_off_d, const int64_t *chrom_len_d,
                                const int32_t *reg_chrom_d, const int64_t *reg_start_d, const int64_t *reg_end_d,
                                int64_t n_reg, int32_t *counts5_d, int32_t *counts3_d,
-                               unsigned long long *totals5_d, unsigned long long *totals3_d, void *stream);
+                               unsigned long long *totals5_d, unsigned long long *totals3_d,
+                               const dig_scan_opts *opts, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * K3  mutation context lookup with REF check.
@@ -193,11 +217,14 @@ int dig_tabulate_genes(const int32_t *mut_gene_d, const int32_t *mut_sample_d, c
  *                sum(end - start + 1) over blocks otherwise); p_out [n_cohort, n_elt, n_col] double;
  *                n_win_out [n_elt] int32
  *   status_d     [1] int32: 0 ok, 2 missing window, 3 window span too large for shared memory
+ *   n_chrom      chromosomes the window map covers (win_map_off_d has n_chrom + 1 entries); an element whose
+ *                chromosome index is outside [0, n_chrom) overlaps no known window: status 2, like the reference's
+ *                KeyError (the same holds for dig_element_region_counts and dig_site_test)
  */
 int dig_element_transfer(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
                          const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt, int64_t window,
-                         const int64_t *win_map_off_d, const int32_t *win_map_d, const int32_t *win_counts_d,
-                         const double *y_pred_d, const double *std_d, const double *y_true_d,
+                         int n_chrom, const int64_t *win_map_off_d, const int32_t *win_map_d,
+                         const int32_t *win_counts_d, const double *y_pred_d, const double *std_d, const double *y_true_d,
                          const uint8_t *flag_d, int64_t n_win, int n_cohort, const double *d_pr_d,
                          const int32_t *blk_counts_d, const double *L_elt_d, int n_col, int max_span_windows,
                          double *mu_d, double *sigma_d, double *r_obs_d, uint8_t *flag_out_d, int64_t *r_size_d,
@@ -279,7 +306,7 @@ int dig_selection_coefficient(const double *obs_d, const double *exp_d, const do
 int dig_window_denominators(const int32_t *win_counts_d, const double *d_pr_d, int64_t n_win, double *denom_plus_d,
                             double *denom_minus_d, void *stream);
 int dig_site_test(const int32_t *site_chrom_d, const int64_t *site_start_d, const uint8_t *site_sub_d,
-                  const int8_t *site_strand_d, const double *site_k_d, int64_t n_site, int64_t window,
+                  const int8_t *site_strand_d, const double *site_k_d, int64_t n_site, int64_t window, int n_chrom,
                   const int64_t *win_map_off_d, const int32_t *win_map_d, const double *y_pred_d, const double *std_d,
                   const double *denom_plus_d, const double *denom_minus_d, const double *d_pr_d, double cj,
                   double *p_out_d, double *exp_out_d, double *pval_out_d, int32_t *status_d, void *stream);
@@ -382,8 +409,8 @@ int dig_overlap_fill(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, con
  */
 int dig_element_region_counts(const int32_t *elt_chrom_d, const int8_t *elt_strand_d, const int64_t *blk_ptr_d,
                               const int64_t *blk_start_d, const int64_t *blk_end_d, int64_t n_elt, int64_t window,
-                              const int64_t *win_map_off_d, const int32_t *win_map_d, const int32_t *win_counts_d,
-                              int64_t n_win, int max_span_windows, int64_t *region_counts_d, int32_t *n_win_out_d,
+                              int n_chrom, const int64_t *win_map_off_d, const int32_t *win_map_d,
+                              const int32_t *win_counts_d, int64_t n_win, int max_span_windows, int64_t *region_counts_d, int32_t *n_win_out_d,
                               int32_t *status_d, void *stream);
 
 /* dig_element_psum: P_SUM of nonc_model (genic_driver_tools.py:361-369) from the persisted per-element arrays:

@@ -141,15 +141,13 @@ def test_scan_large_windows_totals_overflow_guard(dev, oracle, u):
     wins = np.concatenate([tile_windows([0], lengths, 1_000_000)] * 40)      # 320 regions > one wave of warps
     seq = oracle.synth_genome(0, int(lengths[0]), 4, 0)
     want, _ = oracle.count_regions(seq, dg.chrom_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], u, u)
-    hook = ctypes.CDLL(_lib.LIB_PATH).dig_debug_set_totals_limit_kb
-    try:
-        for limit in (1 << 20, 1500):
-            hook(ctypes.c_uint(limit))
-            counts, totals = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], u, u, want_totals=True)
-            assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
-            assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0))
-    finally:
-        hook(ctypes.c_uint(1 << 20))
+    for limit in (0, 1500):                          # 0 = the library default
+        # AUTO sends the 1 Mb regions of a (2,2) scan through the lane-bank kernel's redo list (regions > 32 kb)
+        for variant in ((_lib.SCAN_AUTO, _lib.SCAN_HEX, _lib.SCAN_PER_BASE) if u == 2 else (_lib.SCAN_AUTO,)):
+            counts, totals = kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], u, u, want_totals=True,
+                                                    totals_limit_kb=limit, variant=variant)
+            assert np.array_equal(counts.cpu().numpy().astype(np.int64), want), (limit, variant)
+            assert np.array_equal(totals.cpu().numpy(), want.sum(axis=0)), (limit, variant)
 
 
 def test_fused_penta_tri_scan_matches_two_scans(dev, oracle, gold_dev_genome):
@@ -239,28 +237,25 @@ def test_hexamer_pair_scan_adversarial(dev, oracle):
         seq[o:o + len(s)] = s
     want5, _ = oracle.count_regions(seq, dg.chrom_off, dg.chrom_len, chrom, start, end, 2, 2)
     want3, _ = oracle.count_regions(seq, dg.chrom_off, dg.chrom_len, chrom, start, end, 1, 1)
-    lib = ctypes.CDLL(_lib.LIB_PATH)
-    try:
-        for variant in (0, 2):                       # ATOMS.EXCH.128 flush and plain LDS/STS flush
-            lib.dig_debug_set_scan_variant(variant)
-            for limit in (1 << 20, 64):              # 64 kb: the register totals spill to global many times
-                lib.dig_debug_set_totals_limit_kb(ctypes.c_uint(limit))
-                c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, chrom, start, end, want_totals=True)
-                bad = np.flatnonzero((c5.cpu().numpy() != want5).any(axis=1))
-                assert bad.size == 0, (variant, bad[:5], chrom[bad[:5]], start[bad[:5]], end[bad[:5]])
-                assert np.array_equal(c3.cpu().numpy(), want3)
-                assert np.array_equal(t5.cpu().numpy(), want5.sum(axis=0))
-                assert np.array_equal(t3.cpu().numpy(), want3.sum(axis=0))
-                p5, pt = kernels.count_contexts(dg, chrom, start, end, 2, 2, want_totals=True)
-                assert np.array_equal(p5.cpu().numpy(), want5) and np.array_equal(pt.cpu().numpy(), want5.sum(axis=0))
-                q5, _ = kernels.count_contexts(dg, chrom, start, end, 2, 2)
-                assert np.array_equal(q5.cpu().numpy(), want5)
-        lib.dig_debug_set_scan_variant(1)            # the per-base kernels stay available and agree
-        c5, c3, _, _ = kernels.count_contexts_fused53(dg, chrom, start, end)
-        assert np.array_equal(c5.cpu().numpy(), want5) and np.array_equal(c3.cpu().numpy(), want3)
-    finally:
-        lib.dig_debug_set_scan_variant(0)
-        lib.dig_debug_set_totals_limit_kb(ctypes.c_uint(1 << 20))
+    # lane-bank kernel (+ its redo list: the homopolymer overflows 8-bit fields, long regions exceed its chunk
+    # limit), per-warp hexamer kernel with ATOMS.EXCH.128 flush and with plain LDS/STS flush
+    for variant in (_lib.SCAN_AUTO, _lib.SCAN_HEX, _lib.SCAN_HEX_PLAIN):
+        for limit in (0, 64):                        # 64 kb: the register totals spill to global many times
+            kw = dict(variant=variant, totals_limit_kb=limit)
+            c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, chrom, start, end, want_totals=True, **kw)
+            bad = np.flatnonzero((c5.cpu().numpy() != want5).any(axis=1))
+            assert bad.size == 0, (variant, bad[:5], chrom[bad[:5]], start[bad[:5]], end[bad[:5]])
+            bad = np.flatnonzero((c3.cpu().numpy() != want3).any(axis=1))
+            assert bad.size == 0, (variant, bad[:5], chrom[bad[:5]], start[bad[:5]], end[bad[:5]])
+            assert np.array_equal(t5.cpu().numpy(), want5.sum(axis=0)), variant
+            assert np.array_equal(t3.cpu().numpy(), want3.sum(axis=0)), variant
+            p5, pt = kernels.count_contexts(dg, chrom, start, end, 2, 2, want_totals=True, **kw)
+            assert np.array_equal(p5.cpu().numpy(), want5) and np.array_equal(pt.cpu().numpy(), want5.sum(axis=0))
+            q5, _ = kernels.count_contexts(dg, chrom, start, end, 2, 2, **kw)
+            assert np.array_equal(q5.cpu().numpy(), want5)
+    # the per-base kernels stay available and agree
+    c5, c3, _, _ = kernels.count_contexts_fused53(dg, chrom, start, end, variant=_lib.SCAN_PER_BASE)
+    assert np.array_equal(c5.cpu().numpy(), want5) and np.array_equal(c3.cpu().numpy(), want3)
 
 
 def test_empty_inputs_through_the_c_abi(dev):

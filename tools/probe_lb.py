@@ -1,0 +1,62 @@
+"""Developer probe: lane-bank scan (scan_lb.cu) vs the per-warp hexamer kernel (bit-exactness + timing at hg19 scale).
+usage: probe_lb.py [total_bases] [--quick]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from digdriver_b200 import genome as G, kernels, _lib
+
+
+def timeit(fn, n=7, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), float(np.median(ts))
+
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+total = int(float(args[0])) if args else 3_100_000_000
+lengths = G.hg19_like_lengths(total)
+names = ["chr%d" % (i + 1) for i in range(22)]
+dg = G.DeviceGenome.synthetic(names, lengths, seed=1)
+W = 10_000
+wins = G.tile_windows(np.arange(22), lengths, W)
+rc = torch.from_numpy(wins[:, 0].astype(np.int32)).cuda(); rs = torch.from_numpy(wins[:, 1]).cuda(); re = torch.from_numpy(wins[:, 2]).cuda()
+nb = float((wins[:, 2] - wins[:, 1]).sum())
+ws = kernels.scan_workspace(dg, len(wins))
+res = {}
+for variant, name in ((_lib.SCAN_HEX, "per-warp hexamer"), (_lib.SCAN_AUTO, "lane-bank")):
+    out5 = torch.empty((len(wins), 1024), dtype=torch.int32, device="cuda")
+    out3 = torch.empty((len(wins), 64), dtype=torch.int32, device="cuda")
+    t5 = torch.zeros(1024, dtype=torch.int64, device="cuda"); t3 = torch.zeros(64, dtype=torch.int64, device="cuda")
+    fn = lambda: kernels.count_contexts_fused53(dg, rc, rs, re, out5=out5, out3=out3, totals5=t5, totals3=t3,
+                                                variant=variant, workspace=ws)
+    ws.zero_(); fn(); torch.cuda.synchronize()
+    res[variant] = (out5.clone(), out3.clone(), t5.clone(), t3.clone())
+    if variant == _lib.SCAN_AUTO:
+        print("  redo list length: %d of %d windows" % (int(ws[:4].view(torch.int32).item()), len(wins)), flush=True)
+    best, med = timeit(fn)
+    bpb = 0.375 + 4.0 * (1024 + 64) / W
+    print("fused53 %-18s best %.3f ms med %.3f ms -> %.1f GB/s algorithmic, frac %.3f"
+          % (name, best, med, nb * bpb / best / 1e6, nb * bpb / best / 1e6 / 6556.5), flush=True)
+    o = torch.empty((len(wins), 1024), dtype=torch.int32, device="cuda")
+    tt = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    fn2 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, totals=tt, variant=variant, workspace=ws)
+    best, med = timeit(fn2)
+    bpb = 0.375 + 4.0 * 1024 / W
+    print("penta   %-18s best %.3f ms med %.3f ms -> frac %.3f" % (name, best, med, nb * bpb / best / 1e6 / 6556.5), flush=True)
+    fn3 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, variant=variant, workspace=ws)
+    best, med = timeit(fn3)
+    print("penta no totals %-10s best %.3f ms" % (name, best), flush=True)
+for k, nm in enumerate(("counts5", "counts3", "totals5", "totals3")):
+    a, b = res[_lib.SCAN_AUTO][k], res[_lib.SCAN_HEX][k]
+    eq = bool(torch.equal(a, b))
+    print("  %s equal: %s" % (nm, eq), flush=True)
+    if not eq and a.dim() == 2:
+        badrows = torch.nonzero((a != b).any(dim=1)).flatten()
+        print("    %d bad rows, first %s" % (badrows.numel(), badrows[:10].tolist()), flush=True)
+        r0 = int(badrows[0]); cols = torch.nonzero(a[r0] != b[r0]).flatten()[:8]
+        print("    row %d cols %s got %s want %s" % (r0, cols.tolist(), a[r0][cols].tolist(), b[r0][cols].tolist()), flush=True)

@@ -72,7 +72,7 @@ nw = torch.empty(E, dtype=torch.int32, device=dev)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 wo, wm = t(woff, torch.int64), t(wmap, torch.int32)
 us_rc = timed(lambda: _lib.call("dig_element_region_counts", args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(),
-                                args[3].data_ptr(), args[4].data_ptr(), E, W, wo.data_ptr(), wm.data_ptr(), wc.data_ptr(),
+                                args[3].data_ptr(), args[4].data_ptr(), E, W, int(wo.numel()) - 1, wo.data_ptr(), wm.data_ptr(), wc.data_ptr(),
                                 wc.shape[0], span, rc.data_ptr(), nw.data_ptr(), status.data_ptr(), st))
 L = t(rng.integers(0, 30, (E, 192)), torch.float64)
 R = torch.repeat_interleave(rc, 3, dim=1).contiguous()
