@@ -42,7 +42,8 @@ using namespace digscan;
 namespace {
 
 constexpr int LB_CW = 16;                          // consumer warps
-constexpr int LB_THREADS = (LB_CW + 1) * 32;       // + the producer warp
+constexpr int LB_WW = 4;                           // writer warps, one per slice buffer
+constexpr int LB_THREADS = (LB_CW + LB_WW + 1) * 32;   // + the producer warp
 constexpr int LB_CONS = LB_CW * 32;
 constexpr int LB_SPAN = 128;                       // bases per consumer thread per chunk
 constexpr int LB_CHUNK = LB_CW * LB_SPAN;          // 2048
@@ -56,19 +57,20 @@ constexpr uint32_t OFF_TAB = 0u;                                   // [1024 rows
 constexpr uint32_t OFF_STG = 131072u;
 constexpr uint32_t OUT_BYTES = 32u * 64u * 4u;                     // one 64-bin slice of 32 windows
 constexpr uint32_t OFF_OUT = OFF_STG + 2u * LB_STAGE_BYTES;
-constexpr int LB_NOUT = 4;                                         // slice buffers in flight
+constexpr int LB_NOUT = LB_WW;                                     // slice buffers in flight
 constexpr uint32_t OFF_TRI = OFF_OUT + LB_NOUT * OUT_BYTES;        // [64 bins][33] ints (padded: transposable)
 constexpr uint32_t TRI_BYTES = 64u * 33u * 4u;
 constexpr uint32_t OFF_EXC = OFF_TRI + TRI_BYTES;                  // two lists: [0] = count, [4..] entries
 constexpr uint32_t EXC_BYTES = 2048u;
 constexpr uint32_t OFF_CNT = OFF_EXC + 2u * EXC_BYTES;             // pairs counted per window, two parities
 constexpr uint32_t OFF_CHK = OFF_CNT + 256u;                       // sum of table bytes per window
-constexpr uint32_t OFF_BAR = OFF_CHK + 128u;
+constexpr uint32_t OFF_FLG = OFF_CHK + 128u;                       // batch verdict, writer warp 0 -> the others
+constexpr uint32_t OFF_BAR = OFF_FLG + 16u;
 constexpr uint32_t LB_SMEM = OFF_BAR + 128u;
 static_assert(OFF_BAR % 16u == 0u, "barrier block alignment");
 static_assert(LB_SMEM <= 232448u, "shared memory budget");
 
-enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_OUTFULL = 4, BAR_OUTEMPTY = 8, BAR_DONE = 12 };
+enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_OUTFULL = 4, BAR_OUTEMPTY = 8, BAR_DONE = 12, BAR_CLEAN = 13 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt)
@@ -117,6 +119,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LB_CONS) : "memory"); }
+__device__ __forceinline__ void writer_sync() { asm volatile("bar.sync 2, %0;" ::"n"(LB_WW * 32) : "memory"); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t a)
 {
@@ -297,59 +300,44 @@ struct LbArgs {
     uint32_t zero;            // = 0
 };
 
-// ---- genome staging: issued by the consumer warps, two lanes (= two windows) per warp ---------------------
+// ---- producer warp: lane l brings window l's chunks into the stages ------------------------------------------
 // The chunk sequence of a CTA is the concatenation of the chunks of its batches; chunk number ci lands in stage
-// ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by all sixteen warps.
-struct LbIssuer {
-    int64_t b;        // batch of the next chunk to issue
-    int k;            // chunk inside that batch
-    int nch;          // chunks of batch b (warp maximum)
-    uint32_t ci;      // chunks issued so far
-    LbGeom g;         // this lane's window of batch b
-};
-
+// ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by all sixteen consumer warps.
 template <bool TRI>
-__device__ __forceinline__ void lb_issue_next(LbIssuer &I, const LbArgs &A, int64_t n_batches, uint32_t sbase, int warp,
-                                              int lane)
+__device__ __forceinline__ void lb_producer(const LbArgs &A, uint32_t sbase, int lane)
 {
-    while (I.b < n_batches && I.k >= I.nch) {            // next batch that has something to scan
-        I.b += gridDim.x;
-        I.k = 0;
-        I.nch = 0;
-        if (I.b < n_batches) {
-            I.g = lb_geom<TRI>(I.b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
-            I.nch = warp_max(I.g.nch);
-        }
-    }
-    if (I.b >= n_batches) return;
     const uint32_t bar = sbase + OFF_BAR;
-    const uint32_t stage = I.ci & 1u;
-    mbar_wait(bar + 8u * (BAR_EMPTY + stage), ((I.ci >> 1) & 1u) ^ 1u);
-    if ((lane >> 1) == warp) {
-        const uint32_t full = bar + 8u * (BAR_FULL + stage);
-        if (I.k < I.g.nch) {
-            const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
-            const int64_t G0 = I.g.O + (int64_t)I.k * LB_CHUNK;              // first staged base: multiple of 128, >= -128
-            int64_t dsrc = G0 >> 2, msrc = G0 >> 3;
-            uint32_t ddst = stg + (uint32_t)lane * LB_DSTRIDE, mdst = stg + 32u * LB_DSTRIDE + (uint32_t)lane * LB_MSTRIDE;
-            int64_t dbytes = LB_DSTRIDE, mbytes = LB_MSTRIDE;
-            if (G0 < 0) {                                                    // no base before the genome is ever needed
-                dsrc = 0; ddst += 32u; dbytes -= 32;
-                msrc = 0; mdst += 16u; mbytes -= 16;
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    uint32_t ci = 0u;
+    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x) {
+        const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const int nch = warp_max(g.nch);
+        for (int k = 0; k < nch; ++k, ++ci) {
+            const uint32_t stage = ci & 1u;
+            mbar_wait(bar + 8u * (BAR_EMPTY + stage), ((ci >> 1) & 1u) ^ 1u);
+            const uint32_t full = bar + 8u * (BAR_FULL + stage);
+            if (k < g.nch) {
+                const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
+                const int64_t G0 = g.O + (int64_t)k * LB_CHUNK;              // first staged base: multiple of 128, >= -128
+                int64_t dsrc = G0 >> 2, msrc = G0 >> 3;
+                uint32_t ddst = stg + (uint32_t)lane * LB_DSTRIDE, mdst = stg + 32u * LB_DSTRIDE + (uint32_t)lane * LB_MSTRIDE;
+                int64_t dbytes = LB_DSTRIDE, mbytes = LB_MSTRIDE;
+                if (G0 < 0) {                                                // no base before the genome is ever needed
+                    dsrc = 0; ddst += 32u; dbytes -= 32;
+                    msrc = 0; mdst += 16u; mbytes -= 16;
+                }
+                const int64_t davail = (A.n_bases >> 2) - dsrc, mavail = (A.n_bases >> 3) - msrc;
+                if (dbytes > davail) dbytes = davail;
+                if (mbytes > mavail) mbytes = mavail;
+                mbar_arrive_tx(full, (uint32_t)(dbytes + mbytes));
+                bulk_g2s(ddst, reinterpret_cast<const unsigned char *>(A.p2) + dsrc, (uint32_t)dbytes, full);
+                bulk_g2s(mdst, reinterpret_cast<const unsigned char *>(A.nmask) + msrc, (uint32_t)mbytes, full);
+            } else {
+                mbar_arrive(full);
             }
-            const int64_t davail = (A.n_bases >> 2) - dsrc, mavail = (A.n_bases >> 3) - msrc;
-            if (dbytes > davail) dbytes = davail;
-            if (mbytes > mavail) mbytes = mavail;
-            mbar_arrive_tx(full, (uint32_t)(dbytes + mbytes));
-            bulk_g2s(ddst, reinterpret_cast<const unsigned char *>(A.p2) + dsrc, (uint32_t)dbytes, full);
-            bulk_g2s(mdst, reinterpret_cast<const unsigned char *>(A.nmask) + msrc, (uint32_t)mbytes, full);
-        } else {
-            mbar_arrive(full);
+            __syncwarp();
         }
     }
-    __syncwarp();
-    ++I.k;
-    ++I.ci;
 }
 
 // ---- consumer warps ----------------------------------------------------------------------------------
@@ -359,20 +347,12 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t tabl = sbase + OFF_TAB + (uint32_t)lane * 4u;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
-    const int ctid = warp * 32 + lane;
-    uint32_t cit = 0u, sit = 0u, bi = 0u;
+    uint32_t cit = 0u, bi = 0u;
     // one VECTOR-register copy of the PRMT constant: made formally lane-dependent (A.zero = 0), otherwise ptxas keeps it
     // in a uniform register and copies it into a fresh vector register for every PRMT
     const uint32_t top_r = A.top | (tabl & A.zero);
-
-    LbIssuer I;
-    I.b = blockIdx.x;
-    I.k = 0;
-    I.ci = 0u;
-    I.g = lb_geom<TRI>(I.b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
-    I.nch = warp_max(I.g.nch);
-    lb_issue_next<TRI>(I, A, n_batches, sbase, warp, lane);
-    lb_issue_next<TRI>(I, A, n_batches, sbase, warp, lane);
+    const int sl = warp & 3, wq = warp >> 2;               // write-out: slices sl, sl+4, ..; bin groups 4 wq .. 4 wq + 3
+    const uint32_t outb = sbase + OFF_OUT + (uint32_t)sl * OUT_BYTES + (uint32_t)lane * 256u;
 
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
         const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
@@ -380,6 +360,7 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
         const uint32_t par = bi & 1u;
         const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
         uint32_t npairs = 0u;
+        bool clean = bi == 0u;                             // the kernel prologue zeroed the tables of the first batch
         for (int k = 0; k < nch; ++k, ++cit) {
             const uint32_t stage = cit & 1u;
             mbar_wait(bar + 8u * (BAR_FULL + stage), (cit >> 1) & 1u);
@@ -397,6 +378,10 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + 8u * (BAR_EMPTY + stage));      // the stage is in registers now
+            if (!clean) {                                                    // the writer warps have re-zeroed the tables
+                mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);
+                clean = true;
+            }
             const int base = k * LB_CHUNK + warp * LB_SPAN;                  // local base 0 relative to the origin
             const int lo5 = g.lo5 - base, hi5 = g.hi5 - base;                // centre c (local base index) valid: lo5 <= c < hi5
             const uint32_t any_n = M[0] | M[1] | M[2] | M[3] | (M[4] & 0xF0000000u);
@@ -437,75 +422,103 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 }
                 if ((PV[0] | PV[1] | PV[2] | PV[3]) != 0u) lb_pairs<true>(D, tabl, A.k32, top_r, PV);
             }
-            __syncwarp();
-            lb_issue_next<TRI>(I, A, n_batches, sbase, warp, lane);          // chunk cit + 2
         }
+        if (!clean) mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);         // a batch without chunks still reads the tables
         if (npairs) red_add(sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, npairs);
         cons_sync();                                                         // every hexamer of the batch is in the tables
-        mbar_wait(bar + 8u * BAR_DONE, (bi & 1u) ^ 1u);                      // the writer warp finished the previous batch
+        mbar_wait(bar + 8u * BAR_DONE, (bi & 1u) ^ 1u);                      // writer warp 0 finished the previous batch
 
-        uint32_t chk = 0u;
+        // ---- write-out: this warp fills bin groups 4 wq .. 4 wq + 3 of slices sl, sl + 4, sl + 8, sl + 12
+        uint32_t chk = 0u, tri_acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
-        for (int sg = 0; sg < 16; ++sg, ++sit) {
-            const uint32_t buf = sit & (LB_NOUT - 1);
-            mbar_wait(bar + 8u * (BAR_OUTEMPTY + buf), ((sit / LB_NOUT) & 1u) ^ 1u);
-            const int jl = (warp + lane) & 15;
-            const int j = 16 * sg + jl;                                      // bins 4j .. 4j+3 of window `lane`
-            const uint32_t k0 = lds32(tabl + (uint32_t)(4 * j + 0) * 128u), k1 = lds32(tabl + (uint32_t)(4 * j + 1) * 128u);
-            const uint32_t k2 = lds32(tabl + (uint32_t)(4 * j + 2) * 128u), k3 = lds32(tabl + (uint32_t)(4 * j + 3) * 128u);
-            const uint32_t w0 = lds32(tabl + (uint32_t)(j)*128u), w1 = lds32(tabl + (uint32_t)(256 + j) * 128u);
-            const uint32_t w2 = lds32(tabl + (uint32_t)(512 + j) * 128u), w3 = lds32(tabl + (uint32_t)(768 + j) * 128u);
-            // hexamers STARTING with pentanucleotide m: all four fields of row m
-            const uint32_t a0 = __dp4a(k0, 0x01010101u, 0u), a1 = __dp4a(k1, 0x01010101u, 0u);
-            const uint32_t a2 = __dp4a(k2, 0x01010101u, 0u), a3 = __dp4a(k3, 0x01010101u, 0u);
-            chk += (a0 + a1) + (a2 + a3);
-            // hexamers ENDING with m = (bcde f): byte 3 - f of rows (a bcde), summed over a (<= 4 x 255 per half)
-            const uint32_t ev = (w0 & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + (w2 & 0x00FF00FFu) + (w3 & 0x00FF00FFu);
-            const uint32_t od = ((w0 >> 8) & 0x00FF00FFu) + ((w1 >> 8) & 0x00FF00FFu) + ((w2 >> 8) & 0x00FF00FFu) +
-                                ((w3 >> 8) & 0x00FF00FFu);
-            const uint32_t o0 = a0 + (od >> 16), o1 = a1 + (ev >> 16), o2 = a2 + (od & 0xFFFFu), o3 = a3 + (ev & 0xFFFFu);
-            sts128(sbase + OFF_OUT + buf * OUT_BYTES + (uint32_t)lane * 256u + (uint32_t)jl * 16u, o0, o1, o2, o3);
-            if constexpr (TRI)
-                red_add(sbase + OFF_TRI + ((uint32_t)(j & 63) * 33u + (uint32_t)lane) * 4u, (o0 + o1) + (o2 + o3));
-            if (sg == 15 && chk) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, chk);
+        for (int i = 0; i < 4; ++i) {
+            const int sg = sl + 4 * i;
+            mbar_wait(bar + 8u * (BAR_OUTEMPTY + sl), (((bi << 2) + (uint32_t)i) & 1u) ^ 1u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int jl = (4 * wq + t + lane) & 15;                     // rotated by lane: conflict-free 128-bit stores
+                const int j = 16 * sg + jl;                                  // bins 4j .. 4j+3 of window `lane`
+                const uint32_t k0 = lds32(tabl + (uint32_t)(4 * j + 0) * 128u), k1 = lds32(tabl + (uint32_t)(4 * j + 1) * 128u);
+                const uint32_t k2 = lds32(tabl + (uint32_t)(4 * j + 2) * 128u), k3 = lds32(tabl + (uint32_t)(4 * j + 3) * 128u);
+                const uint32_t w0 = lds32(tabl + (uint32_t)(j)*128u), w1 = lds32(tabl + (uint32_t)(256 + j) * 128u);
+                const uint32_t w2 = lds32(tabl + (uint32_t)(512 + j) * 128u), w3 = lds32(tabl + (uint32_t)(768 + j) * 128u);
+                // hexamers STARTING with pentanucleotide m: all four fields of row m
+                const uint32_t a0 = __dp4a(k0, 0x01010101u, 0u), a1 = __dp4a(k1, 0x01010101u, 0u);
+                const uint32_t a2 = __dp4a(k2, 0x01010101u, 0u), a3 = __dp4a(k3, 0x01010101u, 0u);
+                chk += (a0 + a1) + (a2 + a3);
+                // hexamers ENDING with m = (bcde f): byte 3 - f of the rows (a bcde), summed over a
+                const uint32_t o0 = __dp4a(w3, 0x01000000u, __dp4a(w2, 0x01000000u, __dp4a(w1, 0x01000000u, __dp4a(w0, 0x01000000u, a0))));
+                const uint32_t o1 = __dp4a(w3, 0x00010000u, __dp4a(w2, 0x00010000u, __dp4a(w1, 0x00010000u, __dp4a(w0, 0x00010000u, a1))));
+                const uint32_t o2 = __dp4a(w3, 0x00000100u, __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00000100u, a2))));
+                const uint32_t o3 = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x00000001u, __dp4a(w1, 0x00000001u, __dp4a(w0, 0x00000001u, a3))));
+                sts128(outb + (uint32_t)jl * 16u, o0, o1, o2, o3);
+                tri_acc[t] += (o0 + o1) + (o2 + o3);                         // trinucleotide bin 16 sl + jl, whatever i is
+            }
+            if (i == 3) {
+                if constexpr (TRI) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t bin = (uint32_t)(16 * sl + ((4 * wq + t + lane) & 15));
+                        red_add(sbase + OFF_TRI + (bin * 33u + (uint32_t)lane) * 4u, tri_acc[t]);
+                    }
+                }
+                if (chk) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, chk);
+            }
             fence_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar + 8u * (BAR_OUTFULL + buf));
+            if (lane == 0) mbar_arrive(bar + 8u * (BAR_OUTFULL + sl));
         }
-        cons_sync();                                                         // all table reads done
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sts128(sbase + OFF_TAB + (uint32_t)(ctid + LB_CONS * i) * 16u, 0u, 0u, 0u, 0u);
-        cons_sync();
     }
 }
 
-// ---- writer warp: corrections, genome-wide totals, TMA stores, per-batch bookkeeping ------------------------
+// ---- writer warps: corrections, genome-wide totals, TMA stores, per-batch bookkeeping ----------------------
+// Writer warp q owns slice buffer q and the slices sg = q, q + 4, q + 8, q + 12 of every batch: it waits until the
+// sixteen consumer warps have filled the buffer, applies the batch's single-centre corrections that fall into the
+// slice, adds the slice's column sums to its share of the genome-wide totals, ships the [32][64] tile with one TMA
+// tensor store and hands the buffer back as soon as the store has read it.  Warp 0 also closes the batch:
+// trinucleotide rows, the exact overflow check, the redo list.
 template <bool TRI, bool TOT>
-__device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tmap, uint32_t sbase, int lane)
+__device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tmap, uint32_t sbase, int q, int lane)
 {
     const uint32_t bar = sbase + OFF_BAR;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
-    uint32_t sit = 0u, bi = 0u;
-    unsigned int tot5[TOT ? 32 : 1], tot3[2] = {0u, 0u};
+    uint32_t use = 0u, bi = 0u;                            // use: how often this warp's buffer has been filled
+    unsigned int tot5[TOT ? 8 : 1], tot3[2] = {0u, 0u};
 #pragma unroll
-    for (int i = 0; i < (TOT ? 32 : 1); ++i) tot5[i] = 0u;
+    for (int i = 0; i < (TOT ? 8 : 1); ++i) tot5[i] = 0u;
     unsigned int acc_kb = 0u;
+    const uint32_t out = sbase + OFF_OUT + (uint32_t)q * OUT_BYTES;
+
+    auto flush_totals = [&]() {
+        if constexpr (TOT) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // register i: slice 4 (i >> 1) + q, bins 64 slice + 2 lane + (i & 1)
+                if (tot5[i]) atomicAdd(A.totals5 + 64 * (4 * (i >> 1) + q) + 2 * lane + (i & 1), (unsigned long long)tot5[i]);
+                tot5[i] = 0u;
+            }
+            if constexpr (TRI) {
+                if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
+                if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
+                tot3[0] = tot3[1] = 0u;
+            }
+        }
+    };
 
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
         const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const uint32_t par = bi & 1u;
         const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
         const int64_t r = b * 32 + lane;
-        unsigned int tmp5[TOT ? 32 : 1], tmp3[2] = {0u, 0u};
+        unsigned int tmp5[TOT ? 8 : 1], tmp3[2] = {0u, 0u};
 #pragma unroll
-        for (int i = 0; i < (TOT ? 32 : 1); ++i) tmp5[i] = 0u;
+        for (int i = 0; i < (TOT ? 8 : 1); ++i) tmp5[i] = 0u;
         uint32_t n_exc_raw = 0u;
 #pragma unroll
-        for (int sg = 0; sg < 16; ++sg, ++sit) {
-            const uint32_t buf = sit & (LB_NOUT - 1);
-            mbar_wait(bar + 8u * (BAR_OUTFULL + buf), (sit / LB_NOUT) & 1u);
-            const uint32_t out = sbase + OFF_OUT + buf * OUT_BYTES;
-            if (sg == 0) n_exc_raw = lds32(exc);                             // final: every consumer is past the scan
+        for (int s4 = 0; s4 < 4; ++s4, ++use) {
+            const int sg = 4 * s4 + q;
+            mbar_wait(bar + 8u * (BAR_OUTFULL + q), use & 1u);
+            if (s4 == 0) n_exc_raw = lds32(exc);                             // final: every consumer is past the scan
             const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
             for (uint32_t e = lane; e < n_exc; e += 32u) {
                 const uint32_t ent = lds32(exc + 16u + 4u * e);
@@ -517,8 +530,8 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
 #pragma unroll 8
                 for (int l2 = 0; l2 < 32; ++l2) {
                     const uint2 v = lds64(out + (uint32_t)l2 * 256u + (uint32_t)lane * 8u);
-                    tmp5[2 * sg] += v.x;
-                    tmp5[2 * sg + 1] += v.y;
+                    tmp5[2 * s4] += v.x;
+                    tmp5[2 * s4 + 1] += v.y;
                 }
             }
             fence_async();
@@ -526,45 +539,61 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
             if (lane == 0) {
                 tensor_s2g(tmap, out, 64 * sg, (int)(b * 32));
                 bulk_commit();
-                bulk_wait_read<LB_NOUT - 1>();                               // the store issued LB_NOUT - 1 slices ago has left its buffer
-                if (sit >= (uint32_t)(LB_NOUT - 1)) mbar_arrive(bar + 8u * (BAR_OUTEMPTY + ((sit - (LB_NOUT - 1)) & (LB_NOUT - 1))));
+                bulk_wait_read<0>();                                         // the tile has left shared memory
+                mbar_arrive(bar + 8u * (BAR_OUTEMPTY + q));
             }
             __syncwarp();
         }
-        const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
-        if constexpr (TRI) {
-            const uint32_t tri = sbase + OFF_TRI;
-            for (uint32_t e = lane; e < n_exc; e += 32u) {
-                const uint32_t ent = lds32(exc + 16u + 4u * e);
-                const uint32_t bin = (ent & 0x8000u) ? (ent & 63u) : ((ent >> 2) & 63u);
-                red_add(tri + (bin * 33u + (ent >> 16)) * 4u, 1u);
-            }
-            __syncwarp();
-            for (int l2 = 0; l2 < 32; ++l2) {
-                const int64_t r2 = b * 32 + l2;
-                const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
-                const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
-                if (r2 < A.n_reg) {
-                    __stcs(A.counts3 + r2 * 64 + lane, (int)v0);
-                    __stcs(A.counts3 + r2 * 64 + 32 + lane, (int)v1);
+        writer_sync();                                                       // all sixteen slices are out, all table reads done
+        // the consumers are already loading the next batch: hand them clean tables (a quarter per writer warp)
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i)
+            sts128(sbase + OFF_TAB + (uint32_t)q * 32768u + (uint32_t)(lane + 32 * i) * 16u, 0u, 0u, 0u, 0u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8u * BAR_CLEAN);
+        if (q == 0) {
+            const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
+            if constexpr (TRI) {
+                const uint32_t tri = sbase + OFF_TRI;
+                for (uint32_t e = lane; e < n_exc; e += 32u) {
+                    const uint32_t ent = lds32(exc + 16u + 4u * e);
+                    const uint32_t bin = (ent & 0x8000u) ? (ent & 63u) : ((ent >> 2) & 63u);
+                    red_add(tri + (bin * 33u + (ent >> 16)) * 4u, 1u);
                 }
-                tmp3[0] += v0;
-                tmp3[1] += v1;
+                __syncwarp();
+#pragma unroll 4
+                for (int l2 = 0; l2 < 32; ++l2) {
+                    const int64_t r2 = b * 32 + l2;
+                    const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
+                    const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
+                    if (r2 < A.n_reg) {
+                        __stcs(A.counts3 + r2 * 64 + lane, (int)v0);
+                        __stcs(A.counts3 + r2 * 64 + 32 + lane, (int)v1);
+                    }
+                    tmp3[0] += v0;
+                    tmp3[1] += v1;
+                }
+                __syncwarp();
+#pragma unroll 6
+                for (int i = 0; i < 66; ++i) sts32(tri + (uint32_t)(lane + 32 * i) * 4u, 0u);
             }
-            __syncwarp();
-            for (int i = 0; i < 66; ++i) sts32(tri + (uint32_t)(lane + 32 * i) * 4u, 0u);
+            // exact overflow check: sum of all table bytes == hexamers counted
+            const uint32_t cnt_a = sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, chk_a = sbase + OFF_CHK + (uint32_t)lane * 4u;
+            const bool bad = lds32(cnt_a) != lds32(chk_a);
+            const bool fail = __any_sync(0xffffffffu, bad) || n_exc_raw > (uint32_t)LB_EXC_CAP;
+            sts32(cnt_a, 0u);
+            sts32(chk_a, 0u);
+            if (lane == 0) {
+                sts32(exc, 0u);
+                sts32(sbase + OFF_FLG, fail ? 1u : 0u);
+            }
+            if (g.too_long || (fail && g.active)) {
+                const int pos = atomicAdd(A.fb_count, 1);
+                A.fb_list[pos] = (int32_t)r;
+            }
         }
-        // exact overflow check: sum of all table bytes == hexamers counted
-        const uint32_t cnt_a = sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, chk_a = sbase + OFF_CHK + (uint32_t)lane * 4u;
-        const bool bad = lds32(cnt_a) != lds32(chk_a);
-        const bool fail = __any_sync(0xffffffffu, bad) || n_exc_raw > (uint32_t)LB_EXC_CAP;
-        sts32(cnt_a, 0u);
-        sts32(chk_a, 0u);
-        if (lane == 0) sts32(exc, 0u);
-        if (g.too_long || (fail && g.active)) {
-            const int pos = atomicAdd(A.fb_count, 1);
-            A.fb_list[pos] = (int32_t)r;
-        }
+        writer_sync();                                                       // verdict visible to all writer warps
+        const bool fail = lds32(sbase + OFF_FLG) != 0u;
         if constexpr (TOT) {
             if (!fail) {
                 // 32-bit register totals: move them out before 2^31 bases have been folded in
@@ -572,37 +601,20 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) kb += __shfl_xor_sync(0xffffffffu, kb, o);
                 if (acc_kb + kb > A.tot_limit_kb || acc_kb + kb < acc_kb) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (tot5[i]) atomicAdd(A.totals5 + 64 * (i >> 1) + 2 * lane + (i & 1), (unsigned long long)tot5[i]);
-                        tot5[i] = 0u;
-                    }
-                    if constexpr (TRI) {
-                        if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
-                        if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
-                        tot3[0] = tot3[1] = 0u;
-                    }
+                    flush_totals();
                     acc_kb = 0u;
                 }
                 acc_kb += kb;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tot5[i] += tmp5[i];
+                for (int i = 0; i < 8; ++i) tot5[i] += tmp5[i];
                 tot3[0] += tmp3[0];
                 tot3[1] += tmp3[1];
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar + 8u * BAR_DONE);
+        writer_sync();                                                       // verdict read before warp 0 may rewrite it
+        if (q == 0 && lane == 0) mbar_arrive(bar + 8u * BAR_DONE);
     }
-    if constexpr (TOT) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (tot5[i]) atomicAdd(A.totals5 + 64 * (i >> 1) + 2 * lane + (i & 1), (unsigned long long)tot5[i]);
-        if constexpr (TRI) {
-            if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
-            if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
-        }
-    }
+    flush_totals();
     bulk_wait_all();
 }
 
@@ -624,15 +636,17 @@ __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, 
         mbar_init(bar + 8u * (BAR_EMPTY + 1), LB_CW);
 #pragma unroll
         for (int i = 0; i < LB_NOUT; ++i) {
-            mbar_init(bar + 8u * (BAR_OUTFULL + i), LB_CW);
+            mbar_init(bar + 8u * (BAR_OUTFULL + i), LB_CW / LB_NOUT);      // the four consumer warps that fill slice buffer i
             mbar_init(bar + 8u * (BAR_OUTEMPTY + i), 1u);
         }
         mbar_init(bar + 8u * BAR_DONE, 1u);
+        mbar_init(bar + 8u * BAR_CLEAN, LB_WW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async();
     }
     __syncthreads();
-    if (warp == LB_CW) lb_writer<TRI, TOT>(A, &tmap, sbase, lane);
+    if (warp == LB_CW + LB_WW) lb_producer<TRI>(A, sbase, lane);
+    else if (warp >= LB_CW) lb_writer<TRI, TOT>(A, &tmap, sbase, warp - LB_CW, lane);
     else lb_consumer<TRI>(A, sbase, warp, lane);
 }
 

@@ -30,9 +30,16 @@ def _panel(name):
 
 
 def _cosmic_genes():
+    """Cancer Gene Census list the reference ships as DIGDriver/data/genes_CGC_ALL.txt (transfer_tools.py:996-1017 and
+    the indel / PCAWG scale factors read it through pkg_resources and fail if it is missing).  It is not part of this
+    package: point DIG_DATA_DIR at the reference's data directory.  DIG_ALLOW_NO_CGC=1 is the explicit opt-in to run
+    without it (no gene excluded), e.g. for synthetic benchmarks."""
     genes = _panel('CGC_ALL')
     if genes is None:
-        print('WARNING: genes_CGC_ALL.txt not found (set DIG_DATA_DIR); no gene is excluded from the INDEL scale factor')
+        if os.environ.get('DIG_ALLOW_NO_CGC', '') not in ('1', 'true', 'yes'):
+            raise FileNotFoundError(
+                'genes_CGC_ALL.txt not found: set DIG_DATA_DIR to the directory holding the reference\'s '
+                'DIGDriver/data/genes_*.txt (or DIG_ALLOW_NO_CGC=1 to exclude no gene from the scale factors)')
         genes = []
     return genes + ['CDKN2A.p14arf', 'CDKN2A.p16INK4a']
 

@@ -96,7 +96,20 @@ def _strand_code(values):
     return np.array([-1 if (s == '-' or s == '-1' or s == -1) else 1 for s in values], dtype=np.int8)
 
 
-def nonc_model_arrays(df_elts, L_contexts, region_model, win_counts64, d_pr, f_fasta=None):
+def _indel_params(region_model_indels, win_counts64, d_pr, chrom, strand, ptr, bs, be, res):
+    """MU / SIGMA / R_OBS of the same elements against region_params_indels (--indels-direct, reference :161-164 and
+    :383-386); without it the SNV parameters are copied.  The window counts do not enter these three outputs, so a
+    zero table of the indel model's own size is passed when the SNV one does not fit it."""
+    if region_model_indels is None:
+        return res["MU"], res["SIGMA"], res["R_OBS"]
+    n = len(region_model_indels.df)
+    wc = win_counts64 if len(win_counts64) == n else np.zeros((n, 64), dtype=np.int32)
+    E = len(chrom)
+    ind = transfer_elements(region_model_indels, wc, d_pr, chrom, strand, ptr, bs, be, L_elt=np.zeros((E, 192, 1)))
+    return ind["MU"], ind["SIGMA"], ind["R_OBS"]
+
+
+def nonc_model_arrays(df_elts, L_contexts, region_model, win_counts64, d_pr, f_fasta=None, region_model_indels=None):
     """Element pretrain on in-memory inputs: preprocess_nonc (sequence_tools.py:596-644) + nonc_model
     (reference :300-431) == the loop body of DIG_onthefly (onthefly_tools.py:109-165).
 
@@ -113,15 +126,16 @@ def nonc_model_arrays(df_elts, L_contexts, region_model, win_counts64, d_pr, f_f
     Lb = L_contexts.loc[keys].values                          # raises KeyError like the reference (:637)
     L = np.zeros((E, 192), dtype=np.float64)
     np.add.at(L, owner, Lb)
-    res = transfer_elements(region_model, win_counts64, d_pr, chrom, _strand_code(df_elts.STRAND.values), ptr, bs, be,
-                            L_elt=L.reshape(E, 192, 1))
+    strand = _strand_code(df_elts.STRAND.values)
+    res = transfer_elements(region_model, win_counts64, d_pr, chrom, strand, ptr, bs, be, L_elt=L.reshape(E, 192, 1))
+    mu_ind, sigma_ind, r_ind = _indel_params(region_model_indels, win_counts64, d_pr, chrom, strand, ptr, bs, be, res)
     elt_size = (L.sum(axis=1) / 3).astype(np.int64)           # int(np.sum(L) / 3)  (:380)
     with np.errstate(divide='ignore', invalid='ignore'):
         p_indel = elt_size / res["R_SIZE"].astype(np.float64)
     return pd.DataFrame({
         'ELT': df_elts.ELT.values, 'ELT_SIZE': elt_size, 'FLAG': res["FLAG"], 'R_SIZE': res["R_SIZE"],
-        'R_OBS': res["R_OBS"], 'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"],
-        'MU_INDEL': res["MU"], 'SIGMA_INDEL': res["SIGMA"], 'P_SUM': res["P"][:, 0], 'P_INDEL': p_indel})
+        'R_OBS': res["R_OBS"], 'R_INDEL': r_ind, 'MU': res["MU"], 'SIGMA': res["SIGMA"],
+        'MU_INDEL': mu_ind, 'SIGMA_INDEL': sigma_ind, 'P_SUM': res["P"][:, 0], 'P_INDEL': p_indel})
 
 
 def _window_counts_for(region_model, f_fasta):
@@ -137,6 +151,7 @@ def nonc_model_parallel(f_pretrained, f_nonc_data, nonc_L_key, N_procs=1, indels
     """Reference :434-461 on the directory/HDF5 store written by preprocess_element_model."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
+    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     wkey = 'window_{}'.format(rm.window)
@@ -148,26 +163,31 @@ def nonc_model_parallel(f_pretrained, f_nonc_data, nonc_L_key, N_procs=1, indels
     win_counts = win_vals[rows].astype(np.int32)
     if data.has('{}/{}/sites'.format(wkey, nonc_L_key)):               # preprocess_element_model --f-sites
         df_sites = data.read_table('{}/{}/sites'.format(wkey, nonc_L_key))
+        if indels_direct:
+            raise NotImplementedError("--indels-direct is not defined for site sets (the reference's sites model copies "
+                                      "the SNV parameters, genic_driver_tools.py:660)")
         return sites_model_arrays(df_sites.reset_index(drop=True), rm, win_counts, d_pr)
     df_elts = data.read_table('{}/{}/elements'.format(wkey, nonc_L_key))
     df_elts['BLOCK_STARTS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_STARTS]
     df_elts['BLOCK_ENDS'] = [list(map(int, s.split(','))) for s in df_elts.BLOCK_ENDS]
     L_contexts = data.read_table('{}/{}/L_contexts'.format(wkey, nonc_L_key))
-    return nonc_model_arrays(df_elts, L_contexts, rm, win_counts, d_pr)
+    return nonc_model_arrays(df_elts, L_contexts, rm, win_counts, d_pr, region_model_indels=rm_ind)
 
 
-def genic_model_arrays(genes, region_model, win_counts64, d_pr):
+def genic_model_arrays(genes, region_model, win_counts64, d_pr, region_model_indels=None):
     """genic_model (reference :31-203) on in-memory inputs.  ``genes``: pipeline.GeneTable with chromosome
     NUMBERS in chrom_idx.  Returns the genic pretrain DataFrame (reference :170-201)."""
     res = transfer_elements(region_model, win_counts64, d_pr, genes.chrom_idx, genes.strand, genes.blk_ptr,
                             genes.blk_start, genes.blk_end, L_elt=genes.L)
     P = res["P"]
+    mu_ind, sigma_ind, r_ind = _indel_params(region_model_indels, win_counts64, d_pr, genes.chrom_idx, genes.strand,
+                                             genes.blk_ptr, genes.blk_start, genes.blk_end, res)
     with np.errstate(divide='ignore', invalid='ignore'):
         p_indel = res["ELT_SIZE"] / res["R_SIZE"].astype(np.float64)
     df = pd.DataFrame({'CHROM': [str(c) for c in genes.chrom_idx], 'GENE': genes.names,
                        'GENE_LENGTH': res["ELT_SIZE"], 'R_SIZE': res["R_SIZE"], 'R_OBS': res["R_OBS"],
-                       'R_INDEL': res["R_OBS"], 'MU': res["MU"], 'SIGMA': res["SIGMA"], 'MU_INDEL': res["MU"],
-                       'SIGMA_INDEL': res["SIGMA"], 'FLAG': res["FLAG"], 'P_MIS': P[:, 1], 'P_NONS': P[:, 2],
+                       'R_INDEL': r_ind, 'MU': res["MU"], 'SIGMA': res["SIGMA"], 'MU_INDEL': mu_ind,
+                       'SIGMA_INDEL': sigma_ind, 'FLAG': res["FLAG"], 'P_MIS': P[:, 1], 'P_NONS': P[:, 2],
                        'P_SILENT': P[:, 0], 'P_SPLICE': P[:, 3], 'P_TRUNC': P[:, 2] + P[:, 3], 'P_INDEL': p_indel})
     return df
 
@@ -181,6 +201,7 @@ def genic_model_parallel(f_pretrained_str, f_genic_str, N_procs=1, counts_key="w
     from ..pipeline import GeneTable
     pre = storage.Store(f_pretrained_str, "r")
     rm = RegionModel(pre.read_table('region_params'))
+    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :43-44
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     gs = storage.Store(f_genic_str, "r")
     meta = gs.read_table('genes')
@@ -202,7 +223,7 @@ def genic_model_parallel(f_pretrained_str, f_genic_str, N_procs=1, counts_key="w
         wc = pre.read_array('window_counts_64').astype(np.int32)
     else:
         wc = _window_counts_for(rm, f_fasta)
-    return genic_model_arrays(genes, rm, wc, d_pr)
+    return genic_model_arrays(genes, rm, wc, d_pr, region_model_indels=rm_ind)
 
 
 def sites_model_arrays(df_sites, region_model, win_counts64, d_pr):
@@ -292,6 +313,7 @@ def tiled_model_parallel(f_pretrained, f_nonc_data, save_key, N_procs=1):
     """Reference :692-719 on the directory/HDF5 stores (L_counts written by DigPreprocess.py preprocess_tiled)."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
+    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     wkey = 'window_{}'.format(rm.window)
@@ -318,6 +340,7 @@ def tiled_nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key):
     """Reference :599-690: the tiled pretrain rows of the tiles in ``elt_lst`` ('chr{c}:{s}-{e}' names)."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
+    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     wkey = 'window_{}'.format(rm.window)
@@ -347,6 +370,7 @@ def nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key, indels_direct):
     preprocess_sites (L_counts, region_counts and the overlap list of every element)."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
+    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     names, L, R, overlaps = data.read_element_groups('window_{}/{}'.format(rm.window, save_key), list(elt_lst))

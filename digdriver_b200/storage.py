@@ -37,6 +37,12 @@ def _key_path(path, key, suffix):
     return os.path.join(path, key.strip("/").replace("/", "__") + suffix)
 
 
+def _owned_file(name):
+    """Files a directory store writes: <key>.npy, <key>.table.npz, <prefix>____elements__.npz, attrs.json."""
+    return name == "attrs.json" or name.endswith(".npy") or name.endswith(".table.npz") or \
+        name.endswith("____elements__.npz")
+
+
 class Store:
     """Directory-backed key/value store with the reference's HDF5 key names."""
 
@@ -55,7 +61,14 @@ class Store:
             if mode == "r" and not os.path.isdir(self.path):
                 raise FileNotFoundError(self.path)
             if mode == "w" and os.path.isdir(self.path):
-                for f in os.listdir(self.path):
+                # truncate like HDF5 mode 'w' would -- but only files this store owns: never a user's directory
+                entries = os.listdir(self.path)
+                foreign = [f for f in entries if not _owned_file(f)]
+                if foreign:
+                    raise RuntimeError("%s exists and holds files that are not part of a store (%s%s): refusing to "
+                                       "truncate it; choose another output path" %
+                                       (self.path, ", ".join(sorted(foreign)[:3]), ", ..." if len(foreign) > 3 else ""))
+                for f in entries:
                     os.remove(os.path.join(self.path, f))
             os.makedirs(self.path, exist_ok=True)
 

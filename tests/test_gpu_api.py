@@ -548,6 +548,12 @@ def test_persisted_intermediates_and_chunk_workers(workdir, oracle, tmp_path):
     np.testing.assert_allclose(gi.MU_INDEL.values, 0.25 * gi.MU.values, rtol=1e-12)
     assert np.array_equal(gi.R_INDEL.values, gi.R_OBS.values + 3 * np.array([len(overlaps[names.index(n)]) for n in chunk]))
     assert np.array_equal(gi.SIGMA_INDEL.values, gi.SIGMA.values)
+    # the all-in-one element model honours the flag too (same rows as the chunk worker), and without it copies MU
+    full = gd.nonc_model_parallel(str(pre_dir), p("eltdata"), "K1", indels_direct=True).set_index("ELT").loc[chunk]
+    for col in ("MU", "SIGMA", "R_OBS", "MU_INDEL", "SIGMA_INDEL", "R_INDEL", "P_SUM"):
+        assert np.array_equal(full[col].values, gi[col].values), col
+    plain = gd.nonc_model_parallel(str(pre_dir), p("eltdata"), "K1", indels_direct=False)
+    assert np.array_equal(plain.MU_INDEL.values, plain.MU.values) and np.array_equal(plain.R_INDEL.values, plain.R_OBS.values)
     # ---- preprocess_sites + nonc_model == sites_model_arrays
     ann = pd.read_table(p("annot.tsv"), header=None)
     ann = ann[ann[7] != "INDEL"].iloc[:600].copy()
