@@ -43,7 +43,8 @@ namespace {
 
 constexpr int LB_CW = 16;                          // consumer warps
 constexpr int LB_WW = 4;                           // writer warps, one per slice buffer
-constexpr int LB_THREADS = (LB_CW + LB_WW + 1) * 32;   // + the producer warp
+constexpr int LB_PW = 4;                           // producer warps, eight windows each
+constexpr int LB_THREADS = (LB_CW + LB_WW + LB_PW) * 32;
 constexpr int LB_CONS = LB_CW * 32;
 constexpr int LB_SPAN = 128;                       // bases per consumer thread per chunk
 constexpr int LB_CHUNK = LB_CW * LB_SPAN;          // 2048
@@ -100,6 +101,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
     uint32_t spins = 0u;
     while (!mbar_try(a, parity))
         if (++spins > (1u << 24)) __trap();
+}
+// helper warps (producers, writers) poll with a short sleep: their spinning would take issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_idle(uint32_t a, uint32_t parity)
+{
+    uint32_t spins = 0u;
+    while (!mbar_try(a, parity)) {
+        __nanosleep(40);
+        if (++spins > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -269,11 +279,15 @@ __device__ __forceinline__ void lb_pairs(const uint32_t (&D)[9], uint32_t tabl, 
         uint32_t r;
         if (off <= 20) r = D[q] >> (20 - off);
         else r = __funnelshift_r(D[q + 1], D[q], 52 - off);
-        const bool go = !PRED || ((PV[i >> 4] >> (31 - 2 * (i & 15))) & 1u);
-        if (go) {
-            uint32_t addr;
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(r & 0xFFCu), "r"(k32), "r"(tabl));
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(r & 0xFFCu), "r"(k32), "r"(tabl));
+        if constexpr (!PRED) {
             red_add(addr, field_inc(r, top));
+        } else {
+            // predicated, not branched: the edge spans sit on the critical path of the whole batch
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr),
+                         "r"(field_inc(r, top)), "r"(PV[i >> 4] & (0x80000000u >> (2 * (i & 15))))
+                         : "memory");
         }
     }
 }
@@ -300,11 +314,12 @@ struct LbArgs {
     uint32_t zero;            // = 0
 };
 
-// ---- producer warp: lane l brings window l's chunks into the stages ------------------------------------------
+// ---- producer warps: lane l of warp l / 8 brings window l's chunks into the stages --------------------------
 // The chunk sequence of a CTA is the concatenation of the chunks of its batches; chunk number ci lands in stage
 // ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by all sixteen consumer warps.
+// ptxas issues per-lane bulk copies one lane at a time (a ~30-cycle loop each), hence four warps of eight windows.
 template <bool TRI>
-__device__ __forceinline__ void lb_producer(const LbArgs &A, uint32_t sbase, int lane)
+__device__ __forceinline__ void lb_producer(const LbArgs &A, uint32_t sbase, int pw, int lane)
 {
     const uint32_t bar = sbase + OFF_BAR;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
@@ -314,9 +329,11 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, uint32_t sbase, int
         const int nch = warp_max(g.nch);
         for (int k = 0; k < nch; ++k, ++ci) {
             const uint32_t stage = ci & 1u;
-            mbar_wait(bar + 8u * (BAR_EMPTY + stage), ((ci >> 1) & 1u) ^ 1u);
+            mbar_wait_idle(bar + 8u * (BAR_EMPTY + stage), ((ci >> 1) & 1u) ^ 1u);
             const uint32_t full = bar + 8u * (BAR_FULL + stage);
-            if (k < g.nch) {
+            if ((lane >> 3) != pw) {
+                // another producer warp's window
+            } else if (k < g.nch) {
                 const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
                 const int64_t G0 = g.O + (int64_t)k * LB_CHUNK;              // first staged base: multiple of 128, >= -128
                 int64_t dsrc = G0 >> 2, msrc = G0 >> 3;
@@ -351,9 +368,9 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
     // one VECTOR-register copy of the PRMT constant: made formally lane-dependent (A.zero = 0), otherwise ptxas keeps it
     // in a uniform register and copies it into a fresh vector register for every PRMT
     const uint32_t top_r = A.top | (tabl & A.zero);
-    const int sl = warp & 3, wq = warp >> 2;               // write-out: slices sl, sl+4, ..; bin groups 4 wq .. 4 wq + 3
-    const uint32_t outb = sbase + OFF_OUT + (uint32_t)sl * OUT_BYTES + (uint32_t)lane * 256u;
-
+    // write-out: warps 0-7 fill the even slices, warps 8-15 the odd ones, two bin groups (2 x 4 bins) per thread and
+    // slice; slice sg goes through buffer / writer warp sg & 3, so each half alternates between two buffers
+    const int grp = warp >> 3, w8 = warp & 7;
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
         const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const int nch = warp_max(g.nch);
@@ -428,15 +445,21 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
         cons_sync();                                                         // every hexamer of the batch is in the tables
         mbar_wait(bar + 8u * BAR_DONE, (bi & 1u) ^ 1u);                      // writer warp 0 finished the previous batch
 
-        // ---- write-out: this warp fills bin groups 4 wq .. 4 wq + 3 of slices sl, sl + 4, sl + 8, sl + 12
+        // ---- write-out
         uint32_t chk = 0u, tri_acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-            const int sg = sl + 4 * i;
-            mbar_wait(bar + 8u * (BAR_OUTEMPTY + sl), (((bi << 2) + (uint32_t)i) & 1u) ^ 1u);
+        for (int i2 = 0; i2 < 4; ++i2) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int jl = (4 * wq + t + lane) & 15;                     // rotated by lane: conflict-free 128-bit stores
+          for (int h = 0; h < 2; ++h) {
+            const int i = 2 * i2 + h;
+            const int sg = 2 * i + grp;
+            const uint32_t buf = (uint32_t)(sg & 3);
+            const uint32_t outb = sbase + OFF_OUT + buf * OUT_BYTES + (uint32_t)lane * 256u;
+            // this buffer's use number: slices buf, buf + 4, .. of batch bi
+            mbar_wait(bar + 8u * (BAR_OUTEMPTY + buf), (((bi << 2) + (uint32_t)(sg >> 2)) & 1u) ^ 1u);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int jl = (2 * w8 + t + lane) & 15;                     // rotated by lane: conflict-free 128-bit stores
                 const int j = 16 * sg + jl;                                  // bins 4j .. 4j+3 of window `lane`
                 const uint32_t k0 = lds32(tabl + (uint32_t)(4 * j + 0) * 128u), k1 = lds32(tabl + (uint32_t)(4 * j + 1) * 128u);
                 const uint32_t k2 = lds32(tabl + (uint32_t)(4 * j + 2) * 128u), k3 = lds32(tabl + (uint32_t)(4 * j + 3) * 128u);
@@ -452,21 +475,23 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 const uint32_t o2 = __dp4a(w3, 0x00000100u, __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00000100u, a2))));
                 const uint32_t o3 = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x00000001u, __dp4a(w1, 0x00000001u, __dp4a(w0, 0x00000001u, a3))));
                 sts128(outb + (uint32_t)jl * 16u, o0, o1, o2, o3);
-                tri_acc[t] += (o0 + o1) + (o2 + o3);                         // trinucleotide bin 16 sl + jl, whatever i is
+                // trinucleotide bin 16 (sg & 3) + jl: sg & 3 alternates between two values inside a group
+                tri_acc[2 * h + t] += (o0 + o1) + (o2 + o3);
             }
-            if (i == 3) {
+            if (i2 == 3) {
                 if constexpr (TRI) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint32_t bin = (uint32_t)(16 * sl + ((4 * wq + t + lane) & 15));
-                        red_add(sbase + OFF_TRI + (bin * 33u + (uint32_t)lane) * 4u, tri_acc[t]);
+                    for (int t = 0; t < 2; ++t) {
+                        const uint32_t bin = (uint32_t)(16 * (sg & 3) + ((2 * w8 + t + lane) & 15));
+                        red_add(sbase + OFF_TRI + (bin * 33u + (uint32_t)lane) * 4u, tri_acc[2 * h + t]);
                     }
                 }
-                if (chk) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, chk);
+                if (h == 1 && chk) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, chk);
             }
             fence_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar + 8u * (BAR_OUTFULL + sl));
+            if (lane == 0) mbar_arrive(bar + 8u * (BAR_OUTFULL + buf));
+          }
         }
     }
 }
@@ -517,7 +542,7 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4, ++use) {
             const int sg = 4 * s4 + q;
-            mbar_wait(bar + 8u * (BAR_OUTFULL + q), use & 1u);
+            mbar_wait_idle(bar + 8u * (BAR_OUTFULL + q), use & 1u);
             if (s4 == 0) n_exc_raw = lds32(exc);                             // final: every consumer is past the scan
             const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
             for (uint32_t e = lane; e < n_exc; e += 32u) {
@@ -525,8 +550,13 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
                 if (!(ent & 0x8000u) && ((ent & 1023u) >> 6) == (uint32_t)sg)
                     red_add(out + (ent >> 16) * 256u + (ent & 63u) * 4u, 1u);
             }
+            fence_async();
             __syncwarp();
-            if constexpr (TOT) {
+            if (lane == 0) {
+                tensor_s2g(tmap, out, 64 * sg, (int)(b * 32));
+                bulk_commit();
+            }
+            if constexpr (TOT) {                                             // column sums while the TMA engine reads the tile
 #pragma unroll 8
                 for (int l2 = 0; l2 < 32; ++l2) {
                     const uint2 v = lds64(out + (uint32_t)l2 * 256u + (uint32_t)lane * 8u);
@@ -534,11 +564,8 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
                     tmp5[2 * s4 + 1] += v.y;
                 }
             }
-            fence_async();
             __syncwarp();
             if (lane == 0) {
-                tensor_s2g(tmap, out, 64 * sg, (int)(b * 32));
-                bulk_commit();
                 bulk_wait_read<0>();                                         // the tile has left shared memory
                 mbar_arrive(bar + 8u * (BAR_OUTEMPTY + q));
             }
@@ -636,7 +663,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, 
         mbar_init(bar + 8u * (BAR_EMPTY + 1), LB_CW);
 #pragma unroll
         for (int i = 0; i < LB_NOUT; ++i) {
-            mbar_init(bar + 8u * (BAR_OUTFULL + i), LB_CW / LB_NOUT);      // the four consumer warps that fill slice buffer i
+            mbar_init(bar + 8u * (BAR_OUTFULL + i), LB_CW / 2);            // the eight consumer warps that fill a slice
             mbar_init(bar + 8u * (BAR_OUTEMPTY + i), 1u);
         }
         mbar_init(bar + 8u * BAR_DONE, 1u);
@@ -645,7 +672,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, 
         fence_async();
     }
     __syncthreads();
-    if (warp == LB_CW + LB_WW) lb_producer<TRI>(A, sbase, lane);
+    if (warp >= LB_CW + LB_WW) lb_producer<TRI>(A, sbase, warp - LB_CW - LB_WW, lane);
     else if (warp >= LB_CW) lb_writer<TRI, TOT>(A, &tmap, sbase, warp - LB_CW, lane);
     else lb_consumer<TRI>(A, sbase, warp, lane);
 }
