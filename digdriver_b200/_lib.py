@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libdigb200.so")
+# DIG_LIB_PATH selects another build of the same library (developer probes: tools/probe_lb.py --timing)
+LIB_PATH = os.environ.get("DIG_LIB_PATH") or os.path.join(_PKG_DIR, "libdigb200.so")
 
 _c = ctypes
 _P = _c.c_void_p
@@ -66,7 +67,7 @@ SIGNATURES = {
 class ScanOpts(ctypes.Structure):
     """dig_scan_opts of include/dig_b200.h."""
     _fields_ = [("workspace_d", _c.c_void_p), ("workspace_bytes", _c.c_int64), ("variant", _c.c_int32),
-                ("totals_limit_kb", _c.c_uint32)]
+                ("totals_limit_kb", _c.c_uint32), ("tile_window", _c.c_int64)]
 
 
 SCAN_AUTO, SCAN_PER_BASE, SCAN_HEX_PLAIN, SCAN_HEX = 0, 1, 2, 3

@@ -35,7 +35,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, extra_flags=(), out_path=None):
+    """extra_flags / out_path: developer builds beside the product library (e.g. -DDIG_LB_TIMING)."""
+    if out_path is not None:
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out_path] + sources()
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout)
+            raise RuntimeError("nvcc failed (%d)" % res.returncode)
+        return out_path
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -51,4 +60,7 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--timing" in sys.argv:
+        print(build_library(extra_flags=["-DDIG_LB_TIMING"], out_path=os.path.join(PKG_DIR, "libdigb200_timing.so")))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -34,6 +34,7 @@ struct ScanOpts {
     size_t workspace_bytes = 0;
     int variant = DIG_SCAN_AUTO;
     unsigned int tot_limit_kb = 1u << 20;   // kilobases a CTA may fold into 32-bit partial totals before it goes global
+    int64_t tile_window = 0;
 };
 
 ScanOpts scan_opts(const dig_scan_opts *o)
@@ -44,6 +45,7 @@ ScanOpts scan_opts(const dig_scan_opts *o)
         r.workspace_bytes = o->workspace_bytes > 0 ? (size_t)o->workspace_bytes : 0;
         r.variant = o->variant;
         if (o->totals_limit_kb != 0u) r.tot_limit_kb = o->totals_limit_kb;
+        r.tile_window = o->tile_window;
     }
     return r;
 }
@@ -538,7 +540,7 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
         scan_lb_usable(packed2_d, nmask_d, n_bases, counts5_d, so.workspace, so.workspace_bytes, n_reg))
         return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                               n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb, so.workspace,
-                              (cudaStream_t)stream);
+                              so.tile_window, (cudaStream_t)stream);
     if (so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                                n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb,
@@ -582,7 +584,7 @@ extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nma
     if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && so.variant == DIG_SCAN_AUTO &&
         scan_lb_usable(packed2_d, nmask_d, n_bases, counts_d, so.workspace, so.workspace_bytes, n_reg))
         return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
-                              n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb, so.workspace, st);
+                              n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb, so.workspace, so.tile_window, st);
     if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                                n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb,

@@ -159,6 +159,7 @@ bool scan_lb_usable(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, con
 int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                    const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                    int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
-                   unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, cudaStream_t stream);
+                   unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, int64_t tile_window,
+                   cudaStream_t stream);
 
 }  // namespace digscan

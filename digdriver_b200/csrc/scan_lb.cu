@@ -34,6 +34,7 @@
 // Replaces the per-base Python loop of count_sequence_context (sequence_tools.py:65-78) for
 // count_contexts_in_bed(..., n_up=2, n_down=2) (sequence_tools.py:96-128) and, fused, the (1,1) run; bit-exact.
 #include <cuda.h>
+#include <string.h>
 
 #include "scan_common.cuh"
 
@@ -43,14 +44,23 @@ namespace {
 
 constexpr int LB_CW = 16;                          // consumer warps
 constexpr int LB_WW = 4;                           // writer warps, one per slice buffer
-constexpr int LB_PW = 4;                           // producer warps, eight windows each
+constexpr int LB_PW = 4;                           // producer warps, two groups of four windows each
 constexpr int LB_THREADS = (LB_CW + LB_WW + LB_PW) * 32;
 constexpr int LB_CONS = LB_CW * 32;
 constexpr int LB_SPAN = 128;                       // bases per consumer thread per chunk
 constexpr int LB_CHUNK = LB_CW * LB_SPAN;          // 2048
 constexpr uint32_t LB_DSTRIDE = (LB_CHUNK + 64) / 4;     // 528 B of packed bases per window and stage (33 granules)
 constexpr uint32_t LB_MSTRIDE = (LB_CHUNK + 128) / 8;    // 272 B of N mask (17 granules)
-constexpr uint32_t LB_STAGE_BYTES = 32u * (LB_DSTRIDE + LB_MSTRIDE);
+// Lanes 4r .. 4r+3 form group r and work on windows r, r+8, r+16, r+24 of the batch: in a regular tiling those four
+// strips sit at a fixed pitch (8 windows, a multiple of 128 bases), so ONE 2-D TMA box load brings all four.  A group's
+// strips are contiguous in the stage (the box is written row after row) and start 128-byte aligned.
+constexpr uint32_t LB_DGROUP = 2176u;                    // 4 x 528 B, padded to 17 x 128
+constexpr uint32_t LB_MGROUP = 1152u;                    // 4 x 272 B, padded to 9 x 128
+constexpr uint32_t LB_MBASE = 8u * LB_DGROUP;            // mask strips follow the eight data groups
+constexpr uint32_t LB_STAGE_BYTES = 8u * (LB_DGROUP + LB_MGROUP);
+__device__ __forceinline__ int lb_win(int lane) { return (lane >> 2) + 8 * (lane & 3); }    // window of the batch a lane owns
+__device__ __forceinline__ uint32_t lb_dstrip(int lane) { return (uint32_t)(lane >> 2) * LB_DGROUP + (uint32_t)(lane & 3) * LB_DSTRIDE; }
+__device__ __forceinline__ uint32_t lb_mstrip(int lane) { return LB_MBASE + (uint32_t)(lane >> 2) * LB_MGROUP + (uint32_t)(lane & 3) * LB_MSTRIDE; }
 constexpr int LB_MAX_CHUNKS = 16;                  // regions up to ~32 kb; longer ones go to the per-warp kernel
 constexpr int LB_EXC_CAP = 508;
 
@@ -117,6 +127,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void tensor_g2s(const CUtensorMap *tmap, uint32_t dst, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(tmap), "r"(bar), "r"(x), "r"(y)
+                 : "memory");
+}
 __device__ __forceinline__ void tensor_s2g(const CUtensorMap *tmap, uint32_t src, int x, int y)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(x),
@@ -128,7 +144,17 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifdef DIG_LB_TIMING
+// bar.sync does not block at issue; the reduction variant returns a value, so the clock read after it is honest
+__device__ __forceinline__ void cons_sync()
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\tbar.red.popc.u32 %0, 1, %1, p;\n\t}" : "=r"(r) : "n"(LB_CONS) : "memory");
+    if (r == 0xFFFFFFFFu) __trap();
+}
+#else
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LB_CONS) : "memory"); }
+#endif
 __device__ __forceinline__ void writer_sync() { asm volatile("bar.sync 2, %0;" ::"n"(LB_WW * 32) : "memory"); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t a)
@@ -292,6 +318,14 @@ __device__ __forceinline__ void lb_pairs(const uint32_t (&D)[9], uint32_t tabl, 
     }
 }
 
+#ifdef DIG_LB_TIMING
+#define LB_T(var) const long long var = clock64()
+#define LB_ACC(slot, t0, t1) tacc[slot] += (unsigned long long)((t1) - (t0))
+#else
+#define LB_T(var)
+#define LB_ACC(slot, t0, t1)
+#endif
+
 struct LbArgs {
     const uint32_t *p2;
     const uint32_t *nmask;
@@ -312,32 +346,90 @@ struct LbArgs {
     uint32_t k32;             // = 32 (see lb_pairs)
     uint32_t top;             // = 0x01000000 (see field_inc)
     uint32_t zero;            // = 0
+    int64_t tile_w;           // > 0: the caller says the regions tile chromosomes with windows of this size (a multiple of 16)
+    int64_t dshift, mshift;   // element offsets of the second row phase of the input tensor maps
+    unsigned long long *timing;   // DIG_LB_TIMING builds only: phase counters (cycles summed over consumer warps)
 };
 
-// ---- producer warps: lane l of warp l / 8 brings window l's chunks into the stages --------------------------
-// The chunk sequence of a CTA is the concatenation of the chunks of its batches; chunk number ci lands in stage
-// ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by all sixteen consumer warps.
-// ptxas issues per-lane bulk copies one lane at a time (a ~30-cycle loop each), hence four warps of eight windows.
+// Chunks are scanned LAST ONE FIRST, then 0, 1, ..: the two chunks that hold window edges (slower, predicated spans for
+// the warps that get them) come first, so the warps have re-converged by the time the batch reaches its barrier.
+__device__ __forceinline__ int lb_chunk_order(int kq, int nch) { return kq == 0 ? nch - 1 : kq - 1; }
+
+// ---- producer warps: producer warp pw stages groups 2 pw and 2 pw + 1 (lanes 8 pw .. 8 pw + 7) ----------------
+// The chunk sequence of a CTA is the concatenation of the chunks of its batches (each batch in lb_chunk_order); chunk
+// number ci lands in stage ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by
+// all sixteen consumer warps.
+//   * Regular group (the four windows lie at a pitch of 8 tile windows in one chromosome, nothing clipped): the group
+//     leader issues TWO 2-D TMA box loads per chunk (4 rows x 528 B of bases, 4 rows x 272 B of mask) through tensor
+//     maps that view each genome array as rows of one pitch (lb_input_maps).
+//   * Anything else: every lane issues two 1-D bulk copies for its own window.  ptxas serialises per-lane bulk copies
+//     (ELECT + five R2UR broadcasts, ~25 cycles per copy at SM level whatever the number of issuing warps), which
+//     is what the box path avoids: 16 operations per chunk instead of 64.
+struct LbMaps {
+    CUtensorMap d[2], m[2];   // bases / mask, each with two row phases (a box must not cross the end of a row)
+};
+
 template <bool TRI>
-__device__ __forceinline__ void lb_producer(const LbArgs &A, uint32_t sbase, int pw, int lane)
+__device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps, uint32_t sbase, int pw, int lane)
 {
     const uint32_t bar = sbase + OFF_BAR;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
+    const int m = lane & 3;                                // row of the group's box
+    const bool mine = (lane >> 3) == pw;
     uint32_t ci = 0u;
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x) {
-        const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const LbGeom g = lb_geom<TRI>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const int nch = warp_max(g.nch);
-        for (int k = 0; k < nch; ++k, ++ci) {
+        // regular group: every window has the leader's chunk count and sits m * 8 W bases after the leader's origin
+        const int lead = lane & ~3;
+        const uint32_t olo = __shfl_sync(0xffffffffu, (uint32_t)(unsigned long long)g.O, lead);
+        const uint32_t ohi = __shfl_sync(0xffffffffu, (uint32_t)((unsigned long long)g.O >> 32), lead);
+        const int64_t O0 = (int64_t)(((unsigned long long)ohi << 32) | olo);
+        const int n0 = __shfl_sync(0xffffffffu, g.nch, lead);
+        const bool fits = A.tile_w > 0 && g.nch > 0 && g.nch == n0 && O0 >= 0 && g.O == O0 + (int64_t)m * 8 * A.tile_w &&
+                          g.O + (int64_t)g.nch * LB_CHUNK + 128 <= A.n_bases;      // every staged strip lies inside the arrays
+        const uint32_t okm = __ballot_sync(0xffffffffu, fits);
+        const bool regular = ((okm >> lead) & 0xFu) == 0xFu;
+        // Box coordinates of chunk 0 (element = uint32; a row of the data view holds 8 W bases = W / 2 elements, of the
+        // mask view W / 4): the two divisions are done once per batch, the chunk loop only adds.  The producers share
+        // the issue slots with sixteen consumer warps that saturate the integer pipe, so every instruction in the
+        // chunk loop delays the data.
+        const uint32_t ped = (uint32_t)(A.tile_w >> 1), pem = (uint32_t)(A.tile_w >> 2);
+        uint32_t xd0 = 0u, yd0 = 0u, xm0 = 0u, ym0 = 0u;
+        if (regular && m == 0) {
+            const uint32_t ed = (uint32_t)(O0 >> 4), em = (uint32_t)(O0 >> 5);       // n_bases < 2^35 on this path
+            yd0 = ed / ped; xd0 = ed - yd0 * ped;
+            ym0 = em / pem; xm0 = em - ym0 * pem;
+        }
+        for (int kq = 0; kq < nch; ++kq, ++ci) {
+            const int k = lb_chunk_order(kq, nch);
             const uint32_t stage = ci & 1u;
+            LB_T(t_e0);
             mbar_wait_idle(bar + 8u * (BAR_EMPTY + stage), ((ci >> 1) & 1u) ^ 1u);
+            LB_T(t_e1);
             const uint32_t full = bar + 8u * (BAR_FULL + stage);
-            if ((lane >> 3) != pw) {
+            const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
+            if (!mine) {
                 // another producer warp's window
+            } else if (regular && k < g.nch) {
+                if (m == 0) {
+                    // chunk k starts k * 2048 bases = 128 k (64 k) elements further: at most one row wrap (W >= 4096)
+                    uint32_t xd = xd0 + 128u * (uint32_t)k, yd = yd0, xm = xm0 + 64u * (uint32_t)k, ym = ym0;
+                    if (xd >= ped) { xd -= ped; ++yd; }
+                    if (xm >= pem) { xm -= pem; ++ym; }
+                    int sd = 0, sm = 0;
+                    if (xd + LB_DSTRIDE / 4 > ped) { xd -= (uint32_t)A.dshift; sd = 1; }     // the box would cross the row end:
+                    if (xm + LB_MSTRIDE / 4 > pem) { xm -= (uint32_t)A.mshift; sm = 1; }     // same row of the shifted view
+                    mbar_arrive_tx(full, 4u * (LB_DSTRIDE + LB_MSTRIDE));
+                    tensor_g2s(&maps->d[sd], stg + lb_dstrip(lane), (int)xd, (int)yd, full);
+                    tensor_g2s(&maps->m[sm], stg + lb_mstrip(lane), (int)xm, (int)ym, full);
+                } else {
+                    mbar_arrive(full);
+                }
             } else if (k < g.nch) {
-                const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
                 const int64_t G0 = g.O + (int64_t)k * LB_CHUNK;              // first staged base: multiple of 128, >= -128
                 int64_t dsrc = G0 >> 2, msrc = G0 >> 3;
-                uint32_t ddst = stg + (uint32_t)lane * LB_DSTRIDE, mdst = stg + 32u * LB_DSTRIDE + (uint32_t)lane * LB_MSTRIDE;
+                uint32_t ddst = stg + lb_dstrip(lane), mdst = stg + lb_mstrip(lane);
                 int64_t dbytes = LB_DSTRIDE, mbytes = LB_MSTRIDE;
                 if (G0 < 0) {                                                // no base before the genome is ever needed
                     dsrc = 0; ddst += 32u; dbytes -= 32;
@@ -353,6 +445,17 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, uint32_t sbase, int
                 mbar_arrive(full);
             }
             __syncwarp();
+#ifdef DIG_LB_TIMING
+            if (pw == 0) {                                                   // copy latency: issued -> FULL complete
+                const long long t_i = clock64();
+                mbar_wait(full, (ci >> 1) & 1u);
+                if (lane == 0 && A.timing != nullptr) {
+                    atomicAdd(A.timing + 7, (unsigned long long)(clock64() - t_i));
+                    atomicAdd(A.timing + 11, (unsigned long long)(t_e1 - t_e0));      // producer idle (EMPTY wait)
+                    atomicAdd(A.timing + 12, (unsigned long long)(t_i - t_e1));       // issue
+                }
+            }
+#endif
         }
     }
 }
@@ -371,19 +474,27 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
     // write-out: warps 0-7 fill the even slices, warps 8-15 the odd ones, two bin groups (2 x 4 bins) per thread and
     // slice; slice sg goes through buffer / writer warp sg & 3, so each half alternates between two buffers
     const int grp = warp >> 3, w8 = warp & 7;
+#ifdef DIG_LB_TIMING
+    unsigned long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
-        const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const LbGeom g = lb_geom<TRI>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const int nch = warp_max(g.nch);
         const uint32_t par = bi & 1u;
         const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
         uint32_t npairs = 0u;
         bool clean = bi == 0u;                             // the kernel prologue zeroed the tables of the first batch
-        for (int k = 0; k < nch; ++k, ++cit) {
+        for (int kq = 0; kq < nch; ++kq, ++cit) {
+            const int k = lb_chunk_order(kq, nch);
             const uint32_t stage = cit & 1u;
+            LB_T(t_a);
             mbar_wait(bar + 8u * (BAR_FULL + stage), (cit >> 1) & 1u);
+            LB_T(t_b);
+            LB_ACC(0, t_a, t_b);
+            LB_ACC((kq == 0 ? 8 : (kq == 1 ? 9 : 10)), t_a, t_b);
             const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
-            const uint32_t dptr = stg + (uint32_t)lane * LB_DSTRIDE + (uint32_t)warp * 32u;
-            const uint32_t mptr = stg + 32u * LB_DSTRIDE + (uint32_t)lane * LB_MSTRIDE + (uint32_t)warp * 16u;
+            const uint32_t dptr = stg + lb_dstrip(lane) + (uint32_t)warp * 32u;
+            const uint32_t mptr = stg + lb_mstrip(lane) + (uint32_t)warp * 16u;
             uint32_t D[9], M[5];
             {
                 const uint4 a = lds128(dptr), c = lds128(dptr + 16u), m = lds128(mptr);
@@ -396,9 +507,13 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + 8u * (BAR_EMPTY + stage));      // the stage is in registers now
             if (!clean) {                                                    // the writer warps have re-zeroed the tables
+                LB_T(t_c);
                 mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);
+                LB_T(t_d);
+                LB_ACC(1, t_c, t_d);
                 clean = true;
             }
+            LB_T(t_p0);
             const int base = k * LB_CHUNK + warp * LB_SPAN;                  // local base 0 relative to the origin
             const int lo5 = g.lo5 - base, hi5 = g.hi5 - base;                // centre c (local base index) valid: lo5 <= c < hi5
             const uint32_t any_n = M[0] | M[1] | M[2] | M[3] | (M[4] & 0xF0000000u);
@@ -439,14 +554,21 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 }
                 if ((PV[0] | PV[1] | PV[2] | PV[3]) != 0u) lb_pairs<true>(D, tabl, A.k32, top_r, PV);
             }
+            LB_T(t_p1);
+            LB_ACC(2, t_p0, t_p1);
         }
         if (!clean) mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);         // a batch without chunks still reads the tables
         if (npairs) red_add(sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, npairs);
+        LB_T(t_s0);
         cons_sync();                                                         // every hexamer of the batch is in the tables
+        LB_T(t_s1);
+        LB_ACC(3, t_s0, t_s1);
         mbar_wait(bar + 8u * BAR_DONE, (bi & 1u) ^ 1u);                      // writer warp 0 finished the previous batch
+        LB_T(t_s2);
+        LB_ACC(4, t_s1, t_s2);
 
         // ---- write-out
-        uint32_t chk = 0u, tri_acc[4] = {0u, 0u, 0u, 0u};
+        uint32_t tri_acc[4] = {0u, 0u, 0u, 0u};    // also the overflow check: all bins of a window sum to 2 x (table bytes)
 #pragma unroll 1
         for (int i2 = 0; i2 < 4; ++i2) {
 #pragma unroll
@@ -454,9 +576,12 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
             const int i = 2 * i2 + h;
             const int sg = 2 * i + grp;
             const uint32_t buf = (uint32_t)(sg & 3);
-            const uint32_t outb = sbase + OFF_OUT + buf * OUT_BYTES + (uint32_t)lane * 256u;
+            const uint32_t outb = sbase + OFF_OUT + buf * OUT_BYTES + (uint32_t)lb_win(lane) * 256u;    // tile rows in window order
             // this buffer's use number: slices buf, buf + 4, .. of batch bi
+            LB_T(t_w0);
             mbar_wait(bar + 8u * (BAR_OUTEMPTY + buf), (((bi << 2) + (uint32_t)(sg >> 2)) & 1u) ^ 1u);
+            LB_T(t_w1);
+            LB_ACC(5, t_w0, t_w1);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int jl = (2 * w8 + t + lane) & 15;                     // rotated by lane: conflict-free 128-bit stores
@@ -468,7 +593,6 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 // hexamers STARTING with pentanucleotide m: all four fields of row m
                 const uint32_t a0 = __dp4a(k0, 0x01010101u, 0u), a1 = __dp4a(k1, 0x01010101u, 0u);
                 const uint32_t a2 = __dp4a(k2, 0x01010101u, 0u), a3 = __dp4a(k3, 0x01010101u, 0u);
-                chk += (a0 + a1) + (a2 + a3);
                 // hexamers ENDING with m = (bcde f): byte 3 - f of the rows (a bcde), summed over a
                 const uint32_t o0 = __dp4a(w3, 0x01000000u, __dp4a(w2, 0x01000000u, __dp4a(w1, 0x01000000u, __dp4a(w0, 0x01000000u, a0))));
                 const uint32_t o1 = __dp4a(w3, 0x00010000u, __dp4a(w2, 0x00010000u, __dp4a(w1, 0x00010000u, __dp4a(w0, 0x00010000u, a1))));
@@ -486,14 +610,23 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                         red_add(sbase + OFF_TRI + (bin * 33u + (uint32_t)lane) * 4u, tri_acc[2 * h + t]);
                     }
                 }
-                if (h == 1 && chk) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, chk);
+                if (h == 1) red_add(sbase + OFF_CHK + (uint32_t)lane * 4u, (tri_acc[0] + tri_acc[1]) + (tri_acc[2] + tri_acc[3]));
             }
             fence_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + 8u * (BAR_OUTFULL + buf));
+            LB_T(t_w2);
+            LB_ACC(6, t_w1, t_w2);
           }
         }
     }
+#ifdef DIG_LB_TIMING
+    if (A.timing != nullptr && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 11; ++q)
+            if (q != 7) atomicAdd(A.timing + q, tacc[q]);
+    }
+#endif
 }
 
 // ---- writer warps: corrections, genome-wide totals, TMA stores, per-batch bookkeeping ----------------------
@@ -531,10 +664,10 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
     };
 
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
-        const LbGeom g = lb_geom<TRI>(b * 32 + lane, A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const LbGeom g = lb_geom<TRI>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const uint32_t par = bi & 1u;
         const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
-        const int64_t r = b * 32 + lane;
+        const int64_t r = b * 32 + lb_win(lane);
         unsigned int tmp5[TOT ? 8 : 1], tmp3[2] = {0u, 0u};
 #pragma unroll
         for (int i = 0; i < (TOT ? 8 : 1); ++i) tmp5[i] = 0u;
@@ -548,7 +681,7 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
             for (uint32_t e = lane; e < n_exc; e += 32u) {
                 const uint32_t ent = lds32(exc + 16u + 4u * e);
                 if (!(ent & 0x8000u) && ((ent & 1023u) >> 6) == (uint32_t)sg)
-                    red_add(out + (ent >> 16) * 256u + (ent & 63u) * 4u, 1u);
+                    red_add(out + (uint32_t)lb_win((int)(ent >> 16)) * 256u + (ent & 63u) * 4u, 1u);
             }
             fence_async();
             __syncwarp();
@@ -590,7 +723,7 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
                 __syncwarp();
 #pragma unroll 4
                 for (int l2 = 0; l2 < 32; ++l2) {
-                    const int64_t r2 = b * 32 + l2;
+                    const int64_t r2 = b * 32 + lb_win(l2);
                     const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
                     const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
                     if (r2 < A.n_reg) {
@@ -604,9 +737,10 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
 #pragma unroll 6
                 for (int i = 0; i < 66; ++i) sts32(tri + (uint32_t)(lane + 32 * i) * 4u, 0u);
             }
-            // exact overflow check: sum of all table bytes == hexamers counted
+            // exact overflow check: the bins of a window (before corrections) sum to twice the sum of its table bytes, and
+            // a table without an overflowed field sums to the hexamers counted
             const uint32_t cnt_a = sbase + OFF_CNT + par * 128u + (uint32_t)lane * 4u, chk_a = sbase + OFF_CHK + (uint32_t)lane * 4u;
-            const bool bad = lds32(cnt_a) != lds32(chk_a);
+            const bool bad = 2u * lds32(cnt_a) != lds32(chk_a);
             const bool fail = __any_sync(0xffffffffu, bad) || n_exc_raw > (uint32_t)LB_EXC_CAP;
             sts32(cnt_a, 0u);
             sts32(chk_a, 0u);
@@ -646,7 +780,8 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
 }
 
 template <bool TRI, bool TOT>
-__global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, const __grid_constant__ CUtensorMap tmap,
+                                                                const __grid_constant__ LbMaps imaps)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -672,7 +807,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, 
         fence_async();
     }
     __syncthreads();
-    if (warp >= LB_CW + LB_WW) lb_producer<TRI>(A, sbase, warp - LB_CW - LB_WW, lane);
+    if (warp >= LB_CW + LB_WW) lb_producer<TRI>(A, &imaps, sbase, warp - LB_CW - LB_WW, lane);
     else if (warp >= LB_CW) lb_writer<TRI, TOT>(A, &tmap, sbase, warp - LB_CW, lane);
     else lb_consumer<TRI>(A, sbase, warp, lane);
 }
@@ -681,8 +816,9 @@ typedef CUresult (*LbEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, v
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// counts5 as a 2-D int32 tensor [n_reg][1024] with a [32 rows][64 columns] box: one slice of one batch per store
-int lb_tensor_map(CUtensorMap *tmap, int32_t *counts5, int64_t n_reg)
+// 2-D tensor map over `base`: dim0 x dim1 elements of 4 bytes, rows `pitch` bytes apart, box0 x box1 box, no swizzle
+int lb_encode(CUtensorMap *tmap, CUtensorMapDataType dtype, const void *base, uint64_t dim0, uint64_t dim1, uint64_t pitch,
+              uint32_t box0, uint32_t box1)
 {
     static LbEncodeFn encode = nullptr;                  // driver entry point, resolved once (no libcuda link dependency)
     if (encode == nullptr) {
@@ -695,13 +831,12 @@ int lb_tensor_map(CUtensorMap *tmap, int32_t *counts5, int64_t n_reg)
         }
         encode = reinterpret_cast<LbEncodeFn>(fn);
     }
-    const cuuint64_t gdim[2] = {1024u, (cuuint64_t)n_reg};
-    const cuuint64_t gstride[1] = {4096u};
-    const cuuint32_t box[2] = {64u, 32u};
+    const cuuint64_t gdim[2] = {dim0, dim1};
+    const cuuint64_t gstride[1] = {pitch};
+    const cuuint32_t box[2] = {box0, box1};
     const cuuint32_t estride[2] = {1u, 1u};
-    const CUresult rc = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2u, counts5, gdim, gstride, box, estride,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult rc = encode(tmap, dtype, 2u, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         dig::set_error("%s: cuTensorMapEncodeTiled failed (%d)", __func__, (int)rc);
         return DIG_ERR_CUDA;
@@ -709,8 +844,49 @@ int lb_tensor_map(CUtensorMap *tmap, int32_t *counts5, int64_t n_reg)
     return DIG_OK;
 }
 
+// counts5 as a 2-D int32 tensor [n_reg][1024] with a [32 rows][64 columns] box: one slice of one batch per store
+int lb_tensor_map(CUtensorMap *tmap, int32_t *counts5, int64_t n_reg)
+{
+    return lb_encode(tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, counts5, 1024u, (uint64_t)n_reg, 4096u, 64u, 32u);
+}
+
+// The two genome arrays as rows of 8 tile windows (8 W bases: 2 W bytes of packed bases, W bytes of mask), so that the
+// strips of windows r, r + 8, r + 16, r + 24 of a batch are the rows of one [4][strip] box.  A box must not run over the
+// end of a row, hence a second view of each array shifted by about half a row.  Returns the tile size actually usable
+// (0: no box path) through A.
+int lb_input_maps(LbMaps *maps, LbArgs &A, int64_t tile_w)
+{
+    A.tile_w = 0;
+    A.dshift = A.mshift = 0;
+    memset(maps, 0, sizeof(*maps));
+    if (tile_w < 4096 || (tile_w & 15) != 0 || tile_w > (int64_t)LB_MAX_CHUNKS * LB_CHUNK || A.n_bases >= ((int64_t)1 << 35))
+        return DIG_OK;
+    const uint64_t dbytes = (uint64_t)A.n_bases >> 2, mbytes = (uint64_t)A.n_bases >> 3;
+    const uint64_t dpitch = 2u * (uint64_t)tile_w, mpitch = (uint64_t)tile_w;      // bytes per row
+    const uint64_t dsh = (dpitch / 2) & ~(uint64_t)15, msh = (mpitch / 2) & ~(uint64_t)15;
+    if (dbytes <= dsh + dpitch || mbytes <= msh + mpitch) return DIG_OK;           // tiny genome: not worth a map
+    const unsigned char *p2b = reinterpret_cast<const unsigned char *>(A.p2);
+    const unsigned char *nmb = reinterpret_cast<const unsigned char *>(A.nmask);
+    int rc = lb_encode(&maps->d[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, p2b, dpitch / 4, (dbytes + dpitch - 1) / dpitch, dpitch,
+                       LB_DSTRIDE / 4, 4u);
+    if (rc == DIG_OK)
+        rc = lb_encode(&maps->d[1], CU_TENSOR_MAP_DATA_TYPE_UINT32, p2b + dsh, dpitch / 4, (dbytes - dsh + dpitch - 1) / dpitch,
+                       dpitch, LB_DSTRIDE / 4, 4u);
+    if (rc == DIG_OK)
+        rc = lb_encode(&maps->m[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, nmb, mpitch / 4, (mbytes + mpitch - 1) / mpitch, mpitch,
+                       LB_MSTRIDE / 4, 4u);
+    if (rc == DIG_OK)
+        rc = lb_encode(&maps->m[1], CU_TENSOR_MAP_DATA_TYPE_UINT32, nmb + msh, mpitch / 4, (mbytes - msh + mpitch - 1) / mpitch,
+                       mpitch, LB_MSTRIDE / 4, 4u);
+    if (rc != DIG_OK) return rc;
+    A.tile_w = tile_w;
+    A.dshift = (int64_t)(dsh / 4);
+    A.mshift = (int64_t)(msh / 4);
+    return DIG_OK;
+}
+
 template <bool TRI, bool TOT>
-int launch_lb(const LbArgs &A, const CUtensorMap &tmap, cudaStream_t stream)
+int launch_lb(const LbArgs &A, const CUtensorMap &tmap, const LbMaps &imaps, cudaStream_t stream)
 {
     auto kern = scan_lb_kernel<TRI, TOT>;
     static thread_local bool attr_set = false;
@@ -721,7 +897,7 @@ int launch_lb(const LbArgs &A, const CUtensorMap &tmap, cudaStream_t stream)
     const int64_t n_batches = (A.n_reg + 31) >> 5;
     int64_t blocks = dig::sm_count();
     if (blocks > n_batches) blocks = n_batches;
-    kern<<<(unsigned)blocks, LB_THREADS, LB_SMEM, stream>>>(A, tmap);
+    kern<<<(unsigned)blocks, LB_THREADS, LB_SMEM, stream>>>(A, tmap, imaps);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
@@ -730,7 +906,12 @@ int launch_lb(const LbArgs &A, const CUtensorMap &tmap, cudaStream_t stream)
 
 namespace digscan {
 
-size_t scan_lb_workspace_bytes(int64_t n_reg) { return 16 + (size_t)(n_reg > 0 ? n_reg : 0) * sizeof(int32_t); }
+static size_t lb_list_bytes(int64_t n_reg) { return (16 + (size_t)(n_reg > 0 ? n_reg : 0) * sizeof(int32_t) + 15) & ~(size_t)15; }
+#ifdef DIG_LB_TIMING
+size_t scan_lb_workspace_bytes(int64_t n_reg) { return lb_list_bytes(n_reg) + 128; }     // + 16 phase counters
+#else
+size_t scan_lb_workspace_bytes(int64_t n_reg) { return lb_list_bytes(n_reg); }
+#endif
 
 bool scan_lb_usable(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int32_t *counts5, const void *workspace,
                     size_t workspace_bytes, int64_t n_reg)
@@ -746,7 +927,8 @@ bool scan_lb_usable(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, con
 int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                    const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                    int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
-                   unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, cudaStream_t stream)
+                   unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, int64_t tile_window,
+                   cudaStream_t stream)
 {
     int32_t *fb_count = reinterpret_cast<int32_t *>(workspace);
     int32_t *fb_list = fb_count + 4;
@@ -759,10 +941,20 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
     A.reg_chrom = reg_chrom; A.reg_start = reg_start; A.reg_end = reg_end; A.n_reg = n_reg;
     A.counts5 = counts5; A.counts3 = counts3; A.totals5 = totals5; A.totals3 = totals3;
     A.k32 = 32u; A.top = 0x01000000u; A.zero = 0u;
+    A.timing = nullptr;
+#ifdef DIG_LB_TIMING
+    // dev builds: the phase counters follow the redo list in the workspace
+    A.timing = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(workspace) + lb_list_bytes(n_reg));
+    DIG_CUDA(cudaMemsetAsync(A.timing, 0, 128, stream));
+#endif
     A.fb_count = fb_count; A.fb_list = fb_list; A.tot_limit_kb = tot_limit_kb < (1u << 21) ? tot_limit_kb : (1u << 21);
-    int rc;
-    if (counts3 != nullptr) rc = totals5 != nullptr ? launch_lb<true, true>(A, tmap, stream) : launch_lb<true, false>(A, tmap, stream);
-    else rc = totals5 != nullptr ? launch_lb<false, true>(A, tmap, stream) : launch_lb<false, false>(A, tmap, stream);
+    LbMaps imaps;
+    int rc = lb_input_maps(&imaps, A, tile_window);
+    if (rc != DIG_OK) return rc;
+    if (counts3 != nullptr)
+        rc = totals5 != nullptr ? launch_lb<true, true>(A, tmap, imaps, stream) : launch_lb<true, false>(A, tmap, imaps, stream);
+    else
+        rc = totals5 != nullptr ? launch_lb<false, true>(A, tmap, imaps, stream) : launch_lb<false, false>(A, tmap, imaps, stream);
     if (rc != DIG_OK) return rc;
     return launch_scan_hex(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts5, counts3,
                            totals5, totals3, tot_limit_kb, false, fb_list, fb_count, stream);

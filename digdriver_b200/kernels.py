@@ -24,7 +24,21 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace):
+def _tile_hint(reg_start, reg_end, tile_window):
+    """Window size to pass as dig_scan_opts.tile_window: the caller's, or, for HOST arrays, the common length of the
+    regions (it is only a hint: the kernel verifies it per group of windows on the device)."""
+    if tile_window is not None:
+        return int(tile_window)
+    if isinstance(reg_start, torch.Tensor) or isinstance(reg_end, torch.Tensor):
+        return 0
+    s, e = np.asarray(reg_start), np.asarray(reg_end)
+    if s.size == 0:
+        return 0
+    w = int(e.flat[0]) - int(s.flat[0])
+    return w if w > 0 and bool(np.all(e - s == w)) else 0
+
+
+def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace, tile_window=0):
     """dig_scan_opts for one scan call: the device scratch the lane-bank kernel needs (caller-owned, sized by
     dig_scan_workspace_bytes) plus the A/B knobs.  Returns (struct, workspace tensor to keep alive)."""
     import ctypes
@@ -32,7 +46,8 @@ def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace):
         nbytes = int(_lib.load().dig_scan_workspace_bytes(int(n_reg)))
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     opts = _lib.ScanOpts(workspace.data_ptr() if workspace is not None else None,
-                         workspace.numel() if workspace is not None else 0, int(variant), int(totals_limit_kb))
+                         workspace.numel() if workspace is not None else 0, int(variant), int(totals_limit_kb),
+                         int(tile_window))
     return opts, ctypes.byref(opts), workspace
 
 
@@ -44,7 +59,7 @@ def scan_workspace(genome_or_device, n_reg):
 
 def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, strand=None,
                    want_totals=False, out=None, totals=None, stream=None, variant=_lib.SCAN_AUTO,
-                   totals_limit_kb=0, workspace=None):
+                   totals_limit_kb=0, workspace=None, tile_window=None):
     """K2/K4: per-region context histogram.
 
     genome: DeviceGenome.  reg_chrom: chromosome indices into the genome (int32).
@@ -62,7 +77,8 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
         totals = torch.zeros(K, dtype=torch.int64, device=dev)
     lane_bank = n_up == 2 and n_down == 2 and st is None and variant == _lib.SCAN_AUTO
     opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
-                                           workspace if lane_bank else None)
+                                           workspace if lane_bank else None,
+                                           _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0)
     with torch.cuda.device(dev):
         _lib.call("dig_count_contexts", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
                   genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),
@@ -75,7 +91,7 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
 
 def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=False, out5=None, out3=None,
                            totals5=None, totals3=None, stream=None, variant=_lib.SCAN_AUTO, totals_limit_kb=0,
-                           workspace=None):
+                           workspace=None, tile_window=None):
     """K2 fused: pentanucleotide and trinucleotide tables (+ totals) of the same regions in one pass.
     Returns (counts5 [n,1024], counts3 [n,64], totals5, totals3)."""
     dev = genome.device
@@ -92,7 +108,8 @@ def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=Fa
         totals3 = torch.zeros(64, dtype=torch.int64, device=dev)
     lane_bank = variant == _lib.SCAN_AUTO
     opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
-                                           workspace if lane_bank else None)
+                                           workspace if lane_bank else None,
+                                           _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0)
     with torch.cuda.device(dev):
         _lib.call("dig_count_contexts_fused53", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
                   genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),

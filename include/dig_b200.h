@@ -83,6 +83,11 @@ int dig_pack_genome(const uint8_t *ascii_d, int64_t n_bases, uint32_t *packed2_d
  *        the per-warp kernels run; results are identical.
  *   variant          DIG_SCAN_AUTO, or one specific kernel family for A/B measurements and tests
  *   totals_limit_kb  0 = default; kilobases folded into 32-bit partial totals before they move to totals_d
+ *   tile_window      0 = unknown.  > 0: a HINT that the regions are the reference's window tiling (DataExtractor.py:70-77:
+ *        consecutive windows of this size from 0 in every chromosome, in order).  The lane-bank kernel then fetches the
+ *        genome with 2-D TMA box loads (four windows per load) wherever the hint holds; it checks the hint per group
+ *        of windows on the device and falls back to per-window copies where it does not, so a wrong hint costs time,
+ *        never correctness.  Used when it is a multiple of 16 and >= 4096.
  */
 #define DIG_SCAN_AUTO 0        /* lane-bank kernel when usable, else per-warp hexamer pairs, else per-base */
 #define DIG_SCAN_PER_BASE 1    /* one shared-memory atomic per base (scan.cu) */
@@ -93,6 +98,7 @@ typedef struct dig_scan_opts {
     int64_t workspace_bytes;
     int32_t variant;
     uint32_t totals_limit_kb;
+    int64_t tile_window;
 } dig_scan_opts;
 int64_t dig_scan_workspace_bytes(int64_t n_reg);
 

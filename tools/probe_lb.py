@@ -1,6 +1,8 @@
 """Developer probe: lane-bank scan (scan_lb.cu) vs the per-warp hexamer kernel (bit-exactness + timing at hg19 scale).
 usage: probe_lb.py [total_bases] [--quick]"""
 import sys, os
+if "--timing" in sys.argv:      # python -m digdriver_b200.build --timing  first
+    os.environ["DIG_LIB_PATH"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "digdriver_b200", "libdigb200_timing.so")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from digdriver_b200 import genome as G, kernels, _lib
@@ -23,6 +25,7 @@ lengths = G.hg19_like_lengths(total)
 names = ["chr%d" % (i + 1) for i in range(22)]
 dg = G.DeviceGenome.synthetic(names, lengths, seed=1)
 W = 10_000
+TW = 0 if "--no-hint" in sys.argv else W
 wins = G.tile_windows(np.arange(22), lengths, W)
 rc = torch.from_numpy(wins[:, 0].astype(np.int32)).cuda(); rs = torch.from_numpy(wins[:, 1]).cuda(); re = torch.from_numpy(wins[:, 2]).cuda()
 nb = float((wins[:, 2] - wins[:, 1]).sum())
@@ -33,9 +36,24 @@ for variant, name in ((_lib.SCAN_HEX, "per-warp hexamer"), (_lib.SCAN_AUTO, "lan
     out3 = torch.empty((len(wins), 64), dtype=torch.int32, device="cuda")
     t5 = torch.zeros(1024, dtype=torch.int64, device="cuda"); t3 = torch.zeros(64, dtype=torch.int64, device="cuda")
     fn = lambda: kernels.count_contexts_fused53(dg, rc, rs, re, out5=out5, out3=out3, totals5=t5, totals3=t3,
-                                                variant=variant, workspace=ws)
+                                                variant=variant, workspace=ws, tile_window=TW)
     ws.zero_(); fn(); torch.cuda.synchronize()
     res[variant] = (out5.clone(), out3.clone(), t5.clone(), t3.clone())
+    if variant == _lib.SCAN_AUTO and "--timing" in sys.argv:
+        off = (16 + 4 * len(wins) + 15) // 16 * 16
+        t = ws[off:off + 128].view(torch.int64).cpu().numpy().astype(float)
+        nwarp = 148 * 16
+        names = ["wait FULL", "wait CLEAN", "process chunks", "barrier B1", "wait DONE", "wait OUTEMPTY", "write-out work", "-"]
+        tot = t[:7].sum()
+        print("  phase cycles per consumer warp (sum %.0f = %.3f ms at 1.955 GHz):" % (tot / nwarp, tot / nwarp / 1.955e6))
+        for nm_, v in zip(names[:7], t):
+            print("    %-16s %9.0f  %5.1f%%" % (nm_, v / nwarp, 100 * v / tot))
+        n_chunks = 5 * ((len(wins) + 31) // 32)
+        print("    copy latency (issued -> FULL complete, producer warp 0): %.0f cycles per chunk; issue %.0f; producer idle %.0f"
+              % (t[7] / n_chunks, t[12] / n_chunks, t[11] / n_chunks))
+        nb_ = (len(wins) + 31) // 32
+        print("    FULL wait per consumer warp and chunk: first %.0f, second %.0f, later %.0f cycles"
+              % (t[8] / 16 / nb_, t[9] / 16 / nb_, t[10] / 16 / nb_ / 3))
     if variant == _lib.SCAN_AUTO:
         print("  redo list length: %d of %d windows" % (int(ws[:4].view(torch.int32).item()), len(wins)), flush=True)
     best, med = timeit(fn)
@@ -44,11 +62,11 @@ for variant, name in ((_lib.SCAN_HEX, "per-warp hexamer"), (_lib.SCAN_AUTO, "lan
           % (name, best, med, nb * bpb / best / 1e6, nb * bpb / best / 1e6 / 6556.5), flush=True)
     o = torch.empty((len(wins), 1024), dtype=torch.int32, device="cuda")
     tt = torch.zeros(1024, dtype=torch.int64, device="cuda")
-    fn2 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, totals=tt, variant=variant, workspace=ws)
+    fn2 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, totals=tt, variant=variant, workspace=ws, tile_window=TW)
     best, med = timeit(fn2)
     bpb = 0.375 + 4.0 * 1024 / W
     print("penta   %-18s best %.3f ms med %.3f ms -> frac %.3f" % (name, best, med, nb * bpb / best / 1e6 / 6556.5), flush=True)
-    fn3 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, variant=variant, workspace=ws)
+    fn3 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, variant=variant, workspace=ws, tile_window=TW)
     best, med = timeit(fn3)
     print("penta no totals %-10s best %.3f ms" % (name, best), flush=True)
 for k, nm in enumerate(("counts5", "counts3", "totals5", "totals3")):
