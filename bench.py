@@ -258,9 +258,11 @@ def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
         di.totals3.zero_()
     if ev is not None:
         ev[0].record()
+    if getattr(di, "scan_ws", None) is None or di.scan_ws_n < hi - lo:
+        di.scan_ws, di.scan_ws_n = kernels.scan_workspace(dg, hi - lo), hi - lo
     kernels.count_contexts_fused53(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi],
                                    out5=di.counts5[lo:hi], out3=di.counts3[lo:hi], totals5=di.totals5,
-                                   totals3=di.totals3)
+                                   totals3=di.totals3, workspace=di.scan_ws, tile_window=WINDOW)
     if ev is not None:
         ev[1].record()
 

@@ -477,9 +477,16 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
 #ifdef DIG_LB_TIMING
     unsigned long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
+    LB_T(t_k0);
+    // the descriptor of the NEXT batch is fetched before this batch's write-out: its dependent global loads
+    // (region -> chromosome -> length / offset) would otherwise be exposed at every batch start
+    LbGeom gnext = lb_geom<TRI>((int64_t)blockIdx.x * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
-        const LbGeom g = lb_geom<TRI>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        LB_T(t_g0);
+        const LbGeom g = gnext;
         const int nch = warp_max(g.nch);
+        LB_T(t_g1);
+        LB_ACC(13, t_g0, t_g1);
         const uint32_t par = bi & 1u;
         const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
         uint32_t npairs = 0u;
@@ -567,6 +574,9 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
         LB_T(t_s2);
         LB_ACC(4, t_s1, t_s2);
 
+        if (b + gridDim.x < n_batches)
+            gnext = lb_geom<TRI>((b + gridDim.x) * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+
         // ---- write-out
         uint32_t tri_acc[4] = {0u, 0u, 0u, 0u};    // also the overflow check: all bins of a window sum to 2 x (table bytes)
 #pragma unroll 1
@@ -594,10 +604,11 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 const uint32_t a0 = __dp4a(k0, 0x01010101u, 0u), a1 = __dp4a(k1, 0x01010101u, 0u);
                 const uint32_t a2 = __dp4a(k2, 0x01010101u, 0u), a3 = __dp4a(k3, 0x01010101u, 0u);
                 // hexamers ENDING with m = (bcde f): byte 3 - f of the rows (a bcde), summed over a
+                // (bytes 3 and 1 through IDP.4A on the FMA pipe, bytes 2 and 0 with masks on the integer pipe: both busy)
                 const uint32_t o0 = __dp4a(w3, 0x01000000u, __dp4a(w2, 0x01000000u, __dp4a(w1, 0x01000000u, __dp4a(w0, 0x01000000u, a0))));
-                const uint32_t o1 = __dp4a(w3, 0x00010000u, __dp4a(w2, 0x00010000u, __dp4a(w1, 0x00010000u, __dp4a(w0, 0x00010000u, a1))));
                 const uint32_t o2 = __dp4a(w3, 0x00000100u, __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00000100u, a2))));
-                const uint32_t o3 = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x00000001u, __dp4a(w1, 0x00000001u, __dp4a(w0, 0x00000001u, a3))));
+                const uint32_t ev = ((w0 & 0x00FF00FFu) + (w1 & 0x00FF00FFu)) + ((w2 & 0x00FF00FFu) + (w3 & 0x00FF00FFu));
+                const uint32_t o1 = a1 + (ev >> 16), o3 = a3 + (ev & 0xFFFFu);
                 sts128(outb + (uint32_t)jl * 16u, o0, o1, o2, o3);
                 // trinucleotide bin 16 (sg & 3) + jl: sg & 3 alternates between two values inside a group
                 tri_acc[2 * h + t] += (o0 + o1) + (o2 + o3);
@@ -621,10 +632,12 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
         }
     }
 #ifdef DIG_LB_TIMING
+    LB_T(t_k1);
+    LB_ACC(14, t_k0, t_k1);
     if (A.timing != nullptr && lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 11; ++q)
-            if (q != 7) atomicAdd(A.timing + q, tacc[q]);
+        for (int q = 0; q < 15; ++q)
+            if (q != 7 && q != 11 && q != 12) atomicAdd(A.timing + q, tacc[q]);
     }
 #endif
 }

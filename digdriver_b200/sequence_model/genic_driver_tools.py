@@ -313,7 +313,6 @@ def tiled_model_parallel(f_pretrained, f_nonc_data, save_key, N_procs=1):
     """Reference :692-719 on the directory/HDF5 stores (L_counts written by DigPreprocess.py preprocess_tiled)."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
-    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     wkey = 'window_{}'.format(rm.window)
@@ -340,7 +339,6 @@ def tiled_nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key):
     """Reference :599-690: the tiled pretrain rows of the tiles in ``elt_lst`` ('chr{c}:{s}-{e}' names)."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
-    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     wkey = 'window_{}'.format(rm.window)
@@ -370,7 +368,6 @@ def nonc_model(elt_lst, f_pretrained, f_nonc_data, save_key, indels_direct):
     preprocess_sites (L_counts, region_counts and the overlap list of every element)."""
     pre = storage.Store(f_pretrained, "r")
     rm = RegionModel(pre.read_table('region_params'))
-    rm_ind = RegionModel(pre.read_table('region_params_indels')) if indels_direct else None     # reference :316-317
     d_pr = sequence_tools.d_pr_from_model192(pre.read_table('sequence_model_192'))
     data = storage.Store(f_nonc_data, "r")
     names, L, R, overlaps = data.read_element_groups('window_{}/{}'.format(rm.window, save_key), list(elt_lst))

@@ -51,6 +51,7 @@ for variant, name in ((_lib.SCAN_HEX, "per-warp hexamer"), (_lib.SCAN_AUTO, "lan
         n_chunks = 5 * ((len(wins) + 31) // 32)
         print("    copy latency (issued -> FULL complete, producer warp 0): %.0f cycles per chunk; issue %.0f; producer idle %.0f"
               % (t[7] / n_chunks, t[12] / n_chunks, t[11] / n_chunks))
+        print("    geometry %.0f (%.1f%%); whole consumer loop %.0f cycles per warp" % (t[13] / nwarp, 100 * t[13] / t[14], t[14] / nwarp))
         nb_ = (len(wins) + 31) // 32
         print("    FULL wait per consumer warp and chunk: first %.0f, second %.0f, later %.0f cycles"
               % (t[8] / 16 / nb_, t[9] / 16 / nb_, t[10] / 16 / nb_ / 3))
