@@ -23,6 +23,7 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 total = int(float(args[0])) if args else 3_100_000_000
 lengths = G.hg19_like_lengths(total)
 names = ["chr%d" % (i + 1) for i in range(22)]
+print(torch.cuda.get_device_properties(0).name, torch.cuda.get_device_properties(0).uuid, flush=True)
 dg = G.DeviceGenome.synthetic(names, lengths, seed=1)
 W = 10_000
 TW = 0 if "--no-hint" in sys.argv else W
@@ -70,10 +71,34 @@ for variant, name in ((_lib.SCAN_HEX, "per-warp hexamer"), (_lib.SCAN_AUTO, "lan
     fn3 = lambda: kernels.count_contexts(dg, rc, rs, re, 2, 2, out=o, variant=variant, workspace=ws, tile_window=TW)
     best, med = timeit(fn3)
     print("penta no totals %-10s best %.3f ms" % (name, best), flush=True)
+if "--repeat" in sys.argv:          # race hunt: the lane-bank result must be identical every time
+    n_rep = int(sys.argv[sys.argv.index("--repeat") + 1])
+    want5, want3 = res[_lib.SCAN_HEX][0], res[_lib.SCAN_HEX][1]
+    o5 = torch.empty_like(want5); o3 = torch.empty_like(want3)
+    nbad = 0
+    for it in range(n_rep):
+        tt5 = torch.zeros(1024, dtype=torch.int64, device="cuda") if it % 2 == 0 else None
+        tt3 = torch.zeros(64, dtype=torch.int64, device="cuda") if it % 2 == 0 else None
+        kernels.count_contexts_fused53(dg, rc, rs, re, out5=o5, out3=o3, totals5=tt5, totals3=tt3, variant=_lib.SCAN_AUTO,
+                                       workspace=ws, tile_window=TW)
+        torch.cuda.synchronize()
+        bad = torch.nonzero((o5 != want5).any(dim=1)).flatten()
+        if bad.numel():
+            nbad += 1
+            print("  repeat %d (totals %s): %d bad rows %s (batch %s lane-window %s)" % (it, it % 2 == 0, bad.numel(), bad[:6].tolist(), (bad[:6] // 32).tolist(), (bad[:6] % 32).tolist()), flush=True)
+    print("  repeats with differences: %d of %d" % (nbad, n_rep), flush=True)
 for k, nm in enumerate(("counts5", "counts3", "totals5", "totals3")):
     a, b = res[_lib.SCAN_AUTO][k], res[_lib.SCAN_HEX][k]
     eq = bool(torch.equal(a, b))
     print("  %s equal: %s" % (nm, eq), flush=True)
+    if not eq and a.dim() == 2 and k == 0:
+        # which side is unstable?  run both again
+        o5b = torch.empty_like(a); o3b = torch.empty((len(wins), 64), dtype=torch.int32, device="cuda")
+        for vv, nm2, ref in ((_lib.SCAN_HEX, "per-warp", b), (_lib.SCAN_AUTO, "lane-bank", a)):
+            kernels.count_contexts_fused53(dg, rc, rs, re, out5=o5b, out3=o3b, variant=vv, workspace=ws, tile_window=TW)
+            torch.cuda.synchronize()
+            print("    rerun %s: equals its first run: %s; equals the other kernel's first run: %s"
+                  % (nm2, bool(torch.equal(o5b, ref)), bool(torch.equal(o5b, b if vv == _lib.SCAN_AUTO else a))), flush=True)
     if not eq and a.dim() == 2:
         badrows = torch.nonzero((a != b).any(dim=1)).flatten()
         print("    %d bad rows, first %s" % (badrows.numel(), badrows[:10].tolist()), flush=True)
