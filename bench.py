@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--bases", type=float, default=3.1e9, help="genome size per GPU (debug override)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-sample", action="store_true")
     return ap.parse_args()
 
 
@@ -298,7 +299,9 @@ def test_stage(dg, di, d, dist_ctx, sink=None):
     if not torch.cuda.is_current_stream_capturing():
         obs.record_stream(main)          # allocated on the side stream, consumed on the main one
         nsamp.record_stream(main)
-    return pipeline.gene_burden_test(pre, obs, nsamp, d["n_syn"], collectives=dist_ctx)
+    res = pipeline.gene_burden_test(pre, obs, nsamp, d["n_syn"], collectives=dist_ctx)
+    res["D_PR"], res["CTX"] = d_pr, ctx                  # for the parity sample (outside the timed region)
+    return res
 
 
 def hot_path_step(dg, di, d, dist_ctx, ev=None):
@@ -362,6 +365,24 @@ class GraphedStep:
         """Reads the device status words of the stage (one host synchronisation, outside the timed region)."""
         from digdriver_b200 import kernels
         kernels.check_deferred(self.sink)
+
+
+def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
+    """Post-timing self-check at full size: ~500 windows drawn over the whole 3.1 Gb genome (chromosomes beyond 2^31 in
+    global coordinates included), the SNVs inside them and ~200 genes are recomputed by the CPU oracle from
+    regenerated slices of the synthetic genome and compared with this run's results (oracle/parity_sample.py)."""
+    import torch
+    from oracle import parity_sample as ps
+    dev = dg.device
+    rows = lambda t: (lambda idx: t[torch.from_numpy(np.asarray(idx)).to(dev)].cpu().numpy())
+    got = {"counts5": rows(di.counts5), "counts3": rows(di.counts3), "ctx": res["CTX"].cpu().numpy(),
+           "d_pr": res["D_PR"].cpu().numpy(), "sums": res["SUMS"].cpu().numpy(), "n_syn": d["n_syn"]}
+    for k in ("MU", "SIGMA", "Pi_SYN", "Pi_MIS", "Pi_NONS", "Pi_SPL", "Pi_TRUNC", "Pi_NONSYN", "ALPHA", "THETA", "OBS_SYN",
+              "OBS_MIS", "OBS_NONS", "OBS_SPL", "PVAL_INDEL_BURDEN", "PVAL_MUT_BURDEN"):
+        got[k] = res[k].cpu().numpy()
+    for c in ps.CLASSES:
+        got["PVAL_%s_BURDEN" % c] = res["PVAL_%s_BURDEN" % c].cpu().numpy()
+    return ps.check_sample(d["lengths"], dg.chrom_off, seed, WINDOW, d, got, n_windows=n_windows, n_genes=n_genes)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -633,6 +654,14 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = n_scanned * world / (ms_per_step * 1e-3)
 
+    # ---- parity at full size, outside every timed region (rank 0; the oracle regenerates the slices it needs)
+    parity = None
+    if rank == 0 and not args.no_parity_sample:
+        try:
+            parity = parity_sample(dg, d, di, res, seed=1 + rank)
+        except Exception as exc:      # report, never hide
+            parity = {"ok": False, "detail": "parity sample failed to run: %r" % (exc,)}
+
     # ---- e2e leg: host buffers in and out
     e2e = None
     if not args.no_e2e:
@@ -713,7 +742,7 @@ def main():
             "cuda_graph": {"test_stage_captured": stepper.graph is not None, "error": stepper.error},
             "host_placement": placement,
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline}
+            "cpu_baseline": cpu_baseline, "parity_sample": parity}
     emit_json(line)
     finish()
 

@@ -23,11 +23,15 @@ __global__ void __launch_bounds__(1024) gene_scale_sums_kernel(
 #pragma unroll 4
     for (int64_t g = threadIdx.x; g < n; g += 1024) {
         const double m = mu[g], s = sigma[g];
-        if (g != tp53) a0 += m * P[g * 4 + 0];
+        // pandas' Series.sum() skips NaN (skipna=True): a gene whose windows hold no countable context (P = NaN)
+        // must not poison the cohort-wide scale factors (transfer_tools.py:814, :699-700)
+        const double t0 = m * P[g * 4 + 0];
+        if (g != tp53 && !isnan(t0)) a0 += t0;
         if (cgc == nullptr || !cgc[g]) {
             const double alpha = (m * m) / (s * s);
             const double theta = (s * s) / m;
-            a1 += pi_indel[g] * alpha * theta;
+            const double t1 = pi_indel[g] * alpha * theta;
+            if (!isnan(t1)) a1 += t1;
             a2 += (double)obs[g * 5 + 4];
         }
     }

@@ -96,6 +96,13 @@ __device__ __forceinline__ void mbar_arrive_tx(uint32_t a, uint32_t tx)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(tx) : "memory");
 }
+// "I have finished READING" arrival: `dep` must be computed from every value that was loaded.  An arrive is not ordered
+// after shared-memory loads that are still in flight -- a load queued behind other warps' atomics can be overtaken --
+// so the arrival is made data-dependent on the loads: it cannot issue before they have returned.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t a, uint32_t dep)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(a), "r"(dep) : "memory");
+}
 __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity)
 {
     uint32_t ok;
@@ -511,8 +518,11 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 M[0] = m.x; M[1] = m.y; M[2] = m.z; M[3] = m.w;
                 M[4] = lds32(mptr + 16u);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar + 8u * (BAR_EMPTY + stage));      // the stage is in registers now
+            // the stage may be refilled as soon as all sixteen warps have arrived: only after the loads have RETURNED
+            uint32_t dep = (D[0] | D[1] | D[2]) ^ (D[3] | D[4] | D[5]) ^ (D[6] | D[7] | D[8]) ^ (M[0] | M[1] | M[2]) ^ (M[3] | M[4]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dep |= __shfl_xor_sync(0xffffffffu, dep, o);    // every lane's loads
+            if (lane == 0) mbar_arrive_after_loads(bar + 8u * (BAR_EMPTY + stage), dep);
             if (!clean) {                                                    // the writer warps have re-zeroed the tables
                 LB_T(t_c);
                 mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);
@@ -710,10 +720,16 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
                     tmp5[2 * s4 + 1] += v.y;
                 }
             }
+            uint32_t dep = 0u;
+            if constexpr (TOT) {
+                dep = tmp5[2 * s4] | tmp5[2 * s4 + 1];                       // the column sums have consumed their loads
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dep |= __shfl_xor_sync(0xffffffffu, dep, o);
+            }
             __syncwarp();
             if (lane == 0) {
                 bulk_wait_read<0>();                                         // the tile has left shared memory
-                mbar_arrive(bar + 8u * (BAR_OUTEMPTY + q));
+                mbar_arrive_after_loads(bar + 8u * (BAR_OUTEMPTY + q), dep);
             }
             __syncwarp();
         }
@@ -722,6 +738,7 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
 #pragma unroll 8
         for (int i = 0; i < 64; ++i)
             sts128(sbase + OFF_TAB + (uint32_t)q * 32768u + (uint32_t)(lane + 32 * i) * 16u, 0u, 0u, 0u, 0u);
+        __threadfence_block();                                               // the zeros are in place before anybody is told
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + 8u * BAR_CLEAN);
         if (q == 0) {

@@ -334,3 +334,36 @@ def test_config3_per_site_test_30m_sites(world, oracle):
     with pytest.raises(KeyError):
         kernels.site_test([3], [int(lengths[2]) + 50_000], [5], [0.0], 10_000, m["off"], m["wmap"], m["c64"], m["y_pred"],
                           m["std"], d_pr, device=dev)
+
+
+def test_config2_parity_sample_at_full_size(oracle):
+    """BASELINE config 2 AT SIZE (3.1 Gb, 310 k windows, 1 M SNVs, 20 k genes): ~500 windows drawn uniformly over
+    the whole genome -- chromosomes whose global offset exceeds 2^31 included --, the SNVs inside them and ~200 genes
+    are recomputed by the CPU oracle from regenerated slices of the synthetic genome (oracle/parity_sample.py) and
+    compared with the full GPU run: count rows and mutation contexts bit-exact, pretrain columns to 1e-9, the 13 NB
+    p-values and the Fisher combination to 1e-6 in log10.  The same check runs inside bench.py after the timed
+    region (`parity_sample` in its JSON line)."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    dev = torch.device(DEV)
+    dg, ascii_d, d = bench.build_workload(3.1e9, seed=1, device=dev)
+    del ascii_d
+    di = bench.DeviceInputs(d, dev)
+    res = bench.hot_path_step(dg, di, d, None)
+    torch.cuda.synchronize()
+    out = bench.parity_sample(dg, d, di, res, seed=1, n_windows=500, n_genes=200)
+    assert out["ok"], out
+    assert out["windows"] == 500 and out["genes"] == 200
+    assert out["windows_beyond_2^31"] > 50, out           # ~30 % of hg19 lies beyond 2^31
+    assert out["mutations"] > 500 and out["p_values"] > 500, out
+    # the lane-bank kernel and the per-warp kernel agree on every row of the full table (a checksum of checksums)
+    from digdriver_b200 import kernels, _lib
+    c5 = torch.empty_like(di.counts5)
+    c3 = torch.empty_like(di.counts3)
+    kernels.count_contexts_fused53(dg, di.win_chrom, di.win_start, di.win_end, out5=c5, out3=c3, variant=_lib.SCAN_HEX)
+    assert torch.equal(c5, di.counts5) and torch.equal(c3, di.counts3)
+    assert int(di.counts5.sum(dim=1).max()) <= bench.WINDOW

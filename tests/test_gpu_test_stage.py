@@ -339,6 +339,18 @@ def test_fused_gene_test_kernels_golden():
     # scale by expectation: cj = n_syn / sums[0]
     out2 = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, 1234.0).cpu().numpy()
     np.testing.assert_allclose(out2[22], z["pre_THETA"] * (1234.0 / s[0]), rtol=1e-14)
+    # a gene without countable context has P = NaN; the reference's sums are pandas Series.sum(), which skips NaN
+    # (transfer_tools.py:814, :699): such a row must not turn the cohort-wide scale factors into NaN
+    import pandas as pd
+    P2, pi2 = P.clone(), pi_indel.clone()
+    P2[3, :] = float("nan")
+    pi2[5] = float("nan")
+    s2 = kernels.gene_scale_sums(mu, sigma, P2, pi2, obs, cgc, genes.index("TP53")).cpu().numpy()
+    syn2 = z["pre_Pi_SYN"].copy(); syn2[3] = np.nan
+    ind2 = z["pre_Pi_INDEL"].copy(); ind2[5] = np.nan
+    np.testing.assert_allclose(s2[0], pd.Series((z["pre_MU"] * syn2)[keep]).sum(), rtol=1e-13)
+    np.testing.assert_allclose(s2[1], pd.Series((ind2 * z["pre_ALPHA_INDEL"] * z["pre_THETA_INDEL"])[~cgc]).sum(), rtol=1e-13)
+    assert np.isfinite(s2).all()
 
 
 def test_secondary_gene_tests_golden():

@@ -76,7 +76,13 @@ if "--repeat" in sys.argv:          # race hunt: the lane-bank result must be id
     want5, want3 = res[_lib.SCAN_HEX][0], res[_lib.SCAN_HEX][1]
     o5 = torch.empty_like(want5); o3 = torch.empty_like(want3)
     nbad = 0
+    cold = torch.empty(1 << 30, dtype=torch.uint8, device="cuda") if "--cold" in sys.argv else None
     for it in range(n_rep):
+        if cold is not None:
+            cold.fill_(it & 255)          # evict L2 (and most TLB entries) before every run
+            if it % 3 == 0:
+                ws = kernels.scan_workspace(dg, len(wins))
+                o5 = torch.empty_like(want5); o3 = torch.empty_like(want3)
         tt5 = torch.zeros(1024, dtype=torch.int64, device="cuda") if it % 2 == 0 else None
         tt3 = torch.zeros(64, dtype=torch.int64, device="cuda") if it % 2 == 0 else None
         kernels.count_contexts_fused53(dg, rc, rs, re, out5=o5, out3=o3, totals5=tt5, totals3=tt3, variant=_lib.SCAN_AUTO,
