@@ -41,6 +41,7 @@ N_SAMPLES = 200
 B_PER_BASE_K1024 = 0.25 + 0.125 + 4.0 * 1024 / WINDOW      # 0.7846 B/base
 B_PER_BASE_FUSED = 0.25 + 0.125 + 4.0 * (1024 + 64) / WINDOW  # both tables written by one pass: 0.8102
 B_PER_BASE_K64 = 0.25 + 0.125 + 4.0 * 64 / WINDOW
+SCAN_DRAM_TRAFFIC = 2.4667e9      # dram read + write bytes of one fused scan launch at 3.1 Gb (ncu --set full, profiles/)
 
 
 _JSON_OUT = None
@@ -62,6 +63,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-sample", action="store_true")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="N > 1: strong = ONE 3.1 Gb genome range-sharded over the ranks (default), weak = one genome per rank")
     return ap.parse_args()
 
 
@@ -251,21 +254,100 @@ class DeviceInputs:
 
 def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
     """Context maps + genome totals (K2) for windows [lo, hi): pentanucleotide and trinucleotide tables in one
-    fused pass (dig_count_contexts_fused53)."""
+    fused pass (dig_count_contexts_fused53).  Range-sharded runs (StrongShard) scan only the rank's slice, straight
+    into the rank's block of the buffer that is all-gathered afterwards."""
     from digdriver_b200 import kernels
-    hi = di.win_chrom.numel() if hi is None else hi
+    shard = getattr(di, "shard", None)
+    if shard is not None:
+        lo, hi = shard.lo, shard.hi
+        out5, out3, tot5, tot3 = di.counts5[lo:hi], shard.rows[: hi - lo], shard.tot5, shard.tot3
+    else:
+        hi = di.win_chrom.numel() if hi is None else hi
+        out5, out3, tot5, tot3 = di.counts5[lo:hi], di.counts3[lo:hi], di.totals5, di.totals3
     if zero:
-        di.totals5.zero_()
-        di.totals3.zero_()
+        tot5.zero_()
+        tot3.zero_()
     if ev is not None:
         ev[0].record()
     if getattr(di, "scan_ws", None) is None or di.scan_ws_n < hi - lo:
         di.scan_ws, di.scan_ws_n = kernels.scan_workspace(dg, hi - lo), hi - lo
-    kernels.count_contexts_fused53(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi],
-                                   out5=di.counts5[lo:hi], out3=di.counts3[lo:hi], totals5=di.totals5,
-                                   totals3=di.totals3, workspace=di.scan_ws, tile_window=WINDOW)
+    if hi > lo:
+        kernels.count_contexts_fused53(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi],
+                                       out5=out5, out3=out3, totals5=tot5, totals3=tot3, workspace=di.scan_ws,
+                                       tile_window=WINDOW)
     if ev is not None:
         ev[1].record()
+
+
+class StrongShard:
+    """ONE genome over all ranks (BASELINE north_star: "the 3.1 Gb genome is sharded by range over 8 GPUs").
+
+    Windows are cut into `world` contiguous slices of equal base count (sharding.partition_windows); a rank scans
+    only its slice.  Its trinucleotide rows and its partial genome totals are exchanged by ONE all_gather_into_tensor
+    (sharding.GatheredTable: the element stage reads the gathered buffer in place through a remapped window map);
+    the pentanucleotide rows stay range-sharded (their consumer is the host).  Genes belong to the rank whose slice
+    holds their first block (sharding.partition_elements) and are resolved against the gathered table, so a gene
+    that straddles a cut needs nothing else.  Mutation contexts (K3, 35 us for 1 M SNVs) are computed on every rank
+    -- cheaper than an all-reduce of the substitution counts; observed counts (K5) only for the rank's genes.
+    Further exchanges: all-reduce of the five scale-factor sums, all-gather of the result rows."""
+
+    def __init__(self, d, di, coll, device):
+        import torch
+        from digdriver_b200 import kernels, sharding
+        wins = d["wins"]
+        self.world, self.rank = coll.world, coll.rank
+        parts = sharding.partition_windows(wins[:, 1], wins[:, 2], self.world)
+        self.table = sharding.GatheredTable(parts)
+        self.lo, self.hi = parts[self.rank]
+        gt = self.table
+        self.local = torch.zeros((gt.block_rows, 64), dtype=torch.int32, device=device)
+        self.gathered = torch.zeros((self.world, gt.block_rows, 64), dtype=torch.int32, device=device)
+        self.rows, self.tot5, self.tot3 = gt.local_views(self.local)
+        off, wmap = gt.window_map(wins[:, 0], wins[:, 1], WINDOW, len(d["lengths"]))
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)
+        self.wmap_off, self.wmap = t(off, torch.int64), t(wmap, torch.int32)
+        row_of = gt.row_of_window(len(wins))
+        self.row_of = t(row_of, torch.int64)
+        n_rows = self.world * gt.block_rows
+
+        def relay(x, dt):                  # region parameters in the row order of the gathered buffer
+            out = torch.zeros(n_rows, dtype=dt, device=device)
+            out[self.row_of] = x.to(dt)
+            return out
+        self.y_pred_g, self.std_g, self.y_true_g = (relay(x, torch.float64) for x in (di.y_pred, di.std, di.y_true))
+        self.flag_g = relay(di.flag, torch.uint8)
+        # genes of this rank
+        g_ptr = d["g_ptr"]
+        owner = sharding.partition_elements(d["g_chrom"], d["g_bs"][g_ptr[:-1]], wins[:, 0], wins[:, 1], wins[:, 2], parts)
+        assert (owner >= 0).all(), "a gene starts outside every window"
+        self.gene_ids = np.flatnonzero(owner == self.rank)
+        self.genes_per_rank = [int((owner == r).sum()) for r in range(self.world)]
+        nb = np.diff(g_ptr)[self.gene_ids]
+        ptr = np.zeros(len(self.gene_ids) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum(nb)
+        bsel = np.concatenate([np.arange(g_ptr[g], g_ptr[g + 1]) for g in self.gene_ids]) if len(self.gene_ids) else \
+            np.zeros(0, dtype=np.int64)
+        self.g_chrom, self.g_strand = t(d["g_chrom"][self.gene_ids], torch.int32), t(d["g_strand"][self.gene_ids], torch.int8)
+        self.g_ptr, self.g_bs, self.g_be = t(ptr, torch.int64), t(d["g_bs"][bsel], torch.int64), t(d["g_be"][bsel], torch.int64)
+        self.L = t(d["L"][self.gene_ids], torch.float64)
+        self.n_genes = len(self.gene_ids)
+        self.max_span = kernels.element_max_span(ptr, d["g_bs"][bsel], d["g_be"][bsel], WINDOW)
+        # mutations of this rank's genes, with local gene ids (K5)
+        local_id = np.full(N_GENES, -1, dtype=np.int64)
+        local_id[self.gene_ids] = np.arange(self.n_genes)
+        mg = d["m_gene"]
+        mine = (mg >= 0) & (local_id[np.clip(mg, 0, N_GENES - 1)] >= 0)
+        self.m_gene = t(local_id[mg[mine]], torch.int32)
+        self.m_sample, self.m_cls = t(d["m_sample"][mine], torch.int32), t(d["m_cls"][mine], torch.uint8)
+        self.n_syn = int(((d["m_cls"][mine] == 0)).sum())
+        self.exchange_bytes = int(self.gathered.numel() * 4)
+
+    def all_gather_table(self):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.gathered.view(-1, 64), self.local)
+
+    def totals(self):
+        return self.table.summed_totals(self.gathered)
 
 
 def test_stage(dg, di, d, dist_ctx, sink=None):
@@ -279,6 +361,9 @@ def test_stage(dg, di, d, dist_ctx, sink=None):
     # this becomes two parallel branches
     main = torch.cuda.current_stream(dev)
     side = di.side_stream
+    shard = getattr(di, "shard", None)
+    if shard is not None:
+        return strong_test_stage(dg, di, d, dist_ctx, shard, sink)
     side.wait_stream(main)
     with torch.cuda.stream(side):
         obs, nsamp = kernels.tabulate_genes(di.m_gene, di.m_sample, di.m_cls, N_GENES, device=dev, status_sink=sink)
@@ -304,6 +389,45 @@ def test_stage(dg, di, d, dist_ctx, sink=None):
     return res
 
 
+def strong_test_stage(dg, di, d, dist_ctx, shard, sink):
+    """The test stage of a range-sharded run: table exchange, then this rank's genes (see StrongShard)."""
+    import torch
+    from digdriver_b200 import kernels, pipeline
+    dev = dg.device
+    main = torch.cuda.current_stream(dev)
+    side = di.side_stream
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        # nothing below depends on the scan: observed counts of the rank's genes and the sequence model's numerator
+        obs, nsamp = kernels.tabulate_genes(shard.m_gene, shard.m_sample, shard.m_cls, max(shard.n_genes, 1), device=dev,
+                                            status_sink=sink)
+        if getattr(shard, "k3_by_range", None) is None:
+            ctx = kernels.mutation_contexts(dg, di.m_chrom, di.m_pos, di.m_ref, 1, 1)
+            sub = kernels.substitution_counts(ctx, di.m_alt, 1, 1)
+        else:
+            # e2e leg: only the chromosomes of the rank's slice are resident, so the rank handles the mutations
+            # inside its slice and the 192 counts are all-reduced
+            mc, mp, mr, ma = shard.k3_by_range
+            ctx = kernels.mutation_contexts(dg, mc, mp, mr, 1, 1)
+            sub = kernels.substitution_counts(ctx, ma, 1, 1)
+    shard.all_gather_table()                             # THE exchange: trinucleotide rows + partial totals, one collective
+    tot = shard.totals()
+    main.wait_stream(side)
+    if not torch.cuda.is_current_stream_capturing():
+        for t in (obs, nsamp, ctx, sub):
+            t.record_stream(main)
+    if getattr(shard, "k3_by_range", None) is not None:
+        dist_ctx.all_reduce_sum(sub)
+    d_pr = kernels.sequence_freq(sub.contiguous(), tot[1024:1088].contiguous())
+    pre = kernels.element_transfer(shard.g_chrom, shard.g_strand, shard.g_ptr, shard.g_bs, shard.g_be, WINDOW,
+                                   shard.wmap_off, shard.wmap, shard.gathered.view(-1, 64), shard.y_pred_g, shard.std_g,
+                                   shard.y_true_g, shard.flag_g, d_pr, L_elt=shard.L, device=dev,
+                                   max_span=shard.max_span, status_sink=sink)
+    res = pipeline.gene_burden_test(pre, obs, nsamp, shard.n_syn, collectives=dist_ctx)
+    res["D_PR"], res["CTX"], res["TOTALS"] = d_pr, ctx, tot
+    return res
+
+
 def hot_path_step(dg, di, d, dist_ctx, ev=None):
     """One pass of the whole path on device-resident inputs.  Returns the per-gene result dict."""
     scan_stage(dg, di, ev)
@@ -313,6 +437,21 @@ def hot_path_step(dg, di, d, dist_ctx, ev=None):
 def gather_results(coll, t):
     """Per-gene results of every shard on rank 0 (the reference's pd.concat of chunk results)."""
     return coll.gather_rows(t.unsqueeze(1), sizes=[N_GENES] * coll.world)
+
+
+def result_columns():
+    from digdriver_b200 import pipeline
+    return ["PVAL_%s_BURDEN" % c for c in pipeline.GENE_CLASSES] + ["PVAL_%s_BURDEN_SAMPLE" % c for c in pipeline.GENE_CLASSES] + \
+           ["PVAL_INDEL_BURDEN", "PVAL_MUT_BURDEN"]
+
+
+def gather_strong_results(coll, shard, res):
+    """The 14 p-value columns of every rank's genes on every rank: one all_gather_into_tensor of padded row blocks
+    (rows are in owner-rank order; StrongShard.gene_ids maps them back to the annotation's order)."""
+    import torch
+    from digdriver_b200 import sharding
+    rows = torch.stack([res[c] for c in result_columns()], dim=1)
+    return sharding.all_gather_rows(coll, rows, shard.genes_per_rank)
 
 
 class GraphedStep:
@@ -350,7 +489,10 @@ class GraphedStep:
 
     def _stage(self):
         self.res = test_stage(self.dg, self.di, self.d, self.dist_ctx, sink=self.sink)
-        if self.dist_ctx is not None:
+        shard = getattr(self.di, "shard", None)
+        if shard is not None:
+            self.gathered = gather_strong_results(self.dist_ctx, shard, self.res)
+        elif self.dist_ctx is not None:
             self.gathered = gather_results(self.dist_ctx, self.res["PVAL_MUT_BURDEN"])
 
     def step(self, ev=None):
@@ -374,15 +516,41 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
     import torch
     from oracle import parity_sample as ps
     dev = dg.device
+    shard = getattr(di, "shard", None)
     rows = lambda t: (lambda idx: t[torch.from_numpy(np.asarray(idx)).to(dev)].cpu().numpy())
-    got = {"counts5": rows(di.counts5), "counts3": rows(di.counts3), "ctx": res["CTX"].cpu().numpy(),
-           "d_pr": res["D_PR"].cpu().numpy(), "sums": res["SUMS"].cpu().numpy(), "n_syn": d["n_syn"]}
-    for k in ("MU", "SIGMA", "Pi_SYN", "Pi_MIS", "Pi_NONS", "Pi_SPL", "Pi_TRUNC", "Pi_NONSYN", "ALPHA", "THETA", "OBS_SYN",
-              "OBS_MIS", "OBS_NONS", "OBS_SPL", "PVAL_INDEL_BURDEN", "PVAL_MUT_BURDEN"):
-        got[k] = res[k].cpu().numpy()
-    for c in ps.CLASSES:
-        got["PVAL_%s_BURDEN" % c] = res["PVAL_%s_BURDEN" % c].cpu().numpy()
-    return ps.check_sample(d["lengths"], dg.chrom_off, seed, WINDOW, d, got, n_windows=n_windows, n_genes=n_genes)
+    cols = ["MU", "SIGMA", "Pi_SYN", "Pi_MIS", "Pi_NONS", "Pi_SPL", "Pi_TRUNC", "Pi_NONSYN", "ALPHA", "THETA", "OBS_SYN",
+            "OBS_MIS", "OBS_NONS", "OBS_SPL", "PVAL_INDEL_BURDEN", "PVAL_MUT_BURDEN"] + ["PVAL_%s_BURDEN" % c for c in ps.CLASSES]
+    if shard is None:
+        got = {"counts5": rows(di.counts5), "counts3": rows(di.counts3), "n_syn": d["n_syn"]}
+        for k in cols:
+            got[k] = res[k].cpu().numpy()
+        pools = {}
+    else:
+        # range-sharded run: pentanucleotide rows of the rank's own windows; trinucleotide rows are read from the
+        # all-gathered buffer (so windows scanned by OTHER ranks are checked too); per-gene columns of the rank's genes
+        tab = shard.gathered.view(-1, 64)
+        got = {"counts5": rows(di.counts5),
+               "counts3": lambda idx: tab[shard.row_of[torch.from_numpy(np.asarray(idx)).to(dev)]].cpu().numpy(),
+               "n_syn": float(res["SUMS"][3].item())}         # the all-reduced synonymous count the kernel used
+        for k in cols:
+            full = np.full(N_GENES, np.nan)
+            full[shard.gene_ids] = res[k].cpu().numpy()
+            got[k] = full
+        pools = {"win_pool": np.arange(shard.lo, shard.hi), "gene_pool": shard.gene_ids}
+    got.update({"ctx": res["CTX"].cpu().numpy(), "d_pr": res["D_PR"].cpu().numpy(), "sums": res["SUMS"].cpu().numpy()})
+    out = ps.check_sample(d["lengths"], dg.chrom_off, seed, WINDOW, d, got, n_windows=n_windows, n_genes=n_genes, **pools)
+    if shard is not None:
+        # rows of windows scanned by the OTHER ranks, as they arrived through the exchange
+        other = np.setdiff1d(np.arange(len(d["wins"])), pools["win_pool"])
+        if len(other):
+            idx = np.sort(np.random.default_rng(1).choice(other, size=min(100, len(other)), replace=False))
+            _, c3, _ = ps.window_rows(d["lengths"], dg.chrom_off, seed, d["wins"], idx)
+            same = bool(np.array_equal(np.asarray(got["counts3"](idx), dtype=np.int64), c3))
+            out["gathered_rows_checked"] = int(len(idx))
+            if not same:
+                out["ok"] = False
+                out["detail"] += "; all-gathered trinucleotide rows differ"
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -390,102 +558,134 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
 # ------------------------------------------------------------------------------------------------
 
 class HostPath:
-    """The step through the host-buffer API: pinned ASCII genome -> H2D (per chromosome, overlapped with
-    packing) -> scans -> D2H of both context tables; mutation/gene tables H2D; p-values D2H."""
+    """The step through the host-buffer API of the package: digdriver_b200.host_pipeline.HostScan (pinned host genome
+    -> per-chromosome H2D / pack / fused scan / uint16 narrowing / D2H on three streams) followed by the test stage on
+    mutation and gene tables that also start in pinned host memory; p-values and totals end in host memory.
 
-    def __init__(self, ascii_d, dg, d, device):
+    source = "packed": the packed-genome cache (packed2 + N mask, 0.375 B/base) that get_device_genome /
+    countGenomeContext keep next to the FASTA -- what every run after the first uploads;
+    source = "ascii": the cold path, the FASTA's bytes (1 B/base) packed on the device."""
+
+    def __init__(self, host_genome, d, di, device, shard=None):
         import torch
-        self.device = device
-        self.dg = dg
-        self.d = d
-        n = dg.n_bases
-        self.host_ascii = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        self.host_ascii.copy_(ascii_d)
-        self.dev_ascii = torch.empty(n, dtype=torch.uint8, device=device)
-        n_win = len(d["wins"])
-        self.host_counts5 = torch.empty((n_win, 1024), dtype=torch.int32, pin_memory=True)
-        self.host_counts3 = torch.empty((n_win, 64), dtype=torch.int32, pin_memory=True)
+        from digdriver_b200 import host_pipeline
+        self.device, self.d, self.shard = device, d, shard
+        wins = d["wins"]
+        if shard is not None:
+            wins = wins[shard.lo:shard.hi]
+        self.scan = host_pipeline.HostScan(host_genome, wins, device, tile_window=WINDOW,
+                                           upload_all=shard is None)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        self.host_in = {k: pin(d[k]) for k in ("y_pred", "std", "y_true", "g_chrom", "g_strand", "g_ptr", "g_bs",
-                                                "g_be", "L", "m_chrom", "m_pos", "m_ref", "m_alt", "m_gene",
-                                                "m_cls", "m_sample")}
-        self.host_in["flag"] = pin(d["flag"].astype(np.uint8))
-        self.host_in["wins"] = pin(d["wins"])
-        self.host_out = torch.empty((14, N_GENES), dtype=torch.float64, pin_memory=True)
-        self.host_tot = torch.empty(1024 + 64, dtype=torch.int64, pin_memory=True)
-        self.copy_stream = torch.cuda.Stream(device)
-        self.out_stream = torch.cuda.Stream(device)
-        self.h2d_bytes = n + sum(v.numel() * v.element_size() for v in self.host_in.values())
-        self.d2h_bytes = (self.host_counts5.numel() + self.host_counts3.numel()) * 4 + self.host_out.numel() * 8 + \
-            (1024 + 64) * 8
+        if shard is None:
+            self.host_in = {k: pin(d[k]) for k in ("y_pred", "std", "y_true", "g_chrom", "g_strand", "g_ptr", "g_bs",
+                                                    "g_be", "L", "m_chrom", "m_pos", "m_ref", "m_alt", "m_gene",
+                                                    "m_cls", "m_sample")}
+            self.host_in["flag"] = pin(d["flag"].astype(np.uint8))
+            n_out = N_GENES
+        else:
+            # range-sharded: this rank's genes and their mutations, the mutations inside its window slice (K3), and
+            # the region parameters of all windows (2.5 MB each; K6 may touch a neighbour's windows)
+            # (a mutation belongs to the rank whose slice starts at or before it: the untiled tail of a chromosome
+            # goes with the chromosome's last window)
+            allw, parts = d["wins"], shard.table.parts
+            first_key = lambda r: (int(allw[parts[r][0], 0]) << 40) | int(allw[parts[r][0], 1])
+            lo_key = first_key(shard.rank) if shard.rank > 0 else -1
+            nxt = [r for r in range(shard.rank + 1, shard.world) if parts[r][1] > parts[r][0]]
+            hi_key = first_key(nxt[0]) if nxt else np.iinfo(np.int64).max
+            mk = (d["m_chrom"].astype(np.int64) << 40) | d["m_pos"]
+            sel = (mk >= lo_key) & (mk < hi_key)
+            cpu = lambda t: t.cpu()
+            self.host_in = {"y_pred_g": cpu(shard.y_pred_g).pin_memory(), "std_g": cpu(shard.std_g).pin_memory(),
+                            "y_true_g": cpu(shard.y_true_g).pin_memory(), "flag_g": cpu(shard.flag_g).pin_memory(),
+                            "g_chrom": cpu(shard.g_chrom).pin_memory(), "g_strand": cpu(shard.g_strand).pin_memory(),
+                            "g_ptr": cpu(shard.g_ptr).pin_memory(), "g_bs": cpu(shard.g_bs).pin_memory(),
+                            "g_be": cpu(shard.g_be).pin_memory(), "L": cpu(shard.L).pin_memory(),
+                            "m_gene": cpu(shard.m_gene).pin_memory(), "m_sample": cpu(shard.m_sample).pin_memory(),
+                            "m_cls": cpu(shard.m_cls).pin_memory(),
+                            "k3_chrom": pin(d["m_chrom"][sel]), "k3_pos": pin(d["m_pos"][sel]),
+                            "k3_ref": pin(d["m_ref"][sel]), "k3_alt": pin(d["m_alt"][sel])}
+            n_out = max(shard.n_genes, 1)
+        self.host_out = torch.empty((n_out, 14), dtype=torch.float64, pin_memory=True)
+        self.table_stream = torch.cuda.Stream(device)
+        self.h2d_bytes = self.scan.h2d_bytes + sum(v.numel() * v.element_size() for v in self.host_in.values())
+        self.d2h_bytes = self.scan.d2h_bytes + self.host_out.numel() * 8
+        self.launches = 0
 
     def step(self, di):
-        """H2D, pack, scan and D2H are pipelined per chromosome on three streams: while chromosome c is being
-        scanned, chromosome c+1 is on its way in and the count rows of chromosome c-1 are on their way out."""
+        import copy
         import torch
-        from digdriver_b200 import _lib, kernels, pipeline
-        dg, dev, d = self.dg, self.device, self.d
+        from digdriver_b200 import _lib, kernels
+        dev, d, hs, shard = self.device, self.d, self.scan, self.shard
+        n0 = _lib.launch_count
         main = torch.cuda.current_stream(dev)
-        bounds = list(dg.chrom_off) + [dg.n_bases]
-        wins = d["wins"]
-        wlo = np.searchsorted(wins[:, 0], np.arange(len(dg.chrom_off)), side="left")
-        whi = np.searchsorted(wins[:, 0], np.arange(len(dg.chrom_off)), side="right")
-        self.copy_stream.wait_stream(main)
-        self.out_stream.wait_stream(main)
-        # small tables first (they are needed only by the test stage)
-        with torch.cuda.stream(self.copy_stream):
+        self.table_stream.wait_stream(main)
+        with torch.cuda.stream(self.table_stream):          # small tables ride next to the genome
             t = {k: v.to(dev, non_blocking=True) for k, v in self.host_in.items()}
             ev_tables = torch.cuda.Event()
-            ev_tables.record(self.copy_stream)
+            ev_tables.record(self.table_stream)
+        hs.run(sync=False)
         main.wait_event(ev_tables)
-        w = t["wins"]
-        di.win_chrom, di.win_start, di.win_end = w[:, 0].to(torch.int32), w[:, 1].contiguous(), w[:, 2].contiguous()
-        di.totals5.zero_()
-        di.totals3.zero_()
-        for c, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
-            with torch.cuda.stream(self.copy_stream):
-                self.dev_ascii[a:b].copy_(self.host_ascii[a:b], non_blocking=True)
-                e_in = torch.cuda.Event()
-                e_in.record(self.copy_stream)
-            main.wait_event(e_in)
-            _lib.call("dig_pack_genome", self.dev_ascii.data_ptr() + int(a), int(b - a),
-                      dg.packed2.data_ptr() + int(a) // 16 * 4, dg.nmask.data_ptr() + int(a) // 32 * 4, None,
-                      main.cuda_stream)
-            lo, hi = int(wlo[c]), int(whi[c])
-            if hi > lo:
-                scan_stage(dg, di, None, lo, hi, zero=False)
-                e_scan = torch.cuda.Event()
-                e_scan.record(main)
-                with torch.cuda.stream(self.out_stream):
-                    self.out_stream.wait_event(e_scan)
-                    self.host_counts5[lo:hi].copy_(di.counts5[lo:hi], non_blocking=True)
-                    self.host_counts3[lo:hi].copy_(di.counts3[lo:hi], non_blocking=True)
-        di.y_pred, di.std, di.y_true, di.flag = t["y_pred"], t["std"], t["y_true"], t["flag"]
-        di.g_chrom, di.g_strand, di.g_ptr, di.g_bs, di.g_be, di.L = (t[k] for k in ("g_chrom", "g_strand", "g_ptr",
-                                                                                    "g_bs", "g_be", "L"))
-        di.m_chrom, di.m_pos, di.m_ref, di.m_alt, di.m_gene, di.m_cls, di.m_sample = (
-            t[k] for k in ("m_chrom", "m_pos", "m_ref", "m_alt", "m_gene", "m_cls", "m_sample"))
+        di2 = copy.copy(di)
         sink = []
-        res = test_stage(dg, di, d, None, sink=sink)
-        cols = [res["PVAL_%s_BURDEN" % c] for c in pipeline.GENE_CLASSES] + \
-               [res["PVAL_%s_BURDEN_SAMPLE" % c] for c in pipeline.GENE_CLASSES] + \
-               [res["PVAL_INDEL_BURDEN"], res["PVAL_MUT_BURDEN"]]
-        self.host_out.copy_(torch.stack(cols), non_blocking=True)
-        self.host_tot.copy_(torch.cat([di.totals5, di.totals3]), non_blocking=True)
+        if shard is None:
+            for k in ("y_pred", "std", "y_true", "flag", "g_chrom", "g_strand", "g_ptr", "g_bs", "g_be", "L", "m_chrom",
+                      "m_pos", "m_ref", "m_alt", "m_gene", "m_cls", "m_sample"):
+                setattr(di2, k, t[k])
+            di2.counts3, di2.totals5, di2.totals3 = hs.counts3, hs.totals, hs.totals3
+            res = test_stage(hs.genome, di2, d, None, sink=sink)
+        else:
+            sh = copy.copy(shard)
+            for k in ("y_pred_g", "std_g", "y_true_g", "flag_g", "g_chrom", "g_strand", "g_ptr", "g_bs", "g_be", "L",
+                      "m_gene", "m_sample", "m_cls"):
+                setattr(sh, k, t[k])
+            sh.k3_by_range = (t["k3_chrom"], t["k3_pos"], t["k3_ref"], t["k3_alt"])
+            n_loc = shard.hi - shard.lo
+            sh.rows[:n_loc].copy_(hs.counts3)                 # into this rank's block of the exchange buffer
+            sh.tot5.copy_(hs.totals)
+            sh.tot3.copy_(hs.totals3)
+            di2.shard = sh
+            from digdriver_b200.sharding import Collectives
+            res = test_stage(hs.genome, di2, d, Collectives(), sink=sink)
+        self.host_out.copy_(torch.stack([res[c] for c in result_columns()], dim=1), non_blocking=True)
         torch.cuda.synchronize(dev)
+        hs.finish()
         kernels.check_deferred(sink)
-        return self.host_tot
+        self.launches = _lib.launch_count - n0
+        return self.host_out
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
 
+def _py_mutation_contexts(seq, pos, ref, n_up=1, n_down=1):
+    """The reference's per-mutation loop (mutation_contexts_by_chrom, sequence_tools.py:130-178) on an in-memory
+    chromosome string: fetch + upper per row, REF check, N check, same-START reuse."""
+    out, prev_start, prev = [], None, None
+    for st, r in zip(pos, ref):
+        if st == prev_start and prev is not None:
+            out.append(prev)
+            continue
+        s5 = seq[st - n_up:st + n_down + 1].upper()
+        if len(s5) != n_up + n_down + 1 or s5[n_up] != r:
+            prev_start, prev = st, None
+            continue
+        ctx = "" if "N" in s5 else s5
+        out.append(ctx)
+        prev_start, prev = st, ctx
+    return out
+
+
 def reference_sample_step(n_proc, windows_per_proc, genes_sample, seed, pool=None):
-    """One bounded sample of the same workload with the reference's algorithm: per-base pure-Python
-    context counting under multiprocessing.Pool (sequence_tools.py:65-128) for BOTH context sizes, and
-    the SciPy burden test (transfer_tools.py:394-456, :484-592, :709-729) for `genes_sample` genes.
-    Pool start-up is not timed.  Returns (seconds_scan, bases_scanned, seconds_test, genes_tested)."""
+    """One bounded sample of the same workload with the reference's algorithm, all five stages of BASELINE.md section 3:
+      scan      per-base pure-Python context counting under multiprocessing.Pool (sequence_tools.py:65-128), BOTH sizes;
+      contexts  the per-mutation loop of mutation_contexts_by_chrom (sequence_tools.py:130-178);
+      observed  the pandas group-bys of mutations_per_gene + distinct-sample counts (mutation_tools.py:329-361,
+                transfer_tools.py:235-265) on the FULL coding-mutation table;
+      transfer  the per-gene loop of genic_model / DIG_onthefly (genic_driver_tools.py:86-168, :275-283);
+      test      SciPy burden tests (transfer_tools.py:394-456, :484-592, :709-729) for `genes_sample` genes.
+    Pool start-up is not timed.  Returns a dict of (seconds, units) per stage."""
+    import pandas as pd
     from oracle import dig_oracle
     n_win = n_proc * windows_per_proc
     L = n_win * WINDOW + 10
@@ -508,8 +708,45 @@ def reference_sample_step(n_proc, windows_per_proc, genes_sample, seed, pool=Non
     else:
         for j in jobs_all:
             dig_oracle._py_chunk(j)
-    t_scan = time.perf_counter() - t0
+    out = {"scan": (time.perf_counter() - t0, n_win * WINDOW)}
     rng = np.random.default_rng(seed)
+    # ---- mutation contexts: 30 k SNVs on the first 20 Mb of the sample
+    n_mc = 30_000
+    span = min(L - 10, 20_000_000)
+    pos = np.sort(rng.integers(5, span, n_mc))
+    up = seq[:span + 5].upper()
+    ref = [up[p_] for p_ in pos]
+    t0 = time.perf_counter()
+    _py_mutation_contexts(seq, pos.tolist(), ref)
+    out["contexts"] = (time.perf_counter() - t0, n_mc)
+    # ---- observed counts: the full coding table (335 k rows), pandas as in the reference
+    n_cds = int(0.30 * N_MUT) + int(0.07 * N_MUT) // 2
+    w = 1.0 / np.arange(1, N_SAMPLES + 1)
+    annots = np.array(["Synonymous", "Missense", "Nonsense", "Essential_Splice", "INDEL"])
+    df = pd.DataFrame({"GENE": rng.integers(0, N_GENES, n_cds), "SAMPLE": rng.choice(N_SAMPLES, size=n_cds, p=w / w.sum()),
+                       "ANNOT": annots[rng.choice(5, size=n_cds, p=[0.21, 0.61, 0.04, 0.04, 0.10])]})
+    t0 = time.perf_counter()
+    dig_oracle.gene_observed_counts(df)
+    out["observed"] = (time.perf_counter() - t0, n_cds)
+    # ---- gene transfer: 400 genes of ~10 exons against a 2 000-window map
+    n_g, n_w = 400, 2000
+    nblk = np.minimum(1 + rng.geometric(1 / 8.7, n_g), 300)
+    ptr = np.concatenate([[0], np.cumsum(nblk)])
+    owner = np.repeat(np.arange(n_g), nblk)
+    g0 = rng.integers(10, (n_w - 60) * WINDOW, n_g)
+    rel = np.concatenate([np.arange(k) for k in nblk]) * 1630
+    bs = g0[owner] + rel
+    be = bs + 130
+    counts64 = rng.integers(50, 400, (n_w, 64))
+    yp = rng.gamma(2.0, 10.0, n_w)
+    index = {(0, i * WINDOW): i for i in range(n_w)}
+    Lg = rng.integers(0, 40, (n_g, 192, 4)).astype(np.float64)
+    d_pr = np.exp(rng.normal(np.log(1e-6), 1.0, 192))
+    t0 = time.perf_counter()
+    dig_oracle.gene_transfer(np.zeros(n_g, dtype=np.int64), np.where(rng.random(n_g) < 0.5, -1, 1), ptr, bs, be, Lg, WINDOW,
+                             index, counts64, yp, yp * 0.2, yp, np.zeros(n_w, dtype=bool), d_pr)
+    out["transfer"] = (time.perf_counter() - t0, n_g)
+    # ---- the test
     E = genes_sample
     mu = rng.gamma(2.0, 20.0, E)
     sigma = mu * rng.uniform(0.05, 0.5, E)
@@ -520,15 +757,17 @@ def reference_sample_step(n_proc, windows_per_proc, genes_sample, seed, pool=Non
         k = rng.poisson(mu * pi).astype(np.float64)
         dig_oracle.burden_test(k, alpha, theta, pi)
     dig_oracle.fisher2(rng.uniform(0, 1, E), rng.uniform(0, 1, E))
-    t_test = time.perf_counter() - t0
-    return t_scan, n_win * WINDOW, t_test, E
+    out["test"] = (time.perf_counter() - t0, E)
+    return out
 
 
 def reference_value(total_bases, n_proc, seed, pool, windows_per_proc):
-    """bases/s of the whole step extrapolated linearly from the bounded sample."""
-    t_scan, nb, t_test, ne = reference_sample_step(n_proc, windows_per_proc, N_GENES, seed, pool)
-    t_full = t_scan * (total_bases / nb) + t_test * (N_GENES / ne)
-    return total_bases / t_full, t_scan, nb, t_test
+    """bases/s of the whole step, every stage EXTRAPOLATED linearly from its bounded sample to the workload's size."""
+    st = reference_sample_step(n_proc, windows_per_proc, N_GENES, seed, pool)
+    n_snv = N_MUT - int(0.07 * N_MUT)
+    full = {"scan": total_bases, "contexts": n_snv, "observed": st["observed"][1], "transfer": N_GENES, "test": N_GENES}
+    secs = {k: st[k][0] * (full[k] / st[k][1]) for k in st}
+    return total_bases / sum(secs.values()), st, secs
 
 
 def run_reference(args):
@@ -544,14 +783,21 @@ def run_reference(args):
     wpp = 1000
     pool = mp.Pool(n_proc) if n_proc > 1 else None
     vals, t0, sample = [], time.perf_counter(), ""
+    stages = None
     for i in range(n_steps):
-        v, t_scan, nb, t_test = reference_value(args.bases, n_proc, 1000 + i, pool, wpp)
+        v, st, secs = reference_value(args.bases, n_proc, 1000 + i, pool, wpp)
         if i >= args.warmup:
             vals.append(v)
-        sample = ("%d x 10 kb windows (%.1f Mb) counted for K=1024 and K=64 with the pure-Python per-base loop "
-                  "under multiprocessing.Pool(%d): %.2f s; 13 SciPy NB tests + Fisher on %d genes: %.3f s; "
-                  "extrapolated linearly to %.3g bases" % (nb // WINDOW, nb / 1e6, n_proc, t_scan, N_GENES, t_test,
-                                                          args.bases))
+        nb = st["scan"][1]
+        sample = ("EXTRAPOLATED from bounded samples, stage by stage: scan %d x 10 kb windows (%.1f Mb) for K=1024 and K=64, "
+                  "pure-Python per-base loop under multiprocessing.Pool(%d): %.2f s; mutation contexts of %d SNVs "
+                  "(per-row Python loop, 1 process): %.3f s; observed counts of %d coding mutations (pandas, full size): "
+                  "%.3f s; gene transfer of %d genes (per-gene loop): %.3f s; 13 SciPy NB tests + Fisher on %d genes "
+                  "(full size): %.3f s; each scaled linearly to %.3g bases / %d SNVs / %d genes"
+                  % (nb // WINDOW, nb / 1e6, n_proc, st["scan"][0], st["contexts"][1], st["contexts"][0],
+                     st["observed"][1], st["observed"][0], st["transfer"][1], st["transfer"][0], N_GENES, st["test"][0],
+                     args.bases, N_MUT - int(0.07 * N_MUT), N_GENES))
+        stages = {k: round(v_, 3) for k, v_ in secs.items()}
         if time.perf_counter() - t0 > 150.0 and vals:
             break
     if pool is not None:
@@ -559,21 +805,22 @@ def run_reference(args):
     v = float(np.median(vals))
     line = {"impl": "reference", "metric": "genome_bases_scanned_per_s", "value": v, "unit": "bases/s",
             "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-            "ms_per_step": args.bases / v * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": args.bases / v * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8 bases -> int64 counts; f64 p-values", "data": "synthetic",
-            "config": workload_config(args.bases, args.gpus),
-            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": n_proc, "kind": "port", "sample": sample},
+            "config": workload_config(args.bases, args.gpus, True),
+            "cpu_baseline": {"value": v, "unit": "bases/s", "cores": n_proc, "kind": "port", "sample": sample,
+                             "extrapolated": True, "full_size_seconds_by_stage": stages},
             "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_json(line)
 
 
-def workload_config(bases, n_gpus):
-    return {"workload": "synthetic hg19-sized genome (%.3g bases per GPU, 22 chromosomes), 10 kb windows, "
+def workload_config(bases, n_gpus, strong=True):
+    return {"workload": "synthetic hg19-sized genome (%.3g bases %s, 22 chromosomes), 10 kb windows, "
                         "pentanucleotide + trinucleotide context maps with genome totals, sequence model from "
                         "1M SNVs, 20k-gene CDS pretrain + observed counts + NB burden test (13 p-values + Fisher "
-                        "per gene)" % bases,
+                        "per gene)" % (bases, "in total" if strong else "per GPU"),
             "window": WINDOW, "genes": N_GENES, "snvs": N_MUT, "samples": N_SAMPLES,
-            "parallelism": "range-sharded x%d" % n_gpus,
+            "parallelism": ("ONE genome range-sharded over %d GPU(s)" if strong else "one genome per GPU x%d") % n_gpus,
             "l2_policy": "inputs (1.16 GB packed genome) and outputs (1.35 GB count tables) exceed the 126 MB L2"}
 
 
@@ -594,7 +841,7 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from digdriver_b200 import _lib
+    from digdriver_b200 import _lib, host_pipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -608,12 +855,24 @@ def main():
         dist.init_process_group("nccl", device_id=device)
         from digdriver_b200.sharding import Collectives
         dist_ctx = Collectives()
+    strong = world > 1 and args.scaling in ("auto", "strong")
 
     clocks = ClockSampler(local_rank)
     clocks.start()                       # nvidia-smi takes a while to start: launch it before the set-up
-    dg, ascii_d, d = build_workload(args.bases, seed=1 + rank, device=device)
+    # strong: every rank builds the SAME workload (the generator is a pure function of the position) and keeps the
+    # whole packed genome resident (1.16 GB), but scans only its slice; weak: one genome per rank
+    seed = 1 if strong else 1 + rank
+    dg, ascii_d, d = build_workload(args.bases, seed=seed, device=device)
     di = DeviceInputs(d, device)
-    n_scanned = float((d["wins"][:, 2] - d["wins"][:, 1]).sum())
+    if strong:
+        di.shard = StrongShard(d, di, dist_ctx, device)
+        n_local = float((d["wins"][di.shard.lo:di.shard.hi, 2] - d["wins"][di.shard.lo:di.shard.hi, 1]).sum())
+        n_total = float((d["wins"][:, 2] - d["wins"][:, 1]).sum())
+        n_genes_total = N_GENES
+    else:
+        n_local = float((d["wins"][:, 2] - d["wins"][:, 1]).sum())
+        n_total = n_local * world
+        n_genes_total = N_GENES * world
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -647,42 +906,74 @@ def main():
         launches = args.steps * stepper.launches_per_step
     elapsed_ms = start.elapsed_time(end)
     k5_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_all]))
+    k5_local_ms = k5_ms
     if dist_ctx is not None:
         t = torch.tensor([elapsed_ms, k5_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, k5_ms = float(t[0]), float(t[1])
     ms_per_step = elapsed_ms / args.steps
-    value = n_scanned * world / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
 
     # ---- parity at full size, outside every timed region (rank 0; the oracle regenerates the slices it needs)
     parity = None
     if rank == 0 and not args.no_parity_sample:
         try:
-            parity = parity_sample(dg, d, di, res, seed=1 + rank)
+            parity = parity_sample(dg, d, di, res, seed=seed)
         except Exception as exc:      # report, never hide
             parity = {"ok": False, "detail": "parity sample failed to run: %r" % (exc,)}
 
-    # ---- e2e leg: host buffers in and out
+    # ---- e2e leg: host buffers in and out, through digdriver_b200.host_pipeline
     e2e = None
     if not args.no_e2e:
-        hp = HostPath(ascii_d, dg, d, device)
-        del ascii_d
-        for _ in range(2):
-            hp.step(di)
-        barrier()
+        shard = getattr(di, "shard", None)
+
+        def timed(hp, n):
+            for _ in range(2):
+                hp.step(di)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                hp.step(di)
+            barrier()
+            sec = (time.perf_counter() - t0) / n
+            if dist_ctx is not None:
+                tt = torch.tensor([sec], dtype=torch.float64, device=device)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                sec = float(tt[0])
+            return sec
+
+        def totals_over_ranks(*vals):
+            tt = torch.tensor(vals, dtype=torch.float64, device=device)
+            if dist_ctx is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            return [int(v) for v in tt.tolist()]
+
+        # (1) the steady state: the packed-genome cache as the source (every run after the first one)
+        hg_packed = host_pipeline.HostGenome.from_device(dg)
+        hp = HostPath(hg_packed, d, di, device, shard=shard)
         n_e2e = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            hp.step(di)
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        if dist_ctx is not None:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t[0])
-        e2e = {"value": n_scanned * world / e2e_s, "unit": "bases/s", "ms_per_step": e2e_s * 1e3,
-               "h2d_bytes_per_step": int(hp.h2d_bytes), "d2h_bytes_per_step": int(hp.d2h_bytes),
-               "api": "HostPath.step: pinned host ASCII genome + tables in, count tables + p-values out"}
+        e2e_s = timed(hp, n_e2e)
+        h2d, d2h = totals_over_ranks(hp.h2d_bytes, hp.d2h_bytes)
+        e2e = {"value": n_total / e2e_s, "unit": "bases/s", "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "gpu_launches_per_step": hp.launches,
+               "api": "digdriver_b200.host_pipeline.HostScan + test stage: pinned host packed genome (the .dig2bit cache "
+                      "of get_device_genome / countGenomeContext, 0.375 B/base) + mutation / gene tables in; uint16 "
+                      "count tables, totals and 14 p-value columns out; bytes are summed over ranks"}
+        # host-side check of what arrived (outside the timing): totals of the host copy == device totals of the value leg
+        if rank == 0 and shard is None:
+            same = bool(torch.equal(hp.scan.host_totals, torch.cat([di.totals5, di.totals3]).cpu()))
+            row_ok = bool(np.array_equal(hp.scan.host_counts[:64].numpy().astype(np.int64), di.counts5[:64].cpu().numpy()))
+            e2e["host_results_match_value_leg"] = same and row_ok
+        del hp, hg_packed
+        # (2) the cold path: ASCII in (first run on a new FASTA), packed on the device
+        hg_ascii = host_pipeline.HostGenome.from_device(dg, ascii_d)
+        del ascii_d
+        hp = HostPath(hg_ascii, d, di, device, shard=shard)
+        cold_s = timed(hp, 3)
+        h2d, d2h = totals_over_ranks(hp.h2d_bytes, hp.d2h_bytes)
+        e2e["cold"] = {"value": n_total / cold_s, "ms_per_step": cold_s * 1e3, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "source": "pinned host ASCII genome (1 B/base), K1 pack on the device"}
+        del hp, hg_ascii
 
     clocks.mark_end()
     clock_info = clocks.stop()
@@ -693,18 +984,21 @@ def main():
         peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = n_scanned * B_PER_BASE_FUSED / (k5_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "scan_hex_kernel<TRI, TOT> (pentanucleotide K=1024 through hexamer pairs + "
-                                          "trinucleotide K=64 window tables and genome totals in one pass)",
+    # the scan of THIS rank's windows against its own launch time (rank 0's)
+    achieved = n_local * B_PER_BASE_FUSED / (k5_local_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "scan_lb_kernel<TRI, TOT> (lane-bank scan: pentanucleotide K=1024 through "
+                                          "hexamer pairs + trinucleotide K=64 window tables and genome totals in one pass; "
+                                          "followed by scan_hex_kernel over its redo list, empty here)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default size, from the committed
-                # ncu --set full capture (profiles/r01_scan_hex_summary.txt): 1.169 GB + 1.302 GB
-                "traffic": 2.4707e9 if abs(args.bases - 3.1e9) < 1 else None,
-                "algorithmic_bytes": n_scanned * B_PER_BASE_FUSED,
-                "peak_source": which, "kernel_ms": k5_ms,
+                # ncu --set full capture (profiles/r02_scan_lb_summary.txt)
+                "traffic": SCAN_DRAM_TRAFFIC if abs(args.bases - 3.1e9) < 1 and not strong else None,
+                "algorithmic_bytes": n_local * B_PER_BASE_FUSED,
+                "peak_source": which, "kernel_ms": k5_local_ms,
                 "algorithmic_bytes_per_base": B_PER_BASE_FUSED,
-                "note": "HBM is the roofline the contract asks for; ncu shows the kernel is bound by the shared-memory "
-                        "atomic data pipe (87 % busy after halving the atomics with hexamer pairs), see DESIGN.md section 4", "share_of_step": k5_ms / ms_per_step}
+                "note": "HBM is the roofline the contract asks for; the kernel alternates an integer-ALU-bound counting "
+                        "phase with a shared-memory-bound write-out phase (DESIGN.md section 4)",
+                "share_of_step": k5_local_ms / ms_per_step}
 
     def finish():
         """Leave without tearing NCCL down: destroy_process_group() after a CUDA graph that holds NCCL kernels was
@@ -735,14 +1029,21 @@ def main():
 
     line = {"metric": "genome_bases_scanned_per_s", "value": value, "unit": "bases/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if strong or world == 1 else "weak", "vs_baseline": None,
             "dtype": "u8 bases -> int32 counts; f64 p-values", "data": "synthetic",
-            "config": workload_config(args.bases, world),
-            "elements_tested_per_s": N_GENES * world / (ms_per_step * 1e-3),
+            "config": workload_config(args.bases, world, strong or world == 1),
+            "elements_tested_per_s": n_genes_total / (ms_per_step * 1e-3),
             "cuda_graph": {"test_stage_captured": stepper.graph is not None, "error": stepper.error},
             "host_placement": placement,
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity_sample": parity}
+    if strong:
+        sh = di.shard
+        line["sharding"] = {"windows_per_rank": [b - a for a, b in sh.table.parts], "genes_per_rank": sh.genes_per_rank,
+                            "exchange": "1 all_gather_into_tensor of %.1f MB (trinucleotide rows + partial totals), "
+                                        "1 all_reduce of 4 doubles, 1 all_gather_into_tensor of the result rows; all "
+                                        "inside the CUDA graph" % (sh.exchange_bytes / 1e6),
+                            "scan_kernel_ms_max_over_ranks": k5_ms}
     emit_json(line)
     finish()
 

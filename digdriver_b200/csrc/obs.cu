@@ -245,6 +245,16 @@ inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 extern "C" {
 
+int64_t dig_tabulate_capacity(int64_t n_pairs)
+{
+    if (n_pairs < 0) n_pairs = 0;
+    int64_t cap = 1024;
+    while (cap < 2 * n_pairs + 16) cap <<= 1;
+    return cap;
+}
+int64_t dig_tabulate_elements_workspace_bytes(int64_t n_pairs) { return dig_tabulate_capacity(n_pairs) * 16; }
+int64_t dig_tabulate_genes_workspace_bytes(int64_t n_mut) { return dig_tabulate_capacity(n_mut) * 28; }
+
 int dig_count_hits(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d,
                    const int32_t *blk_elt_d, int64_t n_blk, const int64_t *mut_kstart_d,
                    const int64_t *mut_kend_d, int64_t n_mut, unsigned long long *n_hits_d, void *stream)

@@ -99,9 +99,11 @@ __device__ __forceinline__ void mbar_arrive_tx(uint32_t a, uint32_t tx)
 // "I have finished READING" arrival: `dep` must be computed from every value that was loaded.  An arrive is not ordered
 // after shared-memory loads that are still in flight -- a load queued behind other warps' atomics can be overtaken --
 // so the arrival is made data-dependent on the loads: it cannot issue before they have returned.
-__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t a, uint32_t dep)
+// (`zero` is the kernel argument LbArgs::zero = 0: the dependence has to survive ptxas, which drops a register that is
+// only named in a comment, and folds a literal "& 0")
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t a, uint32_t dep, uint32_t zero)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(a), "r"(dep) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a + (dep & zero)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity)
 {
@@ -223,22 +225,18 @@ struct LbGeom {
     bool active, too_long;
 };
 
+// second half of lb_geom: the region descriptor (c, rs, re) is already in registers
 template <bool TRI>
-__device__ __forceinline__ LbGeom lb_geom(int64_t r, int64_t n_reg, const int64_t *__restrict__ chrom_off,
-                                          const int64_t *__restrict__ chrom_len,
-                                          const int32_t *__restrict__ reg_chrom,
-                                          const int64_t *__restrict__ reg_start,
-                                          const int64_t *__restrict__ reg_end)
+__device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, int64_t re, const int64_t *__restrict__ chrom_off,
+                                           const int64_t *__restrict__ chrom_len)
 {
     LbGeom g;
     g.O = 0;
     g.lo5 = g.hi5 = g.lo3 = g.hi3 = 0;
     g.nch = 0;
-    g.active = r < n_reg;
+    g.active = active;
     g.too_long = false;
     if (g.active) {
-        const int32_t c = __ldg(reg_chrom + r);
-        const int64_t rs = __ldg(reg_start + r), re = __ldg(reg_end + r);
         const int64_t L = __ldg(chrom_len + c), off = __ldg(chrom_off + c);
         int64_t gs[2], ge[2];
 #pragma unroll
@@ -280,6 +278,23 @@ __device__ __forceinline__ LbGeom lb_geom(int64_t r, int64_t n_reg, const int64_
         }
     }
     return g;
+}
+
+template <bool TRI>
+__device__ __forceinline__ LbGeom lb_geom(int64_t r, int64_t n_reg, const int64_t *__restrict__ chrom_off,
+                                          const int64_t *__restrict__ chrom_len,
+                                          const int32_t *__restrict__ reg_chrom,
+                                          const int64_t *__restrict__ reg_start,
+                                          const int64_t *__restrict__ reg_end)
+{
+    int32_t c = 0;
+    int64_t rs = 0, re = 0;
+    if (r < n_reg) {
+        c = __ldg(reg_chrom + r);
+        rs = __ldg(reg_start + r);
+        re = __ldg(reg_end + r);
+    }
+    return lb_geom2<TRI>(r < n_reg, c, rs, re, chrom_off, chrom_len);
 }
 
 // word idx (0..8) of the thread's nine 16-base words without dynamic register indexing
@@ -519,10 +534,11 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 M[4] = lds32(mptr + 16u);
             }
             // the stage may be refilled as soon as all sixteen warps have arrived: only after the loads have RETURNED
-            uint32_t dep = (D[0] | D[1] | D[2]) ^ (D[3] | D[4] | D[5]) ^ (D[6] | D[7] | D[8]) ^ (M[0] | M[1] | M[2]) ^ (M[3] | M[4]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dep |= __shfl_xor_sync(0xffffffffu, dep, o);    // every lane's loads
-            if (lane == 0) mbar_arrive_after_loads(bar + 8u * (BAR_EMPTY + stage), dep);
+            // (one register of each of the five load instructions is enough: a warp's load instruction releases its
+            // scoreboard when the data of ALL lanes has been written, so lane 0's dependence covers the warp)
+            const uint32_t dep = (D[0] | D[4]) ^ (D[8] | M[0]) ^ M[4];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after_loads(bar + 8u * (BAR_EMPTY + stage), dep, A.zero);
             if (!clean) {                                                    // the writer warps have re-zeroed the tables
                 LB_T(t_c);
                 mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);
@@ -535,7 +551,13 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
             const int lo5 = g.lo5 - base, hi5 = g.hi5 - base;                // centre c (local base index) valid: lo5 <= c < hi5
             const uint32_t any_n = M[0] | M[1] | M[2] | M[3] | (M[4] & 0xF0000000u);
             uint32_t PV[4] = {0u, 0u, 0u, 0u};
+#ifdef DIG_LB_UNIFORM_PATH
+            if (__all_sync(0xffffffffu, any_n == 0u && lo5 <= 2 && hi5 >= 130)) {
+#else
+            // per lane, although a warp whose lanes disagree runs both bodies one after the other: sending the whole warp
+            // through the predicated body instead was measured 9 % slower (1.041 vs 0.954 ms at hg19 scale)
             if (any_n == 0u && lo5 <= 2 && hi5 >= 130) {
+#endif
                 lb_pairs<false>(D, tabl, A.k32, top_r, PV);
                 npairs += 64u;
             } else if (k < g.nch) {
@@ -580,17 +602,26 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
         cons_sync();                                                         // every hexamer of the batch is in the tables
         LB_T(t_s1);
         LB_ACC(3, t_s0, t_s1);
+        // descriptor of the next batch's region: requested now, its chromosome looked up one slice pair into the write-out,
+        // so neither of the two dependent global loads is waited for
+        const int64_t rn = (b + gridDim.x) * 32 + lb_win(lane);
+        const bool nact = b + gridDim.x < n_batches && rn < A.n_reg;
+        int32_t nc = 0;
+        int64_t nrs = 0, nre = 0;
+        if (nact) {
+            nc = __ldg(A.reg_chrom + rn);
+            nrs = __ldg(A.reg_start + rn);
+            nre = __ldg(A.reg_end + rn);
+        }
         mbar_wait(bar + 8u * BAR_DONE, (bi & 1u) ^ 1u);                      // writer warp 0 finished the previous batch
         LB_T(t_s2);
         LB_ACC(4, t_s1, t_s2);
-
-        if (b + gridDim.x < n_batches)
-            gnext = lb_geom<TRI>((b + gridDim.x) * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
 
         // ---- write-out
         uint32_t tri_acc[4] = {0u, 0u, 0u, 0u};    // also the overflow check: all bins of a window sum to 2 x (table bytes)
 #pragma unroll 1
         for (int i2 = 0; i2 < 4; ++i2) {
+          if (i2 == 1) gnext = lb_geom2<TRI>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int i = 2 * i2 + h;
@@ -721,15 +752,11 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
                 }
             }
             uint32_t dep = 0u;
-            if constexpr (TOT) {
-                dep = tmp5[2 * s4] | tmp5[2 * s4 + 1];                       // the column sums have consumed their loads
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dep |= __shfl_xor_sync(0xffffffffu, dep, o);
-            }
+            if constexpr (TOT) dep = tmp5[2 * s4] | tmp5[2 * s4 + 1];        // the column sums have consumed their loads
             __syncwarp();
             if (lane == 0) {
                 bulk_wait_read<0>();                                         // the tile has left shared memory
-                mbar_arrive_after_loads(bar + 8u * (BAR_OUTEMPTY + q), dep);
+                mbar_arrive_after_loads(bar + 8u * (BAR_OUTEMPTY + q), dep, A.zero);
             }
             __syncwarp();
         }

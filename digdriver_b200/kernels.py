@@ -166,11 +166,9 @@ def fisher_combine2(p1, p2, device="cuda:0", stream=None):
     return out
 
 
-def _pow2_at_least(n):
-    c = 1024
-    while c < n:
-        c *= 2
-    return c
+def _table_capacity(n_pairs):
+    """Hash-table slots for up to n_pairs distinct keys: the rule lives in the library (dig_tabulate_capacity)."""
+    return int(_lib.load().dig_tabulate_capacity(int(n_pairs)))
 
 
 def _check_status(status, what, sink=None):
@@ -200,9 +198,13 @@ def check_deferred(sink):
 
 def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_sample, mut_isindel,
                       n_elt, n_sample, max_muts_per_sample=10 ** 9, max_per_elt_per_sample=3 * 10 ** 9,
-                      device="cuda:0", stream=None, sample_rows_mode=False, return_table=False):
+                      device="cuda:0", stream=None, sample_rows_mode=False, return_table=False, max_hits=None,
+                      status_sink=None):
     """K5: (OBS_SAMPLES, OBS_SNV, OBS_INDEL) per element and the per-sample totals used for the
-    hypermutator black-list.  Blocks need not be sorted.  Returns (obs int64 [n_elt,3], sample_tot [n_sample])."""
+    hypermutator black-list.  Blocks need not be sorted.  Returns (obs int64 [n_elt,3], sample_tot [n_sample]).
+
+    max_hits: an upper bound of the number of (mutation, element) pairs; with it the table is sized without
+    reading the device-side hit count (no host synchronisation; an overflow still sets the status word)."""
     dev = torch.device(device)
     bks = np.asarray(blk_kstart, dtype=np.int64)
     order = np.argsort(bks, kind="stable")
@@ -217,10 +219,12 @@ def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_s
     n_blk, n_mut = len(bks), t["mks"].numel()
     sptr = _stream(dev, stream)
     with torch.cuda.device(dev):
-        n_hits = torch.zeros(1, dtype=torch.int64, device=dev)
-        _lib.call("dig_count_hits", t["bks"].data_ptr(), t["bke"].data_ptr(), t["pmax"].data_ptr(),
-                  t["belt"].data_ptr(), n_blk, t["mks"].data_ptr(), t["mke"].data_ptr(), n_mut, n_hits.data_ptr(), sptr)
-        cap = _pow2_at_least(2 * int(n_hits.item()) + 16)
+        if max_hits is None:
+            n_hits = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.call("dig_count_hits", t["bks"].data_ptr(), t["bke"].data_ptr(), t["pmax"].data_ptr(),
+                      t["belt"].data_ptr(), n_blk, t["mks"].data_ptr(), t["mke"].data_ptr(), n_mut, n_hits.data_ptr(), sptr)
+            max_hits = int(n_hits.item())
+        cap = _table_capacity(max_hits)
         keys = torch.empty(cap, dtype=torch.int64, device=dev)
         snv = torch.empty(cap, dtype=torch.int32, device=dev)
         ind = torch.empty(cap, dtype=torch.int32, device=dev)
@@ -233,7 +237,7 @@ def tabulate_elements(blk_kstart, blk_kend, blk_elt, mut_kstart, mut_kend, mut_s
                   sample_tot.data_ptr(), int(min(max_muts_per_sample, 2 ** 62)),
                   int(min(max_per_elt_per_sample, 2 ** 62)), n_elt, obs.data_ptr(), status.data_ptr(),
                   int(bool(sample_rows_mode)), sptr)
-        _check_status(status, "dig_tabulate_elements")
+        _check_status(status, "dig_tabulate_elements", status_sink)
     if return_table:
         # the (element, sample) hash table itself: key = (element << 32 | sample) + 1, 0 = empty slot
         return obs[:n_elt], sample_tot[:n_sample], (keys, snv, ind)
@@ -247,7 +251,7 @@ def tabulate_genes(mut_gene, mut_sample, mut_class, n_gene, max_per_gene_per_sam
     dev = torch.device(device)
     mg, ms, mc = _dev(mut_gene, torch.int32, dev), _dev(mut_sample, torch.int32, dev), _dev(mut_class, torch.uint8, dev)
     n_mut = mg.numel()
-    cap = _pow2_at_least(2 * n_mut + 16)
+    cap = _table_capacity(n_mut)
     with torch.cuda.device(dev):
         keys = torch.empty(cap, dtype=torch.int64, device=dev)
         cnt = torch.empty((cap, 5), dtype=torch.int32, device=dev)

@@ -44,7 +44,15 @@ def get_device_genome(f_fasta, device=None):
     key = (path, os.path.getmtime(path), str(device))
     if key not in _GENOME_CACHE:
         _GENOME_CACHE.clear()                       # one packed genome at a time is plenty
-        _GENOME_CACHE[key] = DeviceGenome.from_genome(Genome.from_fasta(path), device)
+        # pinned host copy (the packed cache next to the FASTA when it is valid, else the parsed file), uploaded and
+        # packed chromosome by chromosome on two streams; a freshly packed genome is written back as the cache
+        from .. import host_pipeline
+        use_cache = os.environ.get("DIG_NO_GENOME_CACHE", "") == ""
+        hg, hit = host_pipeline.host_genome_from_fasta(path, use_cache=use_cache)
+        g = host_pipeline.HostScan(hg, np.zeros((0, 3), dtype=np.int64), device, tables=(1, 1)).run().genome
+        if use_cache and not hit:
+            host_pipeline.PackedGenomeCache.store(path, g)
+        _GENOME_CACHE[key] = g
     return _GENOME_CACHE[key]
 
 

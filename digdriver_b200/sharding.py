@@ -135,3 +135,52 @@ def all_gather_rows(coll, t, sizes):
         return out
     keep = torch.cat([torch.arange(r * m, r * m + s_, device=t.device) for r, s_ in enumerate(sizes)])
     return out.index_select(0, keep)
+
+
+# --------------------------------------------------------------------------------------------
+# ONE genome over all ranks (strong scaling): layout of the all-gathered trinucleotide table
+# --------------------------------------------------------------------------------------------
+
+TOTALS_ROWS = 34      # 1024 + 64 genome-wide totals as int64 = 2176 int32 words = 34 rows of 64
+
+
+class GatheredTable:
+    """Layout of the [world, m + TOTALS_ROWS, 64] int32 buffer that ONE all_gather_into_tensor fills: block r holds the
+    trinucleotide rows of rank r's window slice (padded to the longest slice, m rows) followed by that rank's partial
+    genome-wide totals (pentanucleotide | trinucleotide, int64 viewed as 34 int32 rows).  The element stage indexes the
+    buffer in place through a window map that points at the gathered rows, so nothing is copied or compacted, and the
+    totals ride in the same collective (replaces the df.sum(axis=0) of DigPreprocess.py:59 and the pd.concat of
+    sequence_tools.py:125)."""
+
+    def __init__(self, parts):
+        self.parts = [(int(a), int(b)) for a, b in parts]
+        self.world = len(self.parts)
+        self.m = max(1, max(b - a for a, b in self.parts))
+        self.block_rows = self.m + TOTALS_ROWS
+
+    def row_of_window(self, n_win):
+        """int64 [n_win]: row of global window w in buffer.view(-1, 64)."""
+        row = np.full(n_win, -1, dtype=np.int64)
+        for r, (a, b) in enumerate(self.parts):
+            row[a:b] = r * self.block_rows + np.arange(b - a)
+        return row
+
+    def window_map(self, win_chrom_idx, win_start, window, n_chrom):
+        """K6's dense (chromosome, window number) -> row map, pointing into the gathered buffer."""
+        from .kernels import build_window_map
+        off, wmap = build_window_map(win_chrom_idx, win_start, window, n_chrom)
+        rows = self.row_of_window(len(win_chrom_idx))
+        ok = wmap >= 0
+        out = wmap.copy()
+        out[ok] = rows[wmap[ok]].astype(np.int32)
+        return off, out
+
+    def local_views(self, local):
+        """(rows of the own slice [m, 64], totals5 int64 [1024], totals3 int64 [64]) as views of this rank's block."""
+        tot = local[self.m:].view(torch.int64).reshape(-1)
+        return local[: self.m], tot[:1024], tot[1024:1088]
+
+    def summed_totals(self, gathered):
+        """int64 [1088]: the ranks' partial totals added up (gathered: [world, block_rows, 64] int32)."""
+        g = gathered.view(self.world, self.block_rows, 64)[:, self.m:, :].contiguous()
+        return g.view(torch.int64).reshape(self.world, -1).sum(dim=0)

@@ -121,6 +121,13 @@ int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint32_t *nmask_
                                unsigned long long *totals5_d, unsigned long long *totals3_d,
                                const dig_scan_opts *opts, void *stream);
 
+/* Count tables on their way to the host: int32 counts narrowed to uint16 (half the device->host bytes).  A window
+ * of the data extractor's tiling (DataExtractor.py:70-77) holds at most `window` <= 65535 centres, so the rows the
+ * reference stores as int64 (DigPreprocess.py:52-60) fit 16 bits; status_d[0] is OR-ed with 1 if any value does not
+ * (the host then ships the int32 rows instead).  Both buffers 16-byte aligned; status_d is NOT cleared here.
+ */
+int dig_narrow_counts_u16(const int32_t *counts_d, int64_t n_values, uint16_t *out_d, int32_t *status_d, void *stream);
+
 /* ---------------------------------------------------------------------------------
  * K3  mutation context lookup with REF check.
  * Replaces: mutation_contexts_by_chrom (sequence_tools.py:130-178).
@@ -171,6 +178,17 @@ int dig_substitution_counts(const int32_t *ctx_d, const uint8_t *alt_d, int64_t 
  *                (element, sample) counts are capped at max_per_elt_per_sample (:168-169)
  *   status_d     [1] int32: set to 1 if the hash table overflowed (results invalid)
  */
+/* Scratch sizing for K5, so that a C caller needs nothing but this header:
+ *   dig_tabulate_capacity(n_pairs)  slots of the open-addressing table for up to n_pairs distinct (element | gene,
+ *        sample) pairs: the power of two >= max(1024, 2 n_pairs + 16).  n_pairs = *n_hits_d of dig_count_hits for
+ *        elements (an upper bound such as n_mut x the largest number of elements overlapping one position works as
+ *        well and avoids the host read), n_mut for genes.
+ *   dig_tabulate_elements_workspace_bytes(n_pairs) = capacity x (8 + 4 + 4) bytes: tab_key_d, tab_snv_d, tab_indel_d
+ *   dig_tabulate_genes_workspace_bytes(n_mut)      = capacity x (8 + 5 x 4) bytes: tab_key_d, tab_cnt_d
+ */
+int64_t dig_tabulate_capacity(int64_t n_pairs);
+int64_t dig_tabulate_elements_workspace_bytes(int64_t n_pairs);
+int64_t dig_tabulate_genes_workspace_bytes(int64_t n_mut);
 int dig_count_hits(const int64_t *blk_kstart_d, const int64_t *blk_kend_d, const int64_t *blk_pmax_d,
                    const int32_t *blk_elt_d, int64_t n_blk, const int64_t *mut_kstart_d,
                    const int64_t *mut_kend_d, int64_t n_mut, unsigned long long *n_hits_d, void *stream);

@@ -52,7 +52,8 @@ def window_rows(lengths, chrom_off, seed, wins, idx, n_frac16=16):
     return c5, c3, (seq, off, ln, ns, ne)
 
 
-def check_sample(lengths, chrom_off, seed, window, d, got, n_windows=500, n_genes=200, rng_seed=0, n_frac16=16):
+def check_sample(lengths, chrom_off, seed, window, d, got, n_windows=500, n_genes=200, rng_seed=0, n_frac16=16,
+                 win_pool=None, gene_pool=None):
     """`d`: the host workload dict of bench.build_workload; `got`: host arrays of the GPU run --
     counts5 / counts3 as callables idx -> rows (so that only the sampled rows leave the device), ctx (all mutations),
     per-gene columns MU, SIGMA, Pi_SYN .., ALPHA, THETA, OBS_*, PVAL_*, d_pr, sums, n_syn.
@@ -63,7 +64,9 @@ def check_sample(lengths, chrom_off, seed, window, d, got, n_windows=500, n_gene
     chrom_off = np.asarray(chrom_off, dtype=np.int64)
     detail = []
     # ---- windows, uniformly over the genome (the last chromosomes lie beyond 2^31 in global coordinates)
-    idx = np.sort(rng.choice(len(wins), size=min(n_windows, len(wins)), replace=False))
+    # (win_pool / gene_pool: a range-sharded rank holds the rows of its own windows and genes only)
+    pool = np.arange(len(wins)) if win_pool is None else np.asarray(win_pool, dtype=np.int64)
+    idx = np.sort(rng.choice(pool, size=min(n_windows, len(pool)), replace=False))
     hi_off = int((chrom_off[wins[idx, 0]] + wins[idx, 1] > (1 << 31)).sum())
     c5, c3, (seq, off, ln, ns, ne) = window_rows(lengths, chrom_off, seed, wins, idx, n_frac16)
     g5, g3 = np.asarray(got["counts5"](idx), dtype=np.int64), np.asarray(got["counts3"](idx), dtype=np.int64)
@@ -101,7 +104,8 @@ def check_sample(lengths, chrom_off, seed, window, d, got, n_windows=500, n_gene
             detail.append("%d mutation contexts differ (first rows %s)" % (badm.size, sel[order][badm[:5]].tolist()))
     # ---- genes: pretrain columns from oracle-counted window rows, then the test itself
     E = len(d["g_ptr"]) - 1
-    gid = np.sort(rng.choice(E, size=min(n_genes, E), replace=False))
+    gpool = np.arange(E) if gene_pool is None else np.asarray(gene_pool, dtype=np.int64)
+    gid = np.sort(rng.choice(gpool, size=min(n_genes, len(gpool)), replace=False))
     ptr, bs, be = d["g_ptr"], d["g_bs"], d["g_be"]
     need = set()
     for g in gid:

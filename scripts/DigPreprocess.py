@@ -35,21 +35,53 @@ def countGenomeContext(args):
         df_bed[0] = df_bed[0].astype(int)
     df_bed = df_bed.sort_values(by=[0, 1])
     print('Counting nucleotide contexts in {} regions'.format(len(df_bed)))
-    g = sequence_tools.get_device_genome(args.fasta)
-    cidx = g.chrom_indices(df_bed.iloc[:, 0].values)
-    counts, totals = kernels.count_contexts(g, cidx, df_bed.iloc[:, 1].values, df_bed.iloc[:, 2].values,
-                                            args.up, args.down, want_totals=True)
-    cols = list(sequence_tools.mk_context_sequences(args.up, args.down))
     index = ['chr{}:{}-{}'.format(c, s, e) for c, s, e in df_bed.iloc[:, 0:3].values]
-    df = pd.DataFrame(counts.cpu().numpy().astype(np.int64), index=index, columns=cols)
-    S_count = pd.Series(totals.cpu().numpy(), index=cols)              # == df.sum(axis=0), fused into the scan
     idx = df_bed.iloc[:, 0:3].values
-    print('Saving context counts to {}'.format(args.fout))
-    st = storage.Store(args.fout, "w")
-    st.write_table('genome_counts', S_count)
-    st.write_table('all_window_genome_counts', df)
-    st.write_array('idx', idx, dtype=np.int32)
-    st.set_attrs(n_up=args.up, n_down=args.down, collapse=0)
+    starts, ends = df_bed.iloc[:, 1].values.astype(np.int64), df_bed.iloc[:, 2].values.astype(np.int64)
+    fout_tri = getattr(args, "fout_tri", None)
+    if isinstance(args.fasta, (str, os.PathLike)):
+        # host pipeline (digdriver_b200/host_pipeline.py): packed-genome cache next to the FASTA, chromosome-wise
+        # H2D / pack / scan / D2H on three streams, uint16 rows over PCIe; with --fout-tri the trinucleotide table of
+        # the reference's second run (--up 1 --down 1) comes out of the same pass (dig_count_contexts_fused53)
+        from digdriver_b200 import host_pipeline
+        hg, hit = host_pipeline.host_genome_from_fasta(args.fasta, use_cache=not getattr(args, "no_cache", False))
+        lut = {n: i for i, n in enumerate(hg.names)}
+        try:
+            cidx = np.array([lut['chr{}'.format(c)] if 'chr{}'.format(c) in lut else lut[str(c)]
+                             for c in df_bed.iloc[:, 0].values], dtype=np.int64)
+        except KeyError as exc:
+            raise KeyError("chromosome %s not in genome" % (exc,))
+        fused = bool(fout_tri) and (args.up, args.down) == (2, 2)
+        hs = host_pipeline.HostScan(hg, np.stack([cidx, starts, ends], axis=1), sequence_tools.default_device(),
+                                    tables="penta+tri" if fused else (args.up, args.down)).run()
+        if hs.genome.n_other:
+            raise KeyError("genome contains %d characters that are not A/C/G/T/N; the reference fails on them at "
+                           "sequence_tools.py:76" % hs.genome.n_other)
+        if not hit and not getattr(args, "no_cache", False):
+            host_pipeline.PackedGenomeCache.store(args.fasta, hs.genome)
+        counts_h, totals_h = hs.host_counts.numpy(), hs.host_totals[:hs.K].numpy()
+        tri = (hs.host_counts3.numpy(), hs.host_totals[hs.K:].numpy()) if fused else None
+    else:
+        g = sequence_tools.get_device_genome(args.fasta)
+        cidx = g.chrom_indices(df_bed.iloc[:, 0].values)
+        counts, totals = kernels.count_contexts(g, cidx, starts, ends, args.up, args.down, want_totals=True)
+        counts_h, totals_h, tri = counts.cpu().numpy(), totals.cpu().numpy(), None
+
+    def save(fout, n_up, n_down, cnt, tot):
+        cols = list(sequence_tools.mk_context_sequences(n_up, n_down))
+        df = pd.DataFrame(cnt.astype(np.int64), index=index, columns=cols)
+        S_count = pd.Series(np.asarray(tot, dtype=np.int64), index=cols)    # == df.sum(axis=0), fused into the scan
+        print('Saving context counts to {}'.format(fout))
+        st_ = storage.Store(fout, "w")
+        st_.write_table('genome_counts', S_count)
+        st_.write_table('all_window_genome_counts', df)
+        st_.write_array('idx', idx, dtype=np.int32)
+        st_.set_attrs(n_up=n_up, n_down=n_down, collapse=0)
+        return st_
+
+    st = save(args.fout, args.up, args.down, counts_h, totals_h)
+    if tri is not None:
+        save(fout_tri, 1, 1, tri[0], tri[1])
     if args.map_file:
         mapp = np.loadtxt(args.map_file) if not args.map_file.endswith('.npy') else np.load(args.map_file)
         assert len(mapp) == len(idx), "--map-file must hold one mappability value per window"
@@ -140,6 +172,11 @@ def parse_args(text=None):
     a.add_argument('--n-procs', type=int, default=get_cpus())
     a.add_argument('--map-file', type=str, default='')
     a.add_argument('--map-thresh', type=float, default=0.5)
+    a.add_argument('--fout-tri', type=str, default='',
+                   help='(extension) with --up 2 --down 2: also write the --up 1 --down 1 table of the same windows, '
+                        'counted in the same pass')
+    a.add_argument('--no-cache', action='store_true',
+                   help='(extension) neither read nor write the packed-genome cache <fasta>.dig2bit/')
     a.set_defaults(func=countGenomeContext)
     b = sub.add_parser('addMutationContext', help='annotate mutations with their sequence context')
     b.add_argument('fmut', type=str)

@@ -152,3 +152,68 @@ def test_partition_elements_edges():
     owner = sharding.partition_elements([0, 0, 0, 1, 1, 1, 2], [0, 1999, 2000, 500, 1999, 2000, 10], wc, ws, we, parts)
     assert owner.tolist() == [0, 0, 1, 1, 1, -1, -1]              # chr2:2000 and chr3 lie in no window
     assert sharding.partition_elements([], [], wc, ws, we, parts).tolist() == []
+
+
+def _gathered_worker(rank, world, port, ret):
+    """ONE genome over two ranks the way bench.py's strong mode does it: each rank counts its slice into its block of
+    the exchange buffer (rows + partial totals), ONE all_gather_into_tensor, and the element stage resolves windows
+    through the remapped window map -- straddling elements included."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from digdriver_b200 import sharding
+    from digdriver_b200.genome import Genome, tile_windows
+    from oracle import dig_oracle
+    W = 1000
+    lengths = np.array([40_500, 23_000], dtype=np.int64)
+    seqs = [dig_oracle.synth_genome(int(o), int(n), 9) for o, n in zip(np.cumsum(lengths) - lengths, lengths)]
+    g = Genome(["chr1", "chr2"], seqs)
+    wins = tile_windows([0, 1], lengths, W)
+    parts = sharding.partition_windows(wins[:, 1], wins[:, 2], world)
+    gt = sharding.GatheredTable(parts)
+    lo, hi = parts[rank]
+    mine = wins[lo:hi]
+    sub, c, s, e = sharding.slice_genome(g, mine[:, 0], mine[:, 1], mine[:, 2], halo=2)
+    off = np.concatenate([[0], np.cumsum(sub.lengths)[:-1]])
+    cat = np.concatenate(sub.seqs)
+    c3, _ = dig_oracle.count_regions(cat, off, sub.lengths, c, s, e, 1, 1)
+    c5, _ = dig_oracle.count_regions(cat, off, sub.lengths, c, s, e, 2, 2)
+    local = torch.zeros((gt.block_rows, 64), dtype=torch.int32)
+    rows, t5, t3 = gt.local_views(local)
+    rows[: hi - lo] = torch.from_numpy(c3.astype(np.int32))
+    t5.copy_(torch.from_numpy(c5.sum(axis=0)))
+    t3.copy_(torch.from_numpy(c3.sum(axis=0)))
+    gathered = torch.zeros((world, gt.block_rows, 64), dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered.view(-1, 64), local)
+    tot = gt.summed_totals(gathered).numpy()
+    full_off = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    f3, _ = dig_oracle.count_regions(np.concatenate(seqs), full_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 1, 1)
+    f5, _ = dig_oracle.count_regions(np.concatenate(seqs), full_off, lengths, wins[:, 0], wins[:, 1], wins[:, 2], 2, 2)
+    table = gathered.view(-1, 64).numpy()
+    row_of = gt.row_of_window(len(wins))
+    ok_rows = bool(np.array_equal(table[row_of], f3))
+    ok_tot = bool(np.array_equal(tot[:1024], f5.sum(axis=0)) and np.array_equal(tot[1024:], f3.sum(axis=0)))
+    # the window map resolves (chromosome, window number) to gathered rows; an element straddling the cut sees both
+    moff, wmap = gt.window_map(wins[:, 0], wins[:, 1], W, 2)
+    cut = parts[0][1]
+    c_cut, s_cut = int(wins[cut, 0]), int(wins[cut, 1])
+    ok_map = s_cut >= W and int(wins[cut - 1, 0]) == c_cut
+    if ok_map:
+        r_left = wmap[moff[c_cut] + s_cut // W - 1]
+        r_right = wmap[moff[c_cut] + s_cut // W]
+        ok_map = bool(np.array_equal(table[r_left], f3[cut - 1]) and np.array_equal(table[r_right], f3[cut]) and
+                      r_left // gt.block_rows == 0 and r_right // gt.block_rows == 1)
+    ret["r%d" % rank] = (ok_rows, ok_tot, bool(ok_map))
+    dist.destroy_process_group()
+
+
+def test_gathered_table_world2():
+    from oracle import dig_oracle
+    dig_oracle.build()
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gathered_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {"r0": (True, True, True), "r1": (True, True, True)}
