@@ -9,16 +9,18 @@ totals, sequence model from 1 M SNVs, 20 k-gene CDS pretrain + observed counts +
 (13 p-values + Fisher per gene).  One "step" = one pass of that whole path.
 
   value  : genome bases scanned per second over the whole step, inputs resident in HBM;
-  e2e    : the same step through the host-buffer API: ASCII genome, mutations and gene tables start
-           in pinned host memory, counts and p-values end in host memory (copies inside the timing);
+  e2e    : the same step through the package's host-buffer API (digdriver_b200.host_pipeline.HostScan): packed
+           genome (the .dig2bit cache; `cold` = ASCII), mutations and gene tables start in pinned host memory,
+           uint16 count tables and p-values end in host memory (copies inside the timing);
   roofline: the dominant kernel (pentanucleotide scan), algorithmic bytes / its CUDA-event time,
            against the measured HBM peak in MEASURED_PEAKS.json;
   cpu_baseline / --impl reference: the reference's own algorithm (pure-Python per-base loop under
            multiprocessing.Pool, SciPy p-values) timed on this box's host cores on a bounded sample.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank holds one hg19-sized shard of an
-N x 3.1 Gb genome plus its own 20 k genes; NCCL all-reduces the context totals, substitution counts and
-scale-factor sums and gathers the per-gene results on rank 0.
+Multi-GPU (torchrun, one rank per GPU), default --scaling strong: ONE 3.1 Gb genome; the windows are cut into N
+range slices, a rank scans its slice, ONE all_gather_into_tensor carries the trinucleotide rows and the partial genome
+totals, genes go to the rank that holds their first block (StrongShard).  --scaling weak keeps round 1's "one genome
+per rank" run for comparison.
 """
 import argparse
 import json
@@ -554,6 +556,73 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
 
 
 # ------------------------------------------------------------------------------------------------
+# FP64 side of the test stage at the sizes where it binds (BASELINE configs 5 and 3), outside the step's timing
+# ------------------------------------------------------------------------------------------------
+
+# FP64-pipe instructions per thread, from the ncu pass of tools/probe_fp64.py (profiles/r02_fp64_peak.txt):
+# sm__inst_executed_pipe_fp64.sum x 32 / number of threads
+FP64_INSTR_PER_PVALUE = 516704550 * 32 / 9_620_000          # dig_nb_burden_test, config-5 distribution of (k, alpha, p)
+FP64_INSTR_PER_SITE = 600193635 * 32 / 30_000_000           # dig_site_test, config 3 (Poisson(0.05) observed counts)
+FP64_PEAK_FALLBACK = 1.707e13                               # DFMA thread-instructions/s measured by tools/micro_dfma.cu
+
+
+def fp64_extras(dg, di, device):
+    """Timings of the two kernels of the test stage that are FP64-bound at scale: 37 cohorts x 20 k genes x 13 tests
+    (config 5) through ONE launch of the burden-test kernel, and 30 M one-site site sets (config 3).  `fp64_frac` =
+    FP64-pipe instructions (static count per item from the committed ncu pass) / time / measured DFMA peak."""
+    import torch
+    from digdriver_b200 import kernels
+    peak = FP64_PEAK_FALLBACK
+    exe = os.path.join(ROOT, "tools", "micro_dfma")
+    src = "tools/micro_dfma.cu on an earlier box of this pool (profiles/r02_fp64_peak.txt)"
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=60).stdout
+            for ln in out.splitlines():
+                if ln.startswith("fp64_peak_dfma_per_s"):
+                    peak, src = float(ln.split()[1]), "tools/micro_dfma measured in this run"
+        except Exception:
+            pass
+
+    def best_ms(fn, n=3):
+        fn()
+        torch.cuda.synchronize(device)
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize(device)
+            ts.append(a.elapsed_time(b))
+        return min(ts)
+
+    g = torch.Generator(device=device)
+    g.manual_seed(7)
+    n5 = 37 * N_GENES * 13
+    mu = torch._standard_gamma(torch.full((n5,), 2.0, dtype=torch.float64, device=device)) * 20.0
+    sigma = mu * (0.05 + 0.45 * torch.rand(n5, dtype=torch.float64, device=device, generator=g))
+    alpha, theta = mu ** 2 / sigma ** 2, sigma ** 2 / mu
+    pi = 1e-4 + (0.05 - 1e-4) * torch.rand(n5, dtype=torch.float64, device=device, generator=g)
+    k = torch.poisson(mu * pi)
+    ms5 = best_ms(lambda: kernels.nb_burden_test(k, alpha, theta, pi, device))
+    del mu, sigma, alpha, theta, pi, k
+    n3 = 30_000_000
+    n_win = di.win_chrom.numel()
+    w = torch.randint(0, n_win, (n3,), device=device, generator=g)
+    chrom = di.win_chrom[w]
+    start = di.win_start[w] + torch.randint(0, WINDOW, (n3,), device=device, generator=g)
+    sub = torch.randint(0, 192, (n3,), device=device, generator=g).to(torch.uint8)
+    kk = torch.poisson(torch.full((n3,), 0.05, dtype=torch.float64, device=device))
+    d_pr = torch.exp(torch.randn(192, dtype=torch.float64, device=device, generator=g) - 13.8)
+    ms3 = best_ms(lambda: kernels.site_test(chrom, start, sub, kk, WINDOW, di.wmap_off, di.wmap, di.counts3, di.y_pred, di.std,
+                                            d_pr, cj=1.37, device=device, want=()), n=2)
+    return {"fp64_peak_thread_instr_per_s": peak, "fp64_peak_source": src,
+            "config5_burden_test": {"p_values": n5, "ms": ms5, "p_values_per_s": n5 / ms5 * 1e3,
+                                    "fp64_frac": n5 * FP64_INSTR_PER_PVALUE / (ms5 * 1e-3) / peak},
+            "config3_site_test": {"sites": n3, "ms": ms3, "sites_per_s": n3 / ms3 * 1e3,
+                                  "fp64_frac": n3 * FP64_INSTR_PER_SITE / (ms3 * 1e-3) / peak}}
+
+
+# ------------------------------------------------------------------------------------------------
 # e2e leg: host buffers in, host buffers out
 # ------------------------------------------------------------------------------------------------
 
@@ -975,6 +1044,13 @@ def main():
                        "d2h_bytes_per_step": d2h, "source": "pinned host ASCII genome (1 B/base), K1 pack on the device"}
         del hp, hg_ascii
 
+    fp64 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            fp64 = fp64_extras(dg, di, device)
+        except Exception as exc:      # report, never hide
+            fp64 = {"error": repr(exc)[:200]}
+
     clocks.mark_end()
     clock_info = clocks.stop()
 
@@ -1036,7 +1112,7 @@ def main():
             "cuda_graph": {"test_stage_captured": stepper.graph is not None, "error": stepper.error},
             "host_placement": placement,
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity_sample": parity}
+            "cpu_baseline": cpu_baseline, "parity_sample": parity, "test_stage_fp64": fp64}
     if strong:
         sh = di.shard
         line["sharding"] = {"windows_per_rank": [b - a for a, b in sh.table.parts], "genes_per_rank": sh.genes_per_rank,

@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(THREADS, PRIVATE ? 3 : 3) scan_sym_kernel(
     int64_t n_words32, const int64_t *__restrict__ chrom_off, const int64_t *__restrict__ chrom_len,
     const int32_t *__restrict__ reg_chrom, const int64_t *__restrict__ reg_start,
     const int64_t *__restrict__ reg_end, const int8_t *__restrict__ reg_strand, int64_t n_reg,
-    int32_t *__restrict__ counts, unsigned long long *__restrict__ totals, unsigned int tot_limit_kb)
+    int32_t *__restrict__ counts, unsigned long long *__restrict__ totals, unsigned int tot_limit_kb,
+    const int32_t *__restrict__ rlist, const int32_t *__restrict__ rlist_n)
 {
     constexpr int D = U;
     constexpr int KLEN = 2 * U + 1;
@@ -88,7 +89,10 @@ __global__ void __launch_bounds__(THREADS, PRIVATE ? 3 : 3) scan_sym_kernel(
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
 
-    for (int64_t r = gwarp; r < n_reg; r += nwarps) {
+    // rlist != null: only the regions listed (the lane-bank kernel's redo list, scan_lb.cu); its length is read on the device
+    const int64_t n_items = rlist != nullptr ? (int64_t)__ldg(rlist_n) : n_reg;
+    for (int64_t item = gwarp; item < n_items; item += nwarps) {
+        const int64_t r = rlist != nullptr ? (int64_t)__ldg(rlist + item) : item;
         const RegionSpan sp = region_span(chrom_off, chrom_len, reg_chrom, reg_start, reg_end, r, U, D, U, D);
         const bool minus = reg_strand != nullptr && __ldg(reg_strand + r) < 0;
         if (sp.ge > sp.gs) {
@@ -493,7 +497,8 @@ template <int U, bool PRIVATE>
 int launch_sym(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
                const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start,
                const int64_t *reg_end, const int8_t *reg_strand, int64_t n_reg, int32_t *counts,
-               unsigned long long *totals, unsigned int tot_limit_kb, cudaStream_t stream)
+               unsigned long long *totals, unsigned int tot_limit_kb, cudaStream_t stream,
+               const int32_t *rlist = nullptr, const int32_t *rlist_n = nullptr)
 {
     constexpr int K = 1 << (2 * (2 * U + 1));
     constexpr size_t HIST_BYTES = (size_t)K << (PRIVATE ? 7 : 2);
@@ -512,12 +517,25 @@ int launch_sym(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const in
     kern<<<(unsigned)blocks, THREADS, smem, stream>>>(reinterpret_cast<const uint2 *>(p2), p2, nm,
                                                       (n_bases + 31) >> 5, chrom_off, chrom_len, reg_chrom,
                                                       reg_start, reg_end, reg_strand, n_reg, counts, totals,
-                                                      tot_limit_kb);
+                                                      tot_limit_kb, rlist, rlist_n);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
 
 }  // namespace
+
+namespace digscan {
+
+int launch_scan_tri_list(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, const int64_t *chrom_off,
+                         const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start,
+                         const int64_t *reg_end, int64_t n_reg, int32_t *counts3, unsigned long long *totals3,
+                         unsigned int tot_limit_kb, const int32_t *rlist, const int32_t *rlist_n, cudaStream_t stream)
+{
+    return launch_sym<1, true>(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, nullptr, n_reg, counts3,
+                               totals3, tot_limit_kb, stream, rlist, rlist_n);
+}
+
+}  // namespace digscan
 
 extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint32_t *nmask_d, int64_t n_bases,
                                          const int64_t *chrom_off_d, const int64_t *chrom_len_d,
@@ -585,6 +603,13 @@ extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nma
         scan_lb_usable(packed2_d, nmask_d, n_bases, counts_d, so.workspace, so.workspace_bytes, n_reg))
         return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                               n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb, so.workspace, so.tile_window, st);
+    // (the lane-bank kernel works in batches of 32 regions, one CTA per batch: with fewer than two batches per SM -- e.g.
+    // 3 100 windows of 1 Mb -- the per-warp kernel spreads the work better)
+    if (n_up == 1 && n_down == 1 && reg_strand_d == nullptr && so.variant == DIG_SCAN_AUTO &&
+        n_reg >= (int64_t)64 * dig::sm_count() &&
+        scan_lb_usable(packed2_d, nmask_d, n_bases, counts_d, so.workspace, so.workspace_bytes, n_reg))
+        return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
+                              n_reg, nullptr, counts_d, nullptr, totals_d, so.tot_limit_kb, so.workspace, so.tile_window, st);
     if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                                n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb,

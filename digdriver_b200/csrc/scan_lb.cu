@@ -62,6 +62,7 @@ __device__ __forceinline__ int lb_win(int lane) { return (lane >> 2) + 8 * (lane
 __device__ __forceinline__ uint32_t lb_dstrip(int lane) { return (uint32_t)(lane >> 2) * LB_DGROUP + (uint32_t)(lane & 3) * LB_DSTRIDE; }
 __device__ __forceinline__ uint32_t lb_mstrip(int lane) { return LB_MBASE + (uint32_t)(lane >> 2) * LB_MGROUP + (uint32_t)(lane & 3) * LB_MSTRIDE; }
 constexpr int LB_MAX_CHUNKS = 16;                  // regions up to ~32 kb; longer ones go to the per-warp kernel
+constexpr int LB_MAX_CHUNKS_TRI = 1 << 18;         // trinucleotide-only mode counts in 32 bits: regions up to 536 Mb
 constexpr int LB_EXC_CAP = 508;
 
 constexpr uint32_t OFF_TAB = 0u;                                   // [1024 rows][32 lanes] words
@@ -82,6 +83,21 @@ static_assert(OFF_BAR % 16u == 0u, "barrier block alignment");
 static_assert(LB_SMEM <= 232448u, "shared memory budget");
 
 enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_OUTFULL = 4, BAR_OUTEMPTY = 8, BAR_DONE = 12, BAR_CLEAN = 13 };
+
+// Staging ring per mode.  The pentanucleotide modes have room for two stages next to their 128 KB table and the slice
+// buffers; the trinucleotide-only mode (32 KB table, no slice buffers) runs FOUR, which hides the ~3 k cycles between a
+// stage's release and its refill (poll + issue + copy latency) behind three chunks of work instead of one.
+template <int GM>
+struct LbRing {
+    static constexpr uint32_t NST = 2u, LOG = 1u, STG0 = OFF_STG, FULL0 = BAR_FULL, EMPTY0 = BAR_EMPTY;
+};
+constexpr uint32_t TRI_TAB_BYTES = 256u * 128u;                      // [256 4-mers][32 lanes] words
+template <>
+struct LbRing<2> {
+    static constexpr uint32_t NST = 4u, LOG = 2u, STG0 = TRI_TAB_BYTES, FULL0 = 0u, EMPTY0 = 4u;
+};
+enum { TBAR_OUTFULL = 8, TBAR_DONE = 9, TBAR_CLEAN = 10 };           // barrier slots of the trinucleotide-only mode
+static_assert(LbRing<2>::STG0 + 4u * LB_STAGE_BYTES <= OFF_TRI, "trinucleotide-only layout: stages end before the row block");
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt)
@@ -226,7 +242,8 @@ struct LbGeom {
 };
 
 // second half of lb_geom: the region descriptor (c, rs, re) is already in registers
-template <bool TRI>
+// GM: 0 = pentanucleotide table, 1 = pentanucleotide + trinucleotide, 2 = trinucleotide only (lb_*_tri below)
+template <int GM>
 __device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, int64_t re, const int64_t *__restrict__ chrom_off,
                                            const int64_t *__restrict__ chrom_len)
 {
@@ -251,7 +268,10 @@ __device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, i
             if (ge[t] < gs[t]) ge[t] = gs[t];
         }
         int64_t lowc = gs[0], hic = ge[0];
-        if (TRI) {
+        if (GM == 2) {
+            lowc = gs[1];
+            hic = ge[1];
+        } else if (GM == 1) {
             if (ge[1] > gs[1]) {
                 if (ge[0] > gs[0]) {
                     lowc = gs[1] < gs[0] ? gs[1] : gs[0];
@@ -263,9 +283,11 @@ __device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, i
             }
         }
         if (hic > lowc) {
+            // (tried: a whole span of lead-in, O = floor(lowc / 128) * 128 - 128, so that all windows of a tiling begin and
+            // end in the same spans and no warp runs both bodies; measured 1 % slower -- one span in eighty does no work)
             const int64_t O = ((lowc - 2) >> 7) << 7;       // arithmetic shift: floor
             const int64_t nch = (hic - O - 2 + (LB_CHUNK - 1)) / LB_CHUNK;
-            if (nch > LB_MAX_CHUNKS) {
+            if (nch > (GM == 2 ? LB_MAX_CHUNKS_TRI : LB_MAX_CHUNKS)) {
                 g.too_long = true;
             } else {
                 g.O = O;
@@ -280,7 +302,7 @@ __device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, i
     return g;
 }
 
-template <bool TRI>
+template <int GM>
 __device__ __forceinline__ LbGeom lb_geom(int64_t r, int64_t n_reg, const int64_t *__restrict__ chrom_off,
                                           const int64_t *__restrict__ chrom_len,
                                           const int32_t *__restrict__ reg_chrom,
@@ -294,7 +316,7 @@ __device__ __forceinline__ LbGeom lb_geom(int64_t r, int64_t n_reg, const int64_
         rs = __ldg(reg_start + r);
         re = __ldg(reg_end + r);
     }
-    return lb_geom2<TRI>(r < n_reg, c, rs, re, chrom_off, chrom_len);
+    return lb_geom2<GM>(r < n_reg, c, rs, re, chrom_off, chrom_len);
 }
 
 // word idx (0..8) of the thread's nine 16-base words without dynamic register indexing
@@ -391,7 +413,7 @@ struct LbMaps {
     CUtensorMap d[2], m[2];   // bases / mask, each with two row phases (a box must not cross the end of a row)
 };
 
-template <bool TRI>
+template <int GM>
 __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps, uint32_t sbase, int pw, int lane)
 {
     const uint32_t bar = sbase + OFF_BAR;
@@ -400,7 +422,7 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
     const bool mine = (lane >> 3) == pw;
     uint32_t ci = 0u;
     for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x) {
-        const LbGeom g = lb_geom<TRI>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const LbGeom g = lb_geom<GM>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const int nch = warp_max(g.nch);
         // regular group: every window has the leader's chunk count and sits m * 8 W bases after the leader's origin
         const int lead = lane & ~3;
@@ -425,12 +447,13 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
         }
         for (int kq = 0; kq < nch; ++kq, ++ci) {
             const int k = lb_chunk_order(kq, nch);
-            const uint32_t stage = ci & 1u;
+            using R = LbRing<GM>;
+            const uint32_t stage = ci & (R::NST - 1u);
             LB_T(t_e0);
-            mbar_wait_idle(bar + 8u * (BAR_EMPTY + stage), ((ci >> 1) & 1u) ^ 1u);
+            mbar_wait_idle(bar + 8u * (R::EMPTY0 + stage), ((ci >> R::LOG) & 1u) ^ 1u);
             LB_T(t_e1);
-            const uint32_t full = bar + 8u * (BAR_FULL + stage);
-            const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
+            const uint32_t full = bar + 8u * (R::FULL0 + stage);
+            const uint32_t stg = sbase + R::STG0 + stage * LB_STAGE_BYTES;
             if (!mine) {
                 // another producer warp's window
             } else if (regular && k < g.nch) {
@@ -470,7 +493,7 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
 #ifdef DIG_LB_TIMING
             if (pw == 0) {                                                   // copy latency: issued -> FULL complete
                 const long long t_i = clock64();
-                mbar_wait(full, (ci >> 1) & 1u);
+                mbar_wait(full, (ci >> R::LOG) & 1u);
                 if (lane == 0 && A.timing != nullptr) {
                     atomicAdd(A.timing + 7, (unsigned long long)(clock64() - t_i));
                     atomicAdd(A.timing + 11, (unsigned long long)(t_e1 - t_e0));      // producer idle (EMPTY wait)
@@ -522,6 +545,15 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
             LB_ACC(0, t_a, t_b);
             LB_ACC((kq == 0 ? 8 : (kq == 1 ? 9 : 10)), t_a, t_b);
             const uint32_t stg = sbase + OFF_STG + stage * LB_STAGE_BYTES;
+            {
+                // a span that holds no centre of any lane's window (the lead-in span, the tail of the last chunk)
+                const int base0 = k * LB_CHUNK + warp * LB_SPAN;
+                const int lo_u = TRI ? min(g.lo5, g.lo3) : g.lo5, hi_u = TRI ? max(g.hi5, g.hi3) : g.hi5;
+                if (!__any_sync(0xffffffffu, k < g.nch && lo_u - base0 < 130 && hi_u - base0 > 2)) {
+                    if (lane == 0) mbar_arrive(bar + 8u * (BAR_EMPTY + stage));
+                    continue;
+                }
+            }
             const uint32_t dptr = stg + lb_dstrip(lane) + (uint32_t)warp * 32u;
             const uint32_t mptr = stg + lb_mstrip(lane) + (uint32_t)warp * 16u;
             uint32_t D[9], M[5];
@@ -836,6 +868,280 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
     bulk_wait_all();
 }
 
+// =====================================================================================================
+// Trinucleotide-only mode (K = 64: the reference's default `countGenomeContext --up 1 --down 1`, and the scan of the
+// range-sharded element job).  Same staging, same lane = window = bank transposition, but the table is small:
+//   * pairs of adjacent centres are counted as ONE 4-mer (bases 2i+1 .. 2i+4 hold the trinucleotides centred on 2i+2
+//     and 2i+3): 256 bins per window as full 32-bit counters = [256 rows][32 lanes] words, 32 KB per batch.  No packed
+//     fields, so the increment is the constant 1 (ATOMS.POPC.INC) and nothing can overflow: 2 integer instructions + 1
+//     multiply-add + 1 atomic per TWO bases (the per-warp kernel of scan.cu spends 3 + 1 per base).
+//   * write-out: bin xyz = sum_d T[xyz d] + sum_a T[a xyz]; warp w produces bins 4w .. 4w+3 of window `lane` from 32
+//     conflict-free word reads and puts them into the [64][33] block that writer warp 0 stores as rows.  It is 1/16 of
+//     the pentanucleotide write-out, so the batch is dominated by the counting phase.
+//   * centres whose pair partner is invalid (N, region edge) go through the exception list, as in the fused mode.
+template <bool PRED>
+__device__ __forceinline__ void lb_pairs4(const uint32_t (&D)[9], uint32_t tabl, uint32_t k128, const uint32_t (&PV)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const int q = i >> 3, off = 4 * (i & 7);
+        uint32_t r;                                          // 4-mer = bases 2i+1 .. 2i+4 in the low 8 bits
+        if (off <= 20) r = D[q] >> (22 - off);
+        else r = __funnelshift_r(D[q + 1], D[q], 54 - off);
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(r & 0xFFu), "r"(k128), "r"(tabl));
+        if constexpr (!PRED) {
+            red_add(addr, 1u);
+        } else {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr),
+                         "r"(PV[i >> 4] & (0x80000000u >> (2 * (i & 15))))
+                         : "memory");
+        }
+    }
+}
+
+__device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase, int warp, int lane)
+{
+    const uint32_t bar = sbase + OFF_BAR;
+    const uint32_t tabl = sbase + OFF_TAB + (uint32_t)lane * 4u;
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    const uint32_t k128 = A.k32 << 2;
+    uint32_t cit = 0u, bi = 0u;
+#ifdef DIG_LB_TIMING
+    unsigned long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    LB_T(t_k0);
+    LbGeom gnext = lb_geom<2>((int64_t)blockIdx.x * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
+        const LbGeom g = gnext;
+        const int nch = warp_max(g.nch);
+        const uint32_t exc = sbase + OFF_EXC + (bi & 1u) * EXC_BYTES;
+        bool clean = bi == 0u;
+        // the next batch's descriptor is requested at the start of this one: its two dependent loads resolve during the scan
+        const int64_t rn = (b + gridDim.x) * 32 + lb_win(lane);
+        const bool nact = b + gridDim.x < n_batches && rn < A.n_reg;
+        int32_t nc = 0;
+        int64_t nrs = 0, nre = 0;
+        if (nact) {
+            nc = __ldg(A.reg_chrom + rn);
+            nrs = __ldg(A.reg_start + rn);
+            nre = __ldg(A.reg_end + rn);
+        }
+        for (int kq = 0; kq < nch; ++kq, ++cit) {
+            const int k = lb_chunk_order(kq, nch);                           // the order the producers stage the chunks in
+            using R = LbRing<2>;
+            const uint32_t stage = cit & (R::NST - 1u);
+            LB_T(t_a);
+            mbar_wait(bar + 8u * (R::FULL0 + stage), (cit >> R::LOG) & 1u);
+            LB_T(t_b);
+            LB_ACC(0, t_a, t_b);
+            const uint32_t stg = sbase + R::STG0 + stage * LB_STAGE_BYTES;
+            if (!__any_sync(0xffffffffu, k < g.nch && g.lo3 - (k * LB_CHUNK + warp * LB_SPAN) < 130 &&
+                                             g.hi3 - (k * LB_CHUNK + warp * LB_SPAN) > 2)) {
+                if (lane == 0) mbar_arrive(bar + 8u * (R::EMPTY0 + stage));   // no centre of any lane's window in this span
+                if (kq == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
+                continue;
+            }
+            const uint32_t dptr = stg + lb_dstrip(lane) + (uint32_t)warp * 32u;
+            const uint32_t mptr = stg + lb_mstrip(lane) + (uint32_t)warp * 16u;
+            uint32_t D[9], M[5];
+            {
+                const uint4 a = lds128(dptr), c = lds128(dptr + 16u), m = lds128(mptr);
+                D[0] = a.x; D[1] = a.y; D[2] = a.z; D[3] = a.w;
+                D[4] = c.x; D[5] = c.y; D[6] = c.z; D[7] = c.w;
+                D[8] = lds32(dptr + 32u);
+                M[0] = m.x; M[1] = m.y; M[2] = m.z; M[3] = m.w;
+                M[4] = lds32(mptr + 16u);
+            }
+            const uint32_t dep = (D[0] | D[4]) ^ (D[8] | M[0]) ^ M[4];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after_loads(bar + 8u * (R::EMPTY0 + stage), dep, A.zero);
+            if (!clean) {
+                LB_T(t_c);
+                mbar_wait(bar + 8u * TBAR_CLEAN, (bi - 1u) & 1u);
+                LB_T(t_d);
+                LB_ACC(1, t_c, t_d);
+                clean = true;
+            }
+            LB_T(t_p0);
+            const int base = k * LB_CHUNK + warp * LB_SPAN;
+            const int lo3 = g.lo3 - base, hi3 = g.hi3 - base;                // centre c (local base index) valid: lo3 <= c < hi3
+            const uint32_t any_n = M[0] | M[1] | M[2] | M[3] | (M[4] & 0xF0000000u);
+            uint32_t PV[4] = {0u, 0u, 0u, 0u};
+            if (any_n == 0u && lo3 <= 2 && hi3 >= 130) {
+                lb_pairs4<false>(D, tabl, k128, PV);
+            } else if (k < g.nch) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // bit 31 - t of word j <-> centre at local base 32 j + t + 2, its trinucleotide = bases 32 j + t + 1 .. + 3
+                    const uint32_t s1 = __funnelshift_l(M[j + 1], M[j], 1), s2 = __funnelshift_l(M[j + 1], M[j], 2);
+                    const uint32_t s3 = __funnelshift_l(M[j + 1], M[j], 3);
+                    const uint32_t v3 = range_mask(lo3 - 2 - 32 * j, hi3 - 2 - 32 * j) & ~(s1 | s2 | s3);
+                    const uint32_t pv = v3 & (v3 << 1) & 0xAAAAAAAAu;        // both centres of the pair valid
+                    PV[j] = pv;
+                    uint32_t single = v3 & ~(pv | (pv >> 1));
+                    while (single) {
+                        const int t = __clz(single);
+                        single &= ~(0x80000000u >> t);
+                        const uint32_t key = lb_bits(D, 32 * j + t + 1, 6);
+                        const uint32_t pos = atom_add(exc, 1u);
+                        if (pos < (uint32_t)LB_EXC_CAP) sts32(exc + 16u + 4u * pos, ((uint32_t)lane << 16) | 0x8000u | key);
+                    }
+                }
+                if ((PV[0] | PV[1] | PV[2] | PV[3]) != 0u) lb_pairs4<true>(D, tabl, k128, PV);
+            }
+            if (kq == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
+            LB_T(t_p1);
+            LB_ACC(2, t_p0, t_p1);
+        }
+        if (nch == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
+        if (!clean) mbar_wait(bar + 8u * TBAR_CLEAN, (bi - 1u) & 1u);
+        LB_T(t_s0);
+        cons_sync();                                                         // every 4-mer of the batch is in the table
+        LB_T(t_sa);
+        LB_ACC(3, t_s0, t_sa);
+        mbar_wait(bar + 8u * TBAR_DONE, (bi & 1u) ^ 1u);                     // writer warp 0 has stored and re-zeroed the row block
+        LB_T(t_s1);
+        LB_ACC(4, t_sa, t_s1);
+        // ---- write-out: bins 4 warp .. 4 warp + 3 of window `lane`
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t bin = (uint32_t)(4 * warp + t);
+            uint32_t acc = 0u;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) acc += lds32(tabl + (bin * 4u + (uint32_t)d) * 128u);       // trinucleotide + next base
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc += lds32(tabl + ((uint32_t)a * 64u + bin) * 128u);      // previous base + trinucleotide
+            sts32(sbase + OFF_TRI + (bin * 33u + (uint32_t)lane) * 4u, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8u * TBAR_OUTFULL);                 // release: reads done, bins in place
+        LB_T(t_s2);
+        LB_ACC(6, t_s1, t_s2);
+    }
+#ifdef DIG_LB_TIMING
+    LB_T(t_k1);
+    LB_ACC(14, t_k0, t_k1);
+    if (A.timing != nullptr && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 15; ++q)
+            if (q != 7 && q != 11 && q != 12) atomicAdd(A.timing + q, tacc[q]);
+    }
+#endif
+}
+
+template <bool TOT>
+__device__ __forceinline__ void lb_writer_tri(const LbArgs &A, uint32_t sbase, int q, int lane)
+{
+    const uint32_t bar = sbase + OFF_BAR;
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    uint32_t bi = 0u;
+    unsigned int tot3[2] = {0u, 0u};
+    unsigned int acc_kb = 0u;
+    const uint32_t tri = sbase + OFF_TRI;
+    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
+        const LbGeom g = lb_geom<2>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+        const uint32_t exc = sbase + OFF_EXC + (bi & 1u) * EXC_BYTES;
+        const int64_t r = b * 32 + lb_win(lane);
+        mbar_wait_idle(bar + 8u * TBAR_OUTFULL, bi & 1u);                    // all sixteen consumer warps are done with the table
+        // hand the consumers a clean table: a quarter (64 rows = 8 KB) per writer warp
+#pragma unroll 8
+        for (int i = 0; i < 16; ++i)
+            sts128(sbase + OFF_TAB + (uint32_t)q * 8192u + (uint32_t)(lane + 32 * i) * 16u, 0u, 0u, 0u, 0u);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8u * TBAR_CLEAN);
+        if (q == 0) {
+            const uint32_t n_exc_raw = lds32(exc);
+            const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
+            for (uint32_t e = lane; e < n_exc; e += 32u) {
+                const uint32_t ent = lds32(exc + 16u + 4u * e);
+                red_add(tri + ((ent & 63u) * 33u + (ent >> 16)) * 4u, 1u);
+            }
+            __syncwarp();
+            const bool fail = n_exc_raw > (uint32_t)LB_EXC_CAP;              // list overflow: the whole batch is redone
+            unsigned long long tmp3[2] = {0ull, 0ull};
+#pragma unroll 4
+            for (int l2 = 0; l2 < 32; ++l2) {
+                const int64_t r2 = b * 32 + lb_win(l2);
+                const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
+                const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
+                if (r2 < A.n_reg && !fail) {
+                    __stcs(A.counts3 + r2 * 64 + lane, (int)v0);
+                    __stcs(A.counts3 + r2 * 64 + 32 + lane, (int)v1);
+                }
+                tmp3[0] += v0;
+                tmp3[1] += v1;
+            }
+            __syncwarp();
+#pragma unroll 6
+            for (int i = 0; i < 66; ++i) sts32(tri + (uint32_t)(lane + 32 * i) * 4u, 0u);
+            if (lane == 0) sts32(exc, 0u);
+            if (g.too_long || (fail && g.active)) {
+                const int pos = atomicAdd(A.fb_count, 1);
+                A.fb_list[pos] = (int32_t)r;
+            }
+            if constexpr (TOT) {
+                if (!fail) {
+                    unsigned int kb = g.nch > 0 ? (unsigned int)min(g.nch, 1 << 20) * (unsigned int)(LB_CHUNK >> 10) : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) kb += __shfl_xor_sync(0xffffffffu, kb, o);
+                    if (acc_kb + kb > A.tot_limit_kb || acc_kb + kb < acc_kb) {
+                        if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
+                        if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
+                        tot3[0] = tot3[1] = 0u;
+                        acc_kb = 0u;
+                    }
+                    if (kb > A.tot_limit_kb) {                               // one batch alone is beyond 32 bits: straight to the global totals
+                        atomicAdd(A.totals3 + lane, tmp3[0]);
+                        atomicAdd(A.totals3 + 32 + lane, tmp3[1]);
+                    } else {
+                        acc_kb += kb;
+                        tot3[0] += (unsigned int)tmp3[0];
+                        tot3[1] += (unsigned int)tmp3[1];
+                    }
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + 8u * TBAR_DONE);
+        }
+    }
+    if constexpr (TOT) {
+        if (q == 0) {
+            if (tot3[0]) atomicAdd(A.totals3 + lane, (unsigned long long)tot3[0]);
+            if (tot3[1]) atomicAdd(A.totals3 + 32 + lane, (unsigned long long)tot3[1]);
+        }
+    }
+}
+
+template <bool TOT>
+__global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_tri_kernel(const LbArgs A, const __grid_constant__ LbMaps imaps)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if ((sbase & 127u) != 0u) __trap();
+    for (uint32_t i = threadIdx.x; i < OFF_BAR / 16u; i += LB_THREADS) sts128(sbase + i * 16u, 0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) {
+        const uint32_t bar = sbase + OFF_BAR;
+        for (uint32_t st = 0; st < LbRing<2>::NST; ++st) {
+            mbar_init(bar + 8u * (LbRing<2>::FULL0 + st), 32u);
+            mbar_init(bar + 8u * (LbRing<2>::EMPTY0 + st), LB_CW);
+        }
+        mbar_init(bar + 8u * TBAR_OUTFULL, LB_CW);                          // all sixteen consumer warps per batch
+        mbar_init(bar + 8u * TBAR_DONE, 1u);
+        mbar_init(bar + 8u * TBAR_CLEAN, LB_WW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async();
+    }
+    __syncthreads();
+    if (warp >= LB_CW + LB_WW) lb_producer<2>(A, &imaps, sbase, warp - LB_CW - LB_WW, lane);
+    else if (warp >= LB_CW) lb_writer_tri<TOT>(A, sbase, warp - LB_CW, lane);
+    else lb_consumer_tri(A, sbase, warp, lane);
+}
+
 template <bool TRI, bool TOT>
 __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ LbMaps imaps)
@@ -942,6 +1248,23 @@ int lb_input_maps(LbMaps *maps, LbArgs &A, int64_t tile_w)
     return DIG_OK;
 }
 
+template <bool TOT>
+int launch_lb_tri(const LbArgs &A, const LbMaps &imaps, cudaStream_t stream)
+{
+    auto kern = scan_lb_tri_kernel<TOT>;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_SMEM));
+        attr_set = true;
+    }
+    const int64_t n_batches = (A.n_reg + 31) >> 5;
+    int64_t blocks = dig::sm_count();
+    if (blocks > n_batches) blocks = n_batches;
+    kern<<<(unsigned)blocks, LB_THREADS, LB_SMEM, stream>>>(A, imaps);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
+
 template <bool TRI, bool TOT>
 int launch_lb(const LbArgs &A, const CUtensorMap &tmap, const LbMaps &imaps, cudaStream_t stream)
 {
@@ -990,8 +1313,11 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
     int32_t *fb_count = reinterpret_cast<int32_t *>(workspace);
     int32_t *fb_list = fb_count + 4;
     CUtensorMap tmap;
-    const int trc = lb_tensor_map(&tmap, counts5, n_reg);
-    if (trc != DIG_OK) return trc;
+    memset(&tmap, 0, sizeof(tmap));
+    if (counts5 != nullptr) {                            // (null: trinucleotide-only mode, no tensor store)
+        const int trc = lb_tensor_map(&tmap, counts5, n_reg);
+        if (trc != DIG_OK) return trc;
+    }
     DIG_CUDA(cudaMemsetAsync(fb_count, 0, 16, stream));
     LbArgs A;
     A.p2 = p2; A.nmask = nm; A.n_bases = n_bases; A.chrom_off = chrom_off; A.chrom_len = chrom_len;
@@ -1008,6 +1334,14 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
     LbMaps imaps;
     int rc = lb_input_maps(&imaps, A, tile_window);
     if (rc != DIG_OK) return rc;
+    if (counts5 == nullptr) {
+        // trinucleotide table alone: 4-mer pairs in 32-bit lane-bank counters, then the per-warp kernel over the list
+        // (regions beyond LB_MAX_CHUNKS_TRI chunks, batches whose exception list overflowed)
+        rc = totals3 != nullptr ? launch_lb_tri<true>(A, imaps, stream) : launch_lb_tri<false>(A, imaps, stream);
+        if (rc != DIG_OK) return rc;
+        return launch_scan_tri_list(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts3,
+                                    totals3, tot_limit_kb, fb_list, fb_count, stream);
+    }
     if (counts3 != nullptr)
         rc = totals5 != nullptr ? launch_lb<true, true>(A, tmap, imaps, stream) : launch_lb<true, false>(A, tmap, imaps, stream);
     else

@@ -75,7 +75,7 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
         out = torch.empty((n, K), dtype=torch.int32, device=dev)
     if want_totals and totals is None:
         totals = torch.zeros(K, dtype=torch.int64, device=dev)
-    lane_bank = n_up == 2 and n_down == 2 and st is None and variant == _lib.SCAN_AUTO
+    lane_bank = (n_up, n_down) in ((2, 2), (1, 1)) and st is None and variant == _lib.SCAN_AUTO
     opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
                                            workspace if lane_bank else None,
                                            _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0)

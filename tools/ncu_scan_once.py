@@ -11,7 +11,8 @@ rc = torch.from_numpy(wins[:, 0].astype(np.int32)).cuda(); rs = torch.from_numpy
 out5 = torch.empty((len(wins), 1024), dtype=torch.int32, device="cuda")
 out3 = torch.empty((len(wins), 64), dtype=torch.int32, device="cuda")
 t5 = torch.zeros(1024, dtype=torch.int64, device="cuda"); t3 = torch.zeros(64, dtype=torch.int64, device="cuda")
+ws = kernels.scan_workspace(dg, len(wins))
 for _ in range(3):
-    kernels.count_contexts_fused53(dg, rc, rs, re, out5=out5, out3=out3, totals5=t5, totals3=t3)
+    kernels.count_contexts_fused53(dg, rc, rs, re, out5=out5, out3=out3, totals5=t5, totals3=t3, workspace=ws, tile_window=10_000)
 torch.cuda.synchronize()
 print("done")

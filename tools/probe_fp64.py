@@ -78,20 +78,14 @@ print("config 3  dig_site_test (+ window denominators)  %d sites: %.3f ms -> %.2
 
 # ---- worst case of the continued fraction: the alpha >= 5e4 rows of the golden grid, replicated to 1 M values
 z = np.load(os.path.join(ROOT, "tests", "golden", "nbtest.npz"))
-names = list(z.keys())
-ka = next((nm for nm in names if nm.endswith("grid_k") or nm == "k"), None)
-try:
-    gk, ga, gp = z["grid_k"], z["grid_alpha"], z["grid_p"]
-except KeyError:
-    print("golden grid arrays:", names)
-    gk = ga = gp = None
+gk, ga, gp = z["k"].astype(np.float64), z["alpha"].astype(np.float64), z["p"].astype(np.float64)
 if gk is not None:
     big = (ga >= 5e4) & np.isfinite(ga) & np.isfinite(gk) & np.isfinite(gp)
     reps = max(1, 1_000_000 // max(int(big.sum()), 1))
     wk, wa, wp = (torch.from_numpy(np.tile(x[big], reps)).to(dev) for x in (gk, ga, gp))
-    msw = timeit(lambda: kernels.nb_pvalue_midp(wk, wa, wp, dev))
+    msw = timeit(lambda: kernels.nb_pvalue_greater_midp(wk, wa, wp, dev))
     allk, alla, allp = (torch.from_numpy(np.tile(x, max(1, 1_000_000 // len(gk)))).to(dev) for x in (gk, ga, gp))
-    msa = timeit(lambda: kernels.nb_pvalue_midp(allk, alla, allp, dev))
+    msa = timeit(lambda: kernels.nb_pvalue_greater_midp(allk, alla, allp, dev))
     print("worst case  dig_nb_pvalue_greater_midp on the %d grid rows with alpha >= 5e4 (x%d = %d values): %.3f ms -> %.3f G p-values/s"
           % (int(big.sum()), reps, wk.numel(), msw, wk.numel() / msw / 1e6))
     print("whole grid  (%d values): %.3f ms -> %.3f G p-values/s" % (allk.numel(), msa, allk.numel() / msa / 1e6))
