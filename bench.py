@@ -65,6 +65,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-sample", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="strong scaling: trinucleotide rows stored into all ranks' symmetric buffers by the scan kernel "
+                         "(fused, falls back to nccl when symmetric memory is unavailable) or one NCCL all-gather")
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
                     help="N > 1: strong = ONE 3.1 Gb genome range-sharded over the ranks (default), weak = one genome per rank")
     return ap.parse_args()
@@ -273,12 +276,18 @@ def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
         ev[0].record()
     if getattr(di, "scan_ws", None) is None or di.scan_ws_n < hi - lo:
         di.scan_ws, di.scan_ws_n = kernels.scan_workspace(dg, hi - lo), hi - lo
+    fused = shard is not None and shard.fused
     if hi > lo:
         kernels.count_contexts_fused53(dg, di.win_chrom[lo:hi], di.win_start[lo:hi], di.win_end[lo:hi],
                                        out5=out5, out3=out3, totals5=tot5, totals3=tot3, workspace=di.scan_ws,
-                                       tile_window=WINDOW)
+                                       tile_window=WINDOW, peer_rows=shard.peer_rows if fused else None,
+                                       mc_rows=shard.mc_rows if fused else None)
     if ev is not None:
         ev[1].record()
+    if shard is not None:
+        if fused:
+            shard.finish_fused_exchange()
+        shard.table_ready = fused
 
 
 class StrongShard:
@@ -293,7 +302,7 @@ class StrongShard:
     -- cheaper than an all-reduce of the substitution counts; observed counts (K5) only for the rank's genes.
     Further exchanges: all-reduce of the five scale-factor sums, all-gather of the result rows."""
 
-    def __init__(self, d, di, coll, device):
+    def __init__(self, d, di, coll, device, fused_exchange=True):
         import torch
         from digdriver_b200 import kernels, sharding
         wins = d["wins"]
@@ -302,8 +311,34 @@ class StrongShard:
         self.table = sharding.GatheredTable(parts)
         self.lo, self.hi = parts[self.rank]
         gt = self.table
-        self.local = torch.zeros((gt.block_rows, 64), dtype=torch.int32, device=device)
-        self.gathered = torch.zeros((self.world, gt.block_rows, 64), dtype=torch.int32, device=device)
+        # The exchange buffer lives in symmetric (peer-mapped) memory when the platform offers it: the scan kernel then
+        # stores every trinucleotide row straight into all ranks' copies (NVSwitch multicast store, or one store per peer),
+        # the 8.7 KB of partial totals follow with dig_peer_broadcast, and a device barrier replaces the collective.
+        self.fused, self.fused_note, self.symm = False, "disabled (--exchange nccl)", None
+        n_words = self.world * gt.block_rows * 64
+        if fused_exchange:
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(n_words, dtype=torch.int32, device=device)
+                self.symm = symm.rendezvous(buf, dist.group.WORLD)
+                buf.zero_()
+                self.gathered = buf.view(self.world, gt.block_rows, 64)
+                blk = gt.block_rows * 64 * 4
+                self.peer_rows = [int(self.symm.buffer_ptrs[p_]) + self.rank * blk for p_ in range(self.world)]
+                self.peer_tail = [a + gt.m * 64 * 4 for a in self.peer_rows if a != self.peer_rows[self.rank]]
+                mc = int(getattr(self.symm, "multicast_ptr", 0) or 0)
+                self.mc_rows = mc + self.rank * blk if mc and os.environ.get("DIG_NO_MULTICAST", "") == "" else 0
+                self.fused = True
+                self.fused_note = "symmetric memory, %s" % ("multimem stores through the NVSwitch multicast alias" if self.mc_rows
+                                                            else "one store per peer over NVLink")
+            except Exception as exc:      # report, never hide: the NCCL all-gather is the fallback
+                self.fused, self.fused_note = False, "symmetric memory unavailable: %r" % (exc,)
+        if not self.fused:
+            self.gathered = torch.zeros((self.world, gt.block_rows, 64), dtype=torch.int32, device=device)
+        # this rank's block, in place: the scan writes its rows and totals where the other ranks expect them
+        self.local = self.gathered[self.rank]
+        self.table_ready = False
         self.rows, self.tot5, self.tot3 = gt.local_views(self.local)
         off, wmap = gt.window_map(wins[:, 0], wins[:, 1], WINDOW, len(d["lengths"]))
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)
@@ -345,8 +380,17 @@ class StrongShard:
         self.exchange_bytes = int(self.gathered.numel() * 4)
 
     def all_gather_table(self):
+        """NCCL exchange (in place: this rank's block already sits at its offset of the output)."""
         import torch.distributed as dist
         dist.all_gather_into_tensor(self.gathered.view(-1, 64), self.local)
+
+    def finish_fused_exchange(self):
+        """After a scan that stored its rows into every rank's buffer: send the partial totals after them and meet the
+        other ranks (device-side barrier on the current stream; no host synchronisation)."""
+        from digdriver_b200 import kernels
+        if self.peer_tail:
+            kernels.peer_broadcast(self.local[self.table.m:], self.peer_tail)
+        self.symm.barrier(channel=0)
 
     def totals(self):
         return self.table.summed_totals(self.gathered)
@@ -412,7 +456,8 @@ def strong_test_stage(dg, di, d, dist_ctx, shard, sink):
             mc, mp, mr, ma = shard.k3_by_range
             ctx = kernels.mutation_contexts(dg, mc, mp, mr, 1, 1)
             sub = kernels.substitution_counts(ctx, ma, 1, 1)
-    shard.all_gather_table()                             # THE exchange: trinucleotide rows + partial totals, one collective
+    if not shard.table_ready:
+        shard.all_gather_table()                         # THE exchange: trinucleotide rows + partial totals, one collective
     tot = shard.totals()
     main.wait_stream(side)
     if not torch.cuda.is_current_stream_capturing():
@@ -708,6 +753,7 @@ class HostPath:
                       "m_gene", "m_sample", "m_cls"):
                 setattr(sh, k, t[k])
             sh.k3_by_range = (t["k3_chrom"], t["k3_pos"], t["k3_ref"], t["k3_alt"])
+            sh.table_ready = False                            # the host path's rows are exchanged with NCCL
             n_loc = shard.hi - shard.lo
             sh.rows[:n_loc].copy_(hs.counts3)                 # into this rank's block of the exchange buffer
             sh.tot5.copy_(hs.totals)
@@ -934,7 +980,7 @@ def main():
     dg, ascii_d, d = build_workload(args.bases, seed=seed, device=device)
     di = DeviceInputs(d, device)
     if strong:
-        di.shard = StrongShard(d, di, dist_ctx, device)
+        di.shard = StrongShard(d, di, dist_ctx, device, fused_exchange=args.exchange == "fused")
         n_local = float((d["wins"][di.shard.lo:di.shard.hi, 2] - d["wins"][di.shard.lo:di.shard.hi, 1]).sum())
         n_total = float((d["wins"][:, 2] - d["wins"][:, 1]).sum())
         n_genes_total = N_GENES
@@ -1115,10 +1161,12 @@ def main():
             "cpu_baseline": cpu_baseline, "parity_sample": parity, "test_stage_fp64": fp64}
     if strong:
         sh = di.shard
+        how = ("trinucleotide rows stored into every rank's buffer BY THE SCAN KERNEL (%s), partial totals by one "
+               "dig_peer_broadcast, one device barrier" % sh.fused_note) if sh.fused else \
+              ("1 all_gather_into_tensor of %.1f MB (trinucleotide rows + partial totals) [%s]" % (sh.exchange_bytes / 1e6, sh.fused_note))
         line["sharding"] = {"windows_per_rank": [b - a for a, b in sh.table.parts], "genes_per_rank": sh.genes_per_rank,
-                            "exchange": "1 all_gather_into_tensor of %.1f MB (trinucleotide rows + partial totals), "
-                                        "1 all_reduce of 4 doubles, 1 all_gather_into_tensor of the result rows; all "
-                                        "inside the CUDA graph" % (sh.exchange_bytes / 1e6),
+                            "exchange": how + "; then 1 all_reduce of 4 doubles and 1 all_gather_into_tensor of the result "
+                                              "rows inside the CUDA graph",
                             "scan_kernel_ms_max_over_ranks": k5_ms}
     emit_json(line)
     finish()

@@ -33,9 +33,43 @@ __global__ void __launch_bounds__(256) narrow_u16_kernel(const int4 *__restrict_
     if (bad & 0xFFFF0000u) atomicOr(status, 1);       // a negative value has its top bits set as well
 }
 
+struct PeerDst {
+    uint4 *p[8];
+};
+
+__global__ void __launch_bounds__(256) peer_broadcast_kernel(const uint4 *__restrict__ src, int64_t n16, PeerDst dst, int n_dst)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = src[i];
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (d < n_dst) dst.p[d][i] = v;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int dig_peer_broadcast(const void *src_d, int64_t nbytes, void *const *dst_d, int n_dst, void *stream)
+{
+    DIG_CHECK_ARG(nbytes >= 0 && (nbytes & 15) == 0 && n_dst >= 0 && n_dst <= 8, "nbytes must be a multiple of 16, n_dst <= 8");
+    if (nbytes == 0 || n_dst == 0) return DIG_OK;
+    DIG_CHECK_ARG(src_d && dst_d, "null pointer");
+    PeerDst dst;
+    for (int d = 0; d < 8; ++d) {
+        dst.p[d] = d < n_dst ? reinterpret_cast<uint4 *>(dst_d[d]) : nullptr;
+        DIG_CHECK_ARG(d >= n_dst || (dst_d[d] != nullptr && (reinterpret_cast<uintptr_t>(dst_d[d]) & 15u) == 0), "bad destination");
+    }
+    DIG_CHECK_ARG((reinterpret_cast<uintptr_t>(src_d) & 15u) == 0, "src_d must be 16-byte aligned");
+    const int64_t n16 = nbytes >> 4;
+    int64_t blocks = (n16 + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    peer_broadcast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4 *>(src_d), n16, dst, n_dst);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
 
 int dig_narrow_counts_u16(const int32_t *counts_d, int64_t n_values, uint16_t *out_d, int32_t *status_d, void *stream)
 {

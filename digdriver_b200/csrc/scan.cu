@@ -35,6 +35,9 @@ struct ScanOpts {
     int variant = DIG_SCAN_AUTO;
     unsigned int tot_limit_kb = 1u << 20;   // kilobases a CTA may fold into 32-bit partial totals before it goes global
     int64_t tile_window = 0;
+    int n_peer = 0;
+    void *const *peer3 = nullptr;
+    void *mc3 = nullptr;
 };
 
 ScanOpts scan_opts(const dig_scan_opts *o)
@@ -46,6 +49,11 @@ ScanOpts scan_opts(const dig_scan_opts *o)
         r.variant = o->variant;
         if (o->totals_limit_kb != 0u) r.tot_limit_kb = o->totals_limit_kb;
         r.tile_window = o->tile_window;
+        if (o->n_peer_counts3 > 0) {
+            r.n_peer = o->n_peer_counts3 < 8 ? o->n_peer_counts3 : 8;
+            r.peer3 = o->peer_counts3_d;
+            r.mc3 = o->mc_counts3_d;
+        }
     }
     return r;
 }
@@ -558,7 +566,8 @@ extern "C" int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint3
         scan_lb_usable(packed2_d, nmask_d, n_bases, counts5_d, so.workspace, so.workspace_bytes, n_reg))
         return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                               n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb, so.workspace,
-                              so.tile_window, (cudaStream_t)stream);
+                              so.tile_window, (cudaStream_t)stream, so.n_peer, so.peer3, so.mc3);
+    DIG_CHECK_ARG(so.n_peer == 0, "peer_counts3_d needs the lane-bank kernel (workspace, 128-base aligned genome, variant AUTO)");
     if (so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                                n_reg, counts5_d, counts3_d, totals5_d, totals3_d, so.tot_limit_kb,
@@ -609,7 +618,10 @@ extern "C" int dig_count_contexts(const uint32_t *packed2_d, const uint32_t *nma
         n_reg >= (int64_t)64 * dig::sm_count() &&
         scan_lb_usable(packed2_d, nmask_d, n_bases, counts_d, so.workspace, so.workspace_bytes, n_reg))
         return launch_scan_lb(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
-                              n_reg, nullptr, counts_d, nullptr, totals_d, so.tot_limit_kb, so.workspace, so.tile_window, st);
+                              n_reg, nullptr, counts_d, nullptr, totals_d, so.tot_limit_kb, so.workspace, so.tile_window, st,
+                              so.n_peer, so.peer3, so.mc3);
+    DIG_CHECK_ARG(so.n_peer == 0, "peer_counts3_d needs the trinucleotide lane-bank kernel (n_up = n_down = 1, plus strand, "
+                                  "workspace, >= 64 regions per SM, variant AUTO)");
     if (n_up == 2 && n_down == 2 && reg_strand_d == nullptr && so.variant != DIG_SCAN_PER_BASE)
         return launch_scan_hex(packed2_d, nmask_d, n_bases, chrom_off_d, chrom_len_d, reg_chrom_d, reg_start_d, reg_end_d,
                                n_reg, counts_d, nullptr, totals_d, nullptr, so.tot_limit_kb,

@@ -166,6 +166,6 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
                    const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                    int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
                    unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, int64_t tile_window,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int n_peer = 0, void *const *peer_counts3 = nullptr, void *mc_counts3 = nullptr);
 
 }  // namespace digscan

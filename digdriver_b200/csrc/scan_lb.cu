@@ -393,7 +393,37 @@ struct LbArgs {
     int64_t tile_w;           // > 0: the caller says the regions tile chromosomes with windows of this size (a multiple of 16)
     int64_t dshift, mshift;   // element offsets of the second row phase of the input tensor maps
     unsigned long long *timing;   // DIG_LB_TIMING builds only: phase counters (cycles summed over consumer warps)
+    // fused all-gather of the trinucleotide rows (range-sharded runs, dig_scan_opts::peer_counts3_d): n_peer > 0 sends
+    // every row to the same place in each rank's buffer -- one multimem store through the NVSwitch multicast alias when
+    // there is one, else one store per peer over NVLink -- instead of counts3
+    int n_peer;
+    int32_t *mc3;
+    int32_t *peer3[8];
 };
+
+__device__ __forceinline__ void lb_store_tri(const LbArgs &A, int64_t off, int v)
+{
+    if (A.n_peer == 0) {
+        __stcs(A.counts3 + off, v);
+    } else if (A.mc3 != nullptr) {
+        asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(A.mc3 + off), "r"(v) : "memory");
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            if (p < A.n_peer) __stcs(A.peer3[p] + off, v);
+    }
+}
+
+// rows the per-warp kernels re-did after the lane-bank pass (its redo list) exist only locally: send them on as well
+__global__ void __launch_bounds__(256) lb_publish_redo_kernel(const LbArgs A)
+{
+    const int n = *A.fb_count;
+    for (int it = blockIdx.x * 4 + (threadIdx.x >> 6); it < n; it += gridDim.x * 4) {
+        const int64_t r = A.fb_list[it];
+        const int col = threadIdx.x & 63;
+        lb_store_tri(A, r * 64 + col, A.counts3[r * 64 + col]);
+    }
+}
 
 // Chunks are scanned LAST ONE FIRST, then 0, 1, ..: the two chunks that hold window edges (slower, predicated spans for
 // the warps that get them) come first, so the warps have re-converged by the time the batch reaches its barrier.
@@ -506,6 +536,11 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
 }
 
 // ---- consumer warps ----------------------------------------------------------------------------------
+// Warp w works on span w of every chunk.  Tried and measured slower (round 2): spans handed out at run time through a
+// per-stage ticket counter (atomic add, late tickets kept for the stage's next chunk) so that a warp held up by a
+// predicated edge span takes fewer spans afterwards -- the batch barrier wait fell from 3.5 k to 1.4 k cycles per batch
+// in the trinucleotide kernel, but every span then starts with a look + atomic + barrier wait on one lane followed by a
+// shuffle, and the stages are released less regularly: 0.687 vs 0.606 ms (K = 64), 0.995 vs 0.954 ms (fused).
 template <bool TRI>
 __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int warp, int lane)
 {
@@ -816,8 +851,8 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
                     const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
                     const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
                     if (r2 < A.n_reg) {
-                        __stcs(A.counts3 + r2 * 64 + lane, (int)v0);
-                        __stcs(A.counts3 + r2 * 64 + 32 + lane, (int)v1);
+                        lb_store_tri(A, r2 * 64 + lane, (int)v0);
+                        lb_store_tri(A, r2 * 64 + 32 + lane, (int)v1);
                     }
                     tmp3[0] += v0;
                     tmp3[1] += v1;
@@ -1067,8 +1102,8 @@ __device__ __forceinline__ void lb_writer_tri(const LbArgs &A, uint32_t sbase, i
                 const uint32_t v0 = lds32(tri + ((uint32_t)lane * 33u + (uint32_t)l2) * 4u);
                 const uint32_t v1 = lds32(tri + ((uint32_t)(lane + 32) * 33u + (uint32_t)l2) * 4u);
                 if (r2 < A.n_reg && !fail) {
-                    __stcs(A.counts3 + r2 * 64 + lane, (int)v0);
-                    __stcs(A.counts3 + r2 * 64 + 32 + lane, (int)v1);
+                    lb_store_tri(A, r2 * 64 + lane, (int)v0);
+                    lb_store_tri(A, r2 * 64 + 32 + lane, (int)v1);
                 }
                 tmp3[0] += v0;
                 tmp3[1] += v1;
@@ -1308,7 +1343,7 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
                    const int64_t *chrom_len, const int32_t *reg_chrom, const int64_t *reg_start, const int64_t *reg_end,
                    int64_t n_reg, int32_t *counts5, int32_t *counts3, unsigned long long *totals5,
                    unsigned long long *totals3, unsigned int tot_limit_kb, void *workspace, int64_t tile_window,
-                   cudaStream_t stream)
+                   cudaStream_t stream, int n_peer, void *const *peer_counts3, void *mc_counts3)
 {
     int32_t *fb_count = reinterpret_cast<int32_t *>(workspace);
     int32_t *fb_list = fb_count + 4;
@@ -1324,6 +1359,9 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
     A.reg_chrom = reg_chrom; A.reg_start = reg_start; A.reg_end = reg_end; A.n_reg = n_reg;
     A.counts5 = counts5; A.counts3 = counts3; A.totals5 = totals5; A.totals3 = totals3;
     A.k32 = 32u; A.top = 0x01000000u; A.zero = 0u;
+    A.n_peer = counts3 != nullptr && n_peer > 0 ? (n_peer < 8 ? n_peer : 8) : 0;
+    A.mc3 = A.n_peer > 0 ? reinterpret_cast<int32_t *>(mc_counts3) : nullptr;
+    for (int p = 0; p < 8; ++p) A.peer3[p] = p < A.n_peer ? reinterpret_cast<int32_t *>(peer_counts3[p]) : nullptr;
     A.timing = nullptr;
 #ifdef DIG_LB_TIMING
     // dev builds: the phase counters follow the redo list in the workspace
@@ -1339,16 +1377,26 @@ int launch_scan_lb(const uint32_t *p2, const uint32_t *nm, int64_t n_bases, cons
         // (regions beyond LB_MAX_CHUNKS_TRI chunks, batches whose exception list overflowed)
         rc = totals3 != nullptr ? launch_lb_tri<true>(A, imaps, stream) : launch_lb_tri<false>(A, imaps, stream);
         if (rc != DIG_OK) return rc;
-        return launch_scan_tri_list(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts3,
-                                    totals3, tot_limit_kb, fb_list, fb_count, stream);
+        rc = launch_scan_tri_list(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts3,
+                                  totals3, tot_limit_kb, fb_list, fb_count, stream);
+        if (rc == DIG_OK && A.n_peer > 0) {
+            lb_publish_redo_kernel<<<8, 256, 0, stream>>>(A);
+            DIG_CHECK_LAUNCH();
+        }
+        return rc;
     }
     if (counts3 != nullptr)
         rc = totals5 != nullptr ? launch_lb<true, true>(A, tmap, imaps, stream) : launch_lb<true, false>(A, tmap, imaps, stream);
     else
         rc = totals5 != nullptr ? launch_lb<false, true>(A, tmap, imaps, stream) : launch_lb<false, false>(A, tmap, imaps, stream);
     if (rc != DIG_OK) return rc;
-    return launch_scan_hex(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts5, counts3,
-                           totals5, totals3, tot_limit_kb, false, fb_list, fb_count, stream);
+    rc = launch_scan_hex(p2, nm, n_bases, chrom_off, chrom_len, reg_chrom, reg_start, reg_end, n_reg, counts5, counts3,
+                         totals5, totals3, tot_limit_kb, false, fb_list, fb_count, stream);
+    if (rc == DIG_OK && A.n_peer > 0) {
+        lb_publish_redo_kernel<<<8, 256, 0, stream>>>(A);
+        DIG_CHECK_LAUNCH();
+    }
+    return rc;
 }
 
 }  // namespace digscan

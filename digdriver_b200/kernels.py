@@ -38,9 +38,11 @@ def _tile_hint(reg_start, reg_end, tile_window):
     return w if w > 0 and bool(np.all(e - s == w)) else 0
 
 
-def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace, tile_window=0):
+def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace, tile_window=0, peer_rows=None, mc_rows=None):
     """dig_scan_opts for one scan call: the device scratch the lane-bank kernel needs (caller-owned, sized by
-    dig_scan_workspace_bytes) plus the A/B knobs.  Returns (struct, workspace tensor to keep alive)."""
+    dig_scan_workspace_bytes) plus the A/B knobs.  peer_rows: device addresses (ints) of the trinucleotide row block in
+    every rank's peer-mapped buffer (fused all-gather), mc_rows its multicast alias.
+    Returns (struct, byref, workspace tensor to keep alive)."""
     import ctypes
     if workspace is None and n_reg > 0:
         nbytes = int(_lib.load().dig_scan_workspace_bytes(int(n_reg)))
@@ -48,7 +50,23 @@ def _scan_opts(dev, n_reg, variant, totals_limit_kb, workspace, tile_window=0):
     opts = _lib.ScanOpts(workspace.data_ptr() if workspace is not None else None,
                          workspace.numel() if workspace is not None else 0, int(variant), int(totals_limit_kb),
                          int(tile_window))
+    if peer_rows:
+        assert len(peer_rows) <= 8, "at most 8 peers"
+        opts.n_peer_counts3 = len(peer_rows)
+        for i, a in enumerate(peer_rows):
+            opts.peer_counts3_d[i] = int(a)
+        opts.mc_counts3_d = int(mc_rows) if mc_rows else None
     return opts, ctypes.byref(opts), workspace
+
+
+def peer_broadcast(src, dst_addrs, stream=None):
+    """Copy the bytes of `src` (a contiguous device tensor, 16-byte aligned, a multiple of 16 bytes) to each device
+    address in dst_addrs (peer-mapped buffers)."""
+    import ctypes
+    dev = src.device
+    arr = (ctypes.c_void_p * len(dst_addrs))(*[int(a) for a in dst_addrs])
+    with torch.cuda.device(dev):
+        _lib.call("dig_peer_broadcast", src.data_ptr(), src.numel() * src.element_size(), arr, len(dst_addrs), _stream(dev, stream))
 
 
 def scan_workspace(genome_or_device, n_reg):
@@ -59,7 +77,7 @@ def scan_workspace(genome_or_device, n_reg):
 
 def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, strand=None,
                    want_totals=False, out=None, totals=None, stream=None, variant=_lib.SCAN_AUTO,
-                   totals_limit_kb=0, workspace=None, tile_window=None):
+                   totals_limit_kb=0, workspace=None, tile_window=None, peer_rows=None, mc_rows=None):
     """K2/K4: per-region context histogram.
 
     genome: DeviceGenome.  reg_chrom: chromosome indices into the genome (int32).
@@ -78,7 +96,8 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
     lane_bank = (n_up, n_down) in ((2, 2), (1, 1)) and st is None and variant == _lib.SCAN_AUTO
     opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
                                            workspace if lane_bank else None,
-                                           _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0)
+                                           _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0,
+                                           peer_rows, mc_rows)
     with torch.cuda.device(dev):
         _lib.call("dig_count_contexts", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
                   genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),
@@ -91,7 +110,7 @@ def count_contexts(genome, reg_chrom, reg_start, reg_end, n_up=1, n_down=1, stra
 
 def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=False, out5=None, out3=None,
                            totals5=None, totals3=None, stream=None, variant=_lib.SCAN_AUTO, totals_limit_kb=0,
-                           workspace=None, tile_window=None):
+                           workspace=None, tile_window=None, peer_rows=None, mc_rows=None):
     """K2 fused: pentanucleotide and trinucleotide tables (+ totals) of the same regions in one pass.
     Returns (counts5 [n,1024], counts3 [n,64], totals5, totals3)."""
     dev = genome.device
@@ -109,7 +128,8 @@ def count_contexts_fused53(genome, reg_chrom, reg_start, reg_end, want_totals=Fa
     lane_bank = variant == _lib.SCAN_AUTO
     opts, opts_ref, workspace = _scan_opts(dev, n if lane_bank else 0, variant, totals_limit_kb,
                                            workspace if lane_bank else None,
-                                           _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0)
+                                           _tile_hint(reg_start, reg_end, tile_window) if lane_bank else 0,
+                                           peer_rows, mc_rows)
     with torch.cuda.device(dev):
         _lib.call("dig_count_contexts_fused53", genome.packed2.data_ptr(), genome.nmask.data_ptr(), genome.n_bases,
                   genome.chrom_off_d.data_ptr(), genome.chrom_len_d.data_ptr(), rc.data_ptr(), rs.data_ptr(),

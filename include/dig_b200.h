@@ -99,6 +99,18 @@ typedef struct dig_scan_opts {
     int32_t variant;
     uint32_t totals_limit_kb;
     int64_t tile_window;
+    /* Fused all-gather for range-sharded runs (one process per GPU, the trinucleotide table all-gathered so that every
+     * rank can resolve every element; replaces the pd.concat of sequence_tools.py:125): with n_peer_counts3 > 0 the
+     * TRINUCLEOTIDE rows (counts3_d of dig_count_contexts_fused53, counts_d of dig_count_contexts with n_up = n_down = 1)
+     * are stored to the same row offsets of every buffer in peer_counts3_d -- device pointers into each rank's copy of a
+     * symmetric (peer-mapped) buffer, this rank's own included -- INSTEAD of the local pointer, as the kernel produces
+     * them: the exchange overlaps the scan and no collective follows.  mc_counts3_d, when not NULL, is the NVSwitch
+     * multicast alias of the same block: one multimem store then reaches all ranks.  Up to 8 peers; lane-bank kernel
+     * only (DIG_ERR_ARG otherwise).  The caller orders the ranks afterwards (a device barrier) before reading. */
+    int32_t n_peer_counts3;
+    int32_t reserved0;
+    void *peer_counts3_d[8];
+    void *mc_counts3_d;
 } dig_scan_opts;
 int64_t dig_scan_workspace_bytes(int64_t n_reg);
 
@@ -127,6 +139,11 @@ int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint32_t *nmask_
  * (the host then ships the int32 rows instead).  Both buffers 16-byte aligned; status_d is NOT cleared here.
  */
 int dig_narrow_counts_u16(const int32_t *counts_d, int64_t n_values, uint16_t *out_d, int32_t *status_d, void *stream);
+
+/* The same nbytes (a multiple of 16; 16-byte aligned pointers) copied from src_d to each of the n_dst <= 8 device
+ * pointers in dst_d (a HOST array): peer-mapped buffers of the other ranks.  Used for the partial genome totals of a
+ * range-sharded scan (8.7 KB per rank) next to the fused row exchange above. */
+int dig_peer_broadcast(const void *src_d, int64_t nbytes, void *const *dst_d, int n_dst, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * K3  mutation context lookup with REF check.
