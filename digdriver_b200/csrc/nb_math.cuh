@@ -78,36 +78,46 @@ __device__ inline double log_nb_density(double k, double a, double p, double q)
     return log_dbinom_raw(a, k + a, p, q) + log(a / (a + k));
 }
 
-// continued fraction of I_x(a,b) (modified Lentz); converges fast for x < (a+1)/(a+b+2)
+// Continued fraction of I_x(a,b) (the form of Numerical Recipes' betacf: 1 / (1 + d_1 / (1 + d_2 / (1 + ...)))); converges
+// fast for x < (a+1)/(a+b+2).  Evaluated by the forward (Wallis) recurrence on numerators and denominators that carry
+// a common scale instead of modified Lentz: with d_n = N_n / D_n the step
+//     A_n = D_n A_{n-1} + N_n A_{n-2},  B_n likewise,  and (A_{n-1}, B_{n-1}) scaled by D_n as well
+// needs NO division (Lentz spends six per iteration, each a chain of ~30 dependent FP64 instructions; the gene-test kernel
+// is bound by the latency of exactly that chain).  Same truncation rule as before: stop when two successive convergents
+// agree to 1e-15 (|A_n B_{n-1} - A_{n-1} B_n| <= eps |A_{n-1} B_n|, the `del` of Lentz), checked after each odd step.
 __device__ inline double beta_cf(double a, double b, double x)
 {
-    const double FPMIN = 1e-300, EPS = 1e-15;
+    const double EPS = 1e-15, BIG = 0x1p+200, SMALL = 0x1p-200;    // growth per iteration < 2^110 (a + 2m up to ~2^27 squared, twice): products stay finite
     const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-    double c = 1.0;
-    double d = 1.0 - qab * x / qap;
-    if (fabs(d) < FPMIN) d = FPMIN;
-    d = 1.0 / d;
-    double h = d;
+    // convergents after the leading term d_1 = -qab x / qap:  (R, S) = A_1, B_1 and (P, Q) = A_2, B_2, both times qap
+    double R = qap, S = qap, P = qap, Q = qap - qab * x;
     for (int m = 1; m < 2000000; ++m) {
         const double dm = (double)m, m2 = 2.0 * dm;
-        double aa = dm * (b - dm) * x / ((qam + m2) * (a + m2));
-        d = 1.0 + aa * d;
-        if (fabs(d) < FPMIN) d = FPMIN;
-        c = 1.0 + aa / c;
-        if (fabs(c) < FPMIN) c = FPMIN;
-        d = 1.0 / d;
-        h *= d * c;
-        aa = -(a + dm) * (qab + dm) * x / ((a + m2) * (qap + m2));
-        d = 1.0 + aa * d;
-        if (fabs(d) < FPMIN) d = FPMIN;
-        c = 1.0 + aa / c;
-        if (fabs(c) < FPMIN) c = FPMIN;
-        d = 1.0 / d;
-        const double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < EPS) break;
+        // even step: d = m (b - m) x / ((a + 2m - 1)(a + 2m))
+        double N = dm * (b - dm) * x, D = (qam + m2) * (a + m2);
+        double An = D * P + N * R, Bn = D * Q + N * S;
+        R = D * P;
+        S = D * Q;
+        P = An;
+        Q = Bn;
+        // odd step: d = -(a + m)(a + b + m) x / ((a + 2m)(a + 2m + 1))
+        N = -(a + dm) * (qab + dm) * x;
+        D = (a + m2) * (qap + m2);
+        An = D * P + N * R;
+        Bn = D * Q + N * S;
+        R = D * P;
+        S = D * Q;
+        P = An;
+        Q = Bn;
+        if (fabs(P * S - R * Q) <= EPS * fabs(R * Q)) break;
+        const double mag = fabs(Q) > fabs(P) ? fabs(Q) : fabs(P);
+        if (mag > BIG) {
+            P *= SMALL; Q *= SMALL; R *= SMALL; S *= SMALL;
+        } else if (mag < SMALL) {
+            P *= BIG; Q *= BIG; R *= BIG; S *= BIG;
+        }
     }
-    return h;
+    return P / Q;
 }
 
 __device__ inline double nb_midp(double k, double alpha, double p)

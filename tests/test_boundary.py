@@ -59,3 +59,19 @@ def test_missing_extension_fails_loudly(monkeypatch):
     import pytest
     with pytest.raises(_lib.DigError):
         _lib.load()
+
+
+def test_scratch_sizing_entry_points():
+    """A C caller sizes every scratch buffer from the header alone (the K5 capacity rule lived in Python)."""
+    from digdriver_b200 import _lib
+    lib = _lib.load()
+    for n, want in ((0, 1024), (1, 1024), (504, 1024), (505, 2048), (1_000_000, 2_097_152), (-5, 1024)):
+        assert lib.dig_tabulate_capacity(n) == want, n
+    cap = lib.dig_tabulate_capacity(300_000)
+    assert cap >= 2 * 300_000 + 16 and cap & (cap - 1) == 0
+    assert lib.dig_tabulate_elements_workspace_bytes(300_000) == cap * 16      # key 8 + snv 4 + indel 4
+    assert lib.dig_tabulate_genes_workspace_bytes(300_000) == cap * 28         # key 8 + 5 class counters
+    assert lib.dig_scan_workspace_bytes(310_000) >= 16 + 4 * 310_000           # redo count + one int32 per region
+    # the opts struct of the ctypes table has the header's layout (8-byte pointers, no padding surprises)
+    import ctypes
+    assert ctypes.sizeof(_lib.ScanOpts) == 8 + 8 + 4 + 4 + 8 + 4 + 4 + 8 * 8 + 8
