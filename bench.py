@@ -43,7 +43,7 @@ N_SAMPLES = 200
 B_PER_BASE_K1024 = 0.25 + 0.125 + 4.0 * 1024 / WINDOW      # 0.7846 B/base
 B_PER_BASE_FUSED = 0.25 + 0.125 + 4.0 * (1024 + 64) / WINDOW  # both tables written by one pass: 0.8102
 B_PER_BASE_K64 = 0.25 + 0.125 + 4.0 * 64 / WINDOW
-SCAN_DRAM_TRAFFIC = 2.4667e9      # dram read + write bytes of one fused scan launch at 3.1 Gb (ncu --set full, profiles/)
+SCAN_DRAM_TRAFFIC = 2.4661e9      # dram read + write bytes of one fused scan launch at 3.1 Gb (ncu --set full, profiles/)
 
 
 _JSON_OUT = None
@@ -606,8 +606,8 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
 
 # FP64-pipe instructions per thread, from the ncu pass of tools/probe_fp64.py (profiles/r02_fp64_peak.txt):
 # sm__inst_executed_pipe_fp64.sum x 32 / number of threads
-FP64_INSTR_PER_PVALUE = 516704550 * 32 / 9_620_000          # dig_nb_burden_test, config-5 distribution of (k, alpha, p)
-FP64_INSTR_PER_SITE = 600193635 * 32 / 30_000_000           # dig_site_test, config 3 (Poisson(0.05) observed counts)
+FP64_INSTR_PER_PVALUE = 404151555 * 32 / 9_620_000          # dig_nb_burden_test, config-5 distribution of (k, alpha, p)
+FP64_INSTR_PER_SITE = 539514614 * 32 / 30_000_000           # dig_site_test, config 3 (Poisson(0.05) observed counts)
 FP64_PEAK_FALLBACK = 1.707e13                               # DFMA thread-instructions/s measured by tools/micro_dfma.cu
 
 
@@ -676,7 +676,7 @@ class HostPath:
     -> per-chromosome H2D / pack / fused scan / uint16 narrowing / D2H on three streams) followed by the test stage on
     mutation and gene tables that also start in pinned host memory; p-values and totals end in host memory.
 
-    source = "packed": the packed-genome cache (packed2 + N mask, 0.375 B/base) that get_device_genome /
+    source = "packed": the packed-genome cache (2-bit bases + run-length N mask, 0.25 B/base) that get_device_genome /
     countGenomeContext keep next to the FASTA -- what every run after the first uploads;
     source = "ascii": the cold path, the FASTA's bytes (1 B/base) packed on the device."""
 
@@ -1072,8 +1072,8 @@ def main():
         e2e = {"value": n_total / e2e_s, "unit": "bases/s", "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "gpu_launches_per_step": hp.launches,
                "api": "digdriver_b200.host_pipeline.HostScan + test stage: pinned host packed genome (the .dig2bit cache "
-                      "of get_device_genome / countGenomeContext, 0.375 B/base) + mutation / gene tables in; uint16 "
-                      "count tables, totals and 14 p-value columns out; bytes are summed over ranks"}
+                      "of get_device_genome / countGenomeContext: 2-bit bases + run-length N mask, 0.25 B/base) + mutation "
+                      "/ gene tables in; uint16 count tables, totals and 14 p-value columns out; bytes are summed over ranks"}
         # host-side check of what arrived (outside the timing): totals of the host copy == device totals of the value leg
         if rank == 0 and shard is None:
             same = bool(torch.equal(hp.scan.host_totals, torch.cat([di.totals5, di.totals3]).cpu()))

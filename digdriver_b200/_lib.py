@@ -30,6 +30,7 @@ SIGNATURES = {
     "dig_count_contexts_fused53": (_I, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "dig_narrow_counts_u16": (_I, [_P, _I64, _P, _P, _P]),
     "dig_peer_broadcast": (_I, [_P, _I64, _P, _I, _P]),
+    "dig_nmask_fill_runs": (_I, [_P, _I64, _P, _I64, _I64, _P]),
     "dig_tabulate_capacity": (_I64, [_I64]),
     "dig_tabulate_elements_workspace_bytes": (_I64, [_I64]),
     "dig_tabulate_genes_workspace_bytes": (_I64, [_I64]),
@@ -89,7 +90,7 @@ KERNELS_PER_CALL = {
     "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
     "dig_window_denominators": 1, "dig_site_test": 1, "dig_gene_dnds_sel": 1, "dig_selection_coefficient": 1, "dig_region_prob_norm": 1, "dig_position_obs": 1, "dig_position_test": 1, "dig_nb_pvalue_exact": 1,
     "dig_nb_pvalue_variant": 1, "dig_loglik": 1, "dig_gene_llr_test": 1, "dig_overlap_count": 1, "dig_overlap_fill": 1,
-    "dig_element_region_counts": 1, "dig_element_psum": 1, "dig_narrow_counts_u16": 1, "dig_peer_broadcast": 1,
+    "dig_element_region_counts": 1, "dig_element_psum": 1, "dig_narrow_counts_u16": 1, "dig_peer_broadcast": 1, "dig_nmask_fill_runs": 1,
 }
 launch_count = 0
 

@@ -33,6 +33,22 @@ __global__ void __launch_bounds__(256) narrow_u16_kernel(const int4 *__restrict_
     if (bad & 0xFFFF0000u) atomicOr(status, 1);       // a negative value has its top bits set as well
 }
 
+// N mask from its run-length form: run r = (first word, number of words, word value); runs are disjoint
+__global__ void __launch_bounds__(256) nmask_fill_runs_kernel(const int64_t *__restrict__ runs, int64_t n_runs,
+                                                              uint32_t *__restrict__ nmask, int64_t word0, int64_t n_words)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_runs; r += nwarp) {
+        const int64_t first = runs[3 * r], cnt = runs[3 * r + 1];
+        const uint32_t val = (uint32_t)runs[3 * r + 2];
+        for (int64_t i = lane; i < cnt; i += 32) {
+            const int64_t w = first + i;
+            if (w >= word0 && w < word0 + n_words) nmask[w] = val;
+        }
+    }
+}
+
 struct PeerDst {
     uint4 *p[8];
 };
@@ -51,6 +67,20 @@ __global__ void __launch_bounds__(256) peer_broadcast_kernel(const uint4 *__rest
 }  // namespace
 
 extern "C" {
+
+int dig_nmask_fill_runs(const int64_t *runs_d, int64_t n_runs, uint32_t *nmask_d, int64_t word0, int64_t n_words, void *stream)
+{
+    DIG_CHECK_ARG(n_runs >= 0 && word0 >= 0 && n_words >= 0, "negative size");
+    if (n_words == 0) return DIG_OK;
+    DIG_CHECK_ARG(nmask_d != nullptr && (n_runs == 0 || runs_d != nullptr), "null pointer");
+    DIG_CUDA(cudaMemsetAsync(nmask_d + word0, 0, (size_t)n_words * sizeof(uint32_t), (cudaStream_t)stream));
+    if (n_runs == 0) return DIG_OK;
+    int64_t blocks = (n_runs + 7) / 8;
+    if (blocks > 1184) blocks = 1184;
+    nmask_fill_runs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(runs_d, n_runs, nmask_d, word0, n_words);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
 
 int dig_peer_broadcast(const void *src_d, int64_t nbytes, void *const *dst_d, int n_dst, void *stream)
 {

@@ -2,7 +2,8 @@
 
 The reference reads the FASTA window by window in a multiprocessing.Pool (sequence_tools.py:96-128) and gathers the
 rows with pd.concat.  Here the genome sits in pinned host memory -- as ASCII, or as the packed cache written next to
-the FASTA (packed2 + nmask, 0.375 B/base: a third of the bytes over PCIe) -- and goes through the device once,
+the FASTA (2-bit bases + the N mask in run-length form, 0.25 B/base: a quarter of the bytes over PCIe) -- and goes through
+the device once,
 chromosome by chromosome, on three streams:
 
     copy stream :  H2D of chromosome c+1
@@ -13,8 +14,8 @@ The device genome stays resident for the stages that follow (mutation contexts, 
 shipped as uint16 whenever every region is shorter than 65536 bases (a region holds at most its length in centres, so
 no count can exceed it); the narrowing kernel double-checks and the int32 rows are shipped instead if it objects.
 
-PackedGenomeCache: `<fasta>.dig2bit/` holds the packed arrays keyed on the FASTA's path, size and mtime, so that a
-second run neither parses nor packs nor uploads ASCII.
+PackedGenomeCache: `<fasta>.dig2bit/` holds the packed bases and the mask runs keyed on the FASTA's path, size and mtime, so
+that a second run neither parses nor packs nor uploads ASCII.
 """
 import json
 import os
@@ -25,7 +26,26 @@ import torch
 from . import _lib, kernels
 from .genome import DeviceGenome, Genome, _layout
 
-CACHE_VERSION = 1
+CACHE_VERSION = 2
+
+
+def mask_runs_of(nmask_words, chrom_off, n_bases):
+    """Run-length form of the N mask: int64 [n, 3] rows (first word, number of words, 32-bit word value) over the non-zero
+    words, split at chromosome boundaries so that a chromosome's runs can be written on their own.  A genome has a few
+    hundred to a few thousand N runs (hg19: 3 % of the bases), so this replaces 1/3 of the packed bytes by ~100 KB."""
+    w = np.ascontiguousarray(nmask_words).view(np.uint32).reshape(-1)
+    idx = np.flatnonzero(w)
+    if idx.size == 0:
+        return np.zeros((0, 3), dtype=np.int64)
+    val = w[idx]
+    bounds = (np.asarray(chrom_off, dtype=np.int64) // 32)                # first mask word of every chromosome
+    chrom_of = np.searchsorted(bounds, idx, side="right")
+    brk = np.ones(idx.size, dtype=bool)
+    brk[1:] = (idx[1:] != idx[:-1] + 1) | (val[1:] != val[:-1]) | (chrom_of[1:] != chrom_of[:-1])
+    first = np.flatnonzero(brk)
+    count = np.diff(np.append(first, idx.size))
+    return np.stack([idx[first].astype(np.int64), count.astype(np.int64), val[first].astype(np.int64)], axis=1)
+
 
 
 def _pinned(shape, dtype):
@@ -36,13 +56,16 @@ class HostGenome:
     """A genome in pinned host memory in the device layout (chromosomes concatenated, each starting at a multiple of
     128 bases): either `ascii` (uint8 [n_bases], padding = 'N') or `packed2` + `nmask` (int32 words)."""
 
-    def __init__(self, names, chrom_len, ascii=None, packed2=None, nmask=None, n_other=0):
+    def __init__(self, names, chrom_len, ascii=None, packed2=None, nmask=None, n_other=0, mask_runs=None):
         self.names = list(names)
         self.chrom_len = np.asarray(chrom_len, dtype=np.int64)
         self.chrom_off, self.n_bases = _layout(self.chrom_len)
         self.ascii, self.packed2, self.nmask = ascii, packed2, nmask
+        # packed sources carry the N mask as words (nmask) or in run-length form (mask_runs, pinned int64 [n, 3])
+        self.mask_runs = mask_runs
         self.n_other = int(n_other)
-        assert (ascii is not None) != (packed2 is not None and nmask is not None), "either ASCII or packed arrays"
+        assert (ascii is not None) != (packed2 is not None and (nmask is not None or mask_runs is not None)), \
+            "either ASCII or packed arrays (with the N mask as words or as runs)"
 
     @property
     def is_packed(self):
@@ -51,7 +74,8 @@ class HostGenome:
     @property
     def nbytes(self):
         if self.is_packed:
-            return self.packed2.numel() * 4 + self.nmask.numel() * 4
+            mask = self.nmask.numel() * 4 if self.nmask is not None else self.mask_runs.numel() * 8
+            return self.packed2.numel() * 4 + mask
         return self.ascii.numel()
 
     @classmethod
@@ -67,17 +91,21 @@ class HostGenome:
         return cls(genome.names, lengths, ascii=buf[:total])
 
     @classmethod
-    def from_device(cls, dg, ascii_d=None):
-        """Pinned copy of a DeviceGenome: the packed arrays, or (ascii_d given) the ASCII it was packed from."""
+    def from_device(cls, dg, ascii_d=None, rle_mask=True):
+        """Pinned copy of a DeviceGenome: the packed bases + the N mask in run-length form (rle_mask=False: as words), or
+        (ascii_d given) the ASCII it was packed from."""
         if ascii_d is not None:
             buf = _pinned((ascii_d.numel(),), torch.uint8)
             buf.copy_(ascii_d)
             return cls(dg.names, dg.chrom_len, ascii=buf, n_other=dg.n_other)
         p2 = _pinned((dg.packed2.numel(),), torch.int32)
-        nm = _pinned((dg.nmask.numel(),), torch.int32)
         p2.copy_(dg.packed2)
-        nm.copy_(dg.nmask)
-        return cls(dg.names, dg.chrom_len, packed2=p2, nmask=nm, n_other=dg.n_other)
+        if not rle_mask:
+            nm = _pinned((dg.nmask.numel(),), torch.int32)
+            nm.copy_(dg.nmask)
+            return cls(dg.names, dg.chrom_len, packed2=p2, nmask=nm, n_other=dg.n_other)
+        runs = mask_runs_of(dg.nmask.cpu().numpy(), dg.chrom_off, dg.n_bases)
+        return cls(dg.names, dg.chrom_len, packed2=p2, mask_runs=torch.from_numpy(runs).pin_memory(), n_other=dg.n_other)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -85,7 +113,7 @@ class HostGenome:
 # ------------------------------------------------------------------------------------------------
 
 class PackedGenomeCache:
-    """`<fasta>.dig2bit/{meta.json, packed2.bin, nmask.bin}`; valid while the FASTA's size and mtime are unchanged."""
+    """`<fasta>.dig2bit/{meta.json, packed2.bin, nmask_runs.npy}`; valid while the FASTA's size and mtime are unchanged."""
 
     @staticmethod
     def cache_dir(fasta_path, cache_dir=None):
@@ -108,18 +136,21 @@ class PackedGenomeCache:
             meta = json.load(open(meta_p))
             if meta.get("key") != cls._key(fasta_path):
                 return None
-            n2, nm = int(meta["packed2_words"]), int(meta["nmask_words"])
+            n2 = int(meta["packed2_words"])
             p2 = _pinned((n2,), torch.int32)
-            nmk = _pinned((nm,), torch.int32)
-            for buf, name, n in ((p2, "packed2.bin", n2), (nmk, "nmask.bin", nm)):
-                path = os.path.join(d, name)
-                if os.path.getsize(path) != 4 * n:
-                    return None
-                with open(path, "rb") as f:
-                    got = f.readinto(memoryview(buf.numpy()).cast("B"))
-                if got != 4 * n:
-                    return None
-            return HostGenome(meta["names"], meta["chrom_len"], packed2=p2, nmask=nmk, n_other=meta["n_other"])
+            path = os.path.join(d, "packed2.bin")
+            if os.path.getsize(path) != 4 * n2:
+                return None
+            with open(path, "rb") as f:
+                got = f.readinto(memoryview(p2.numpy()).cast("B"))
+            if got != 4 * n2:
+                return None
+            runs = np.load(os.path.join(d, "nmask_runs.npy"))
+            if runs.ndim != 2 or runs.shape[1] != 3 or runs.shape[0] != int(meta["n_mask_runs"]):
+                return None
+            return HostGenome(meta["names"], meta["chrom_len"], packed2=p2,
+                              mask_runs=torch.from_numpy(np.ascontiguousarray(runs, dtype=np.int64)).pin_memory(),
+                              n_other=meta["n_other"])
         except (OSError, ValueError, KeyError):
             return None
 
@@ -130,11 +161,11 @@ class PackedGenomeCache:
         try:
             os.makedirs(d, exist_ok=True)
             p2 = dg.packed2.cpu().numpy()
-            nm = dg.nmask.cpu().numpy()
+            runs = mask_runs_of(dg.nmask.cpu().numpy(), dg.chrom_off, dg.n_bases)
             p2.tofile(os.path.join(d, "packed2.bin"))
-            nm.tofile(os.path.join(d, "nmask.bin"))
+            np.save(os.path.join(d, "nmask_runs.npy"), runs)
             meta = {"key": cls._key(fasta_path), "names": list(dg.names), "chrom_len": [int(x) for x in dg.chrom_len],
-                    "n_other": int(dg.n_other), "packed2_words": int(p2.size), "nmask_words": int(nm.size)}
+                    "n_other": int(dg.n_other), "packed2_words": int(p2.size), "n_mask_runs": int(runs.shape[0])}
             tmp = os.path.join(d, "meta.json.tmp")
             json.dump(meta, open(tmp, "w"))
             os.replace(tmp, os.path.join(d, "meta.json"))          # the meta file appears last: a torn cache is invalid
@@ -205,6 +236,15 @@ class HostScan:
         self.nmask = torch.empty(max(int(lib.dig_nmask_words(n)), 1), dtype=torch.int32, device=dev)
         self.n_other_d = torch.zeros(1, dtype=torch.int64, device=dev)
         self.dev_ascii = None if hg.is_packed else torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        self.runs_d, self.run_lo = None, None
+        if hg.is_packed and hg.nmask is None:
+            # run-length mask: the (small) run table goes up once per pass, each chromosome's share is expanded on the
+            # device right before its scan (dig_nmask_fill_runs)
+            runs = hg.mask_runs.numpy()
+            self.runs_d = torch.empty((max(len(runs), 1), 3), dtype=torch.int64, device=dev)
+            word_off = np.append(hg.chrom_off // 32, (n + 31) // 32)
+            self.run_lo = np.searchsorted(runs[:, 0], word_off, side="left") if len(runs) else np.zeros(len(word_off), dtype=np.int64)
+            self.word_off = word_off
         self.genome = DeviceGenome(hg.names, hg.chrom_len, hg.chrom_off, n, self.packed2, self.nmask, hg.n_other, dev)
         self.win_chrom = torch.from_numpy(w[:, 0].astype(np.int32)).to(dev)
         self.win_start = torch.from_numpy(np.ascontiguousarray(w[:, 1])).to(dev)
@@ -227,9 +267,10 @@ class HostScan:
         self.host_status = _pinned((1,), torch.int32)
         self.copy_stream = torch.cuda.Stream(dev)
         self.out_stream = torch.cuda.Stream(dev)
-        per_base = 0.375 if hg.is_packed else 1.0
+        per_base = (0.375 if hg.nmask is not None else 0.25) if hg.is_packed else 1.0
         ends = np.append(hg.chrom_off[1:], hg.n_bases) if n_chrom else np.zeros(0, dtype=np.int64)
-        self.h2d_bytes = int(sum(int(ends[c] - hg.chrom_off[c]) for c, _, _ in self.order) * per_base)
+        self.h2d_bytes = int(sum(int(ends[c] - hg.chrom_off[c]) for c, _, _ in self.order) * per_base) + \
+            (int(hg.mask_runs.numel()) * 8 if hg.is_packed and hg.nmask is None else 0)
         per = 2 if self.narrow else 4
         self.d2h_bytes = self.n_win * (self.K + (64 if self.fused else 0)) * per + self.host_totals.numel() * 8 + 4
         self.launches_per_run = 0
@@ -243,7 +284,8 @@ class HostScan:
             return
         if hg.is_packed:
             self.packed2[a // 16:b // 16].copy_(hg.packed2[a // 16:b // 16], non_blocking=True)
-            self.nmask[a // 32:b // 32].copy_(hg.nmask[a // 32:b // 32], non_blocking=True)
+            if hg.nmask is not None:
+                self.nmask[a // 32:b // 32].copy_(hg.nmask[a // 32:b // 32], non_blocking=True)
         else:
             self.dev_ascii[a:b].copy_(hg.ascii[a:b], non_blocking=True)
 
@@ -251,6 +293,10 @@ class HostScan:
         hg = self.hg
         a = int(hg.chrom_off[c])
         b = int(hg.chrom_off[c + 1]) if c + 1 < len(hg.chrom_off) else hg.n_bases
+        if hg.is_packed and self.runs_d is not None and b > a:
+            lo, hi = int(self.run_lo[c]), int(self.run_lo[c + 1])
+            _lib.call("dig_nmask_fill_runs", self.runs_d.data_ptr() + lo * 24, hi - lo, self.nmask.data_ptr(),
+                      int(self.word_off[c]), int(self.word_off[c + 1] - self.word_off[c]), stream.cuda_stream)
         if hg.is_packed or b <= a:
             return
         _lib.call("dig_pack_genome", self.dev_ascii.data_ptr() + a, b - a, self.packed2.data_ptr() + a // 16 * 4,
@@ -296,6 +342,9 @@ class HostScan:
         if not self.hg.is_packed:
             self.n_other_d.zero_()
         with torch.cuda.device(dev):
+            if self.runs_d is not None and self.hg.mask_runs.numel():
+                with torch.cuda.stream(cs):
+                    self.runs_d[: self.hg.mask_runs.shape[0]].copy_(self.hg.mask_runs, non_blocking=True)
             for c, lo, hi in self.order:
                 with torch.cuda.stream(cs):
                     self._upload(c)

@@ -140,6 +140,12 @@ int dig_count_contexts_fused53(const uint32_t *packed2_d, const uint32_t *nmask_
  */
 int dig_narrow_counts_u16(const int32_t *counts_d, int64_t n_values, uint16_t *out_d, int32_t *status_d, void *stream);
 
+/* N mask from its run-length form (the packed-genome cache keeps the mask that way: a genome has a few hundred to a few
+ * thousand N runs, so the mask -- a third of the packed bytes -- does not travel over PCIe at all).  runs_d [n_runs, 3]
+ * int64: (first word, number of words, 32-bit word value), disjoint.  Words [word0, word0 + n_words) of nmask_d are
+ * cleared, then the runs (clipped to that range) are written. */
+int dig_nmask_fill_runs(const int64_t *runs_d, int64_t n_runs, uint32_t *nmask_d, int64_t word0, int64_t n_words, void *stream);
+
 /* The same nbytes (a multiple of 16; 16-byte aligned pointers) copied from src_d to each of the n_dst <= 8 device
  * pointers in dst_d (a HOST array): peer-mapped buffers of the other ranks.  Used for the partial genome totals of a
  * range-sharded scan (8.7 KB per rank) next to the fused row exchange above. */

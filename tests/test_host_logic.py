@@ -252,3 +252,26 @@ def test_nb_model_train_sequence_model_from_store(tmp_path):
     exp_train, exp_test = nb_model.expected_mutations_by_context(train, [(2, 0, 1000)], str(tmp_path / "m"), N=2)
     np.testing.assert_allclose(exp_train.values, [100 * d["AAA"] + 30 * d["ACG"], 50 * d["AAA"] + 20 * d["ACG"]], rtol=1e-15)
     np.testing.assert_allclose(exp_test.values, [10 * d["AAA"] + 5 * d["ACG"]], rtol=1e-15)
+
+
+def test_mask_runs_round_trip():
+    """Run-length form of the N mask (packed-genome cache, host_pipeline.mask_runs_of): lossless, split at chromosome
+    boundaries, empty for an N-free genome."""
+    from digdriver_b200.host_pipeline import mask_runs_of
+    rng = np.random.default_rng(4)
+    n_words = 3000
+    bits = np.zeros(n_words * 32, dtype=np.uint8)
+    for _ in range(40):
+        a = int(rng.integers(0, n_words * 32 - 700))
+        bits[a:a + int(rng.integers(1, 600))] = 1
+    bits[32 * 1000 - 5:32 * 1000 + 70] = 1                 # crosses the boundary between the two chromosomes below
+    words = np.packbits(bits).view(">u4").astype(np.uint32)
+    runs = mask_runs_of(words.view(np.int32), np.array([0, 32_000]), n_words * 32)
+    assert runs.dtype == np.int64 and runs.shape[1] == 3 and len(runs) < 400
+    out = np.zeros(n_words, dtype=np.uint32)
+    for first, cnt, val in runs:
+        assert not np.any(out[first:first + cnt])          # disjoint
+        out[first:first + cnt] = val
+    assert np.array_equal(out, words)
+    assert not any(f < 1000 < f + c for f, c, _ in runs)   # no run spans the chromosome boundary (word 1000)
+    assert mask_runs_of(np.zeros(10, dtype=np.int32), np.array([0]), 320).shape == (0, 3)
