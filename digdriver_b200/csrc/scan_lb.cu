@@ -53,14 +53,25 @@ constexpr uint32_t LB_DSTRIDE = (LB_CHUNK + 64) / 4;     // 528 B of packed base
 constexpr uint32_t LB_MSTRIDE = (LB_CHUNK + 128) / 8;    // 272 B of N mask (17 granules)
 // Lanes 4r .. 4r+3 form group r and work on windows r, r+8, r+16, r+24 of the batch: in a regular tiling those four
 // strips sit at a fixed pitch (8 windows, a multiple of 128 bases), so ONE 2-D TMA box load brings all four.  A group's
-// strips are contiguous in the stage (the box is written row after row) and start 128-byte aligned.
-constexpr uint32_t LB_DGROUP = 2176u;                    // 4 x 528 B, padded to 17 x 128
-constexpr uint32_t LB_MGROUP = 1152u;                    // 4 x 272 B, padded to 9 x 128
+// strips are the rows of the box (written one after the other) and the group starts 128-byte aligned.
+// Bank layout of the strips: a consumer warp reads the same 32 (16) bytes of all 32 strips with 128-bit loads, eight
+// lanes per pass, so the eight strips of lanes 8q .. 8q+7 (two groups) must start in eight different 16-byte columns of
+// the 128-byte bank row.  Rows of 34 (18) granules put a group's four strips on columns 0, 2, 4, 6, and the strips of ODD
+// groups begin one granule into their rows (the box of an odd group is fetched 16 bytes early): columns 1, 3, 5, 7.
+// (With 33 / 17-granule rows and no shift both groups sat on columns 0-3: every such load took two passes, the single
+// word loads behind them eight: 2.6 k of the 15 k shared-memory wavefronts per batch.)
+constexpr uint32_t LB_DROW = LB_DSTRIDE + 16u;           // 544 B: row pitch in shared memory = width of the data box
+constexpr uint32_t LB_MROW = LB_MSTRIDE + 16u;           // 288 B
+constexpr uint32_t LB_DGROUP = 4u * LB_DROW;             // 2176 = 17 x 128
+constexpr uint32_t LB_MGROUP = 4u * LB_MROW;             // 1152 = 9 x 128
+static_assert(LB_DGROUP % 128u == 0u && LB_MGROUP % 128u == 0u, "groups start 128-byte aligned (TMA box destination)");
 constexpr uint32_t LB_MBASE = 8u * LB_DGROUP;            // mask strips follow the eight data groups
 constexpr uint32_t LB_STAGE_BYTES = 8u * (LB_DGROUP + LB_MGROUP);
 __device__ __forceinline__ int lb_win(int lane) { return (lane >> 2) + 8 * (lane & 3); }    // window of the batch a lane owns
-__device__ __forceinline__ uint32_t lb_dstrip(int lane) { return (uint32_t)(lane >> 2) * LB_DGROUP + (uint32_t)(lane & 3) * LB_DSTRIDE; }
-__device__ __forceinline__ uint32_t lb_mstrip(int lane) { return LB_MBASE + (uint32_t)(lane >> 2) * LB_MGROUP + (uint32_t)(lane & 3) * LB_MSTRIDE; }
+__device__ __forceinline__ uint32_t lb_dgroup(int lane) { return (uint32_t)(lane >> 2) * LB_DGROUP; }
+__device__ __forceinline__ uint32_t lb_mgroup(int lane) { return LB_MBASE + (uint32_t)(lane >> 2) * LB_MGROUP; }
+__device__ __forceinline__ uint32_t lb_dstrip(int lane) { return lb_dgroup(lane) + (uint32_t)(lane & 3) * LB_DROW + (uint32_t)((lane >> 2) & 1) * 16u; }
+__device__ __forceinline__ uint32_t lb_mstrip(int lane) { return lb_mgroup(lane) + (uint32_t)(lane & 3) * LB_MROW + (uint32_t)((lane >> 2) & 1) * 16u; }
 constexpr int LB_MAX_CHUNKS = 16;                  // regions up to ~32 kb; longer ones go to the per-warp kernel
 constexpr int LB_MAX_CHUNKS_TRI = 1 << 18;         // trinucleotide-only mode counts in 32 bits: regions up to 536 Mb
 constexpr int LB_EXC_CAP = 508;
@@ -492,12 +503,15 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
                     uint32_t xd = xd0 + 128u * (uint32_t)k, yd = yd0, xm = xm0 + 64u * (uint32_t)k, ym = ym0;
                     if (xd >= ped) { xd -= ped; ++yd; }
                     if (xm >= pem) { xm -= pem; ++ym; }
-                    int sd = 0, sm = 0;
-                    if (xd + LB_DSTRIDE / 4 > ped) { xd -= (uint32_t)A.dshift; sd = 1; }     // the box would cross the row end:
-                    if (xm + LB_MSTRIDE / 4 > pem) { xm -= (uint32_t)A.mshift; sm = 1; }     // same row of the shifted view
-                    mbar_arrive_tx(full, 4u * (LB_DSTRIDE + LB_MSTRIDE));
-                    tensor_g2s(&maps->d[sd], stg + lb_dstrip(lane), (int)xd, (int)yd, full);
-                    tensor_g2s(&maps->m[sm], stg + lb_mstrip(lane), (int)xm, (int)ym, full);
+                    // odd groups: the box starts one granule (four elements) early, see the bank layout above; a start
+                    // before the row only reads zeros into a lead-in nobody looks at
+                    const int lead = ((lane >> 2) & 1) * 4;
+                    int bxd = (int)xd - lead, bxm = (int)xm - lead, sd = 0, sm = 0;
+                    if (bxd + (int)(LB_DROW / 4) > (int)ped) { bxd -= (int)A.dshift; sd = 1; }     // the box would cross the row end:
+                    if (bxm + (int)(LB_MROW / 4) > (int)pem) { bxm -= (int)A.mshift; sm = 1; }     // same row of the shifted view
+                    mbar_arrive_tx(full, 4u * (LB_DROW + LB_MROW));
+                    tensor_g2s(&maps->d[sd], stg + lb_dgroup(lane), bxd, (int)yd, full);
+                    tensor_g2s(&maps->m[sm], stg + lb_mgroup(lane), bxm, (int)ym, full);
                 } else {
                     mbar_arrive(full);
                 }
@@ -1268,16 +1282,16 @@ int lb_input_maps(LbMaps *maps, LbArgs &A, int64_t tile_w)
     const unsigned char *p2b = reinterpret_cast<const unsigned char *>(A.p2);
     const unsigned char *nmb = reinterpret_cast<const unsigned char *>(A.nmask);
     int rc = lb_encode(&maps->d[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, p2b, dpitch / 4, (dbytes + dpitch - 1) / dpitch, dpitch,
-                       LB_DSTRIDE / 4, 4u);
+                       LB_DROW / 4, 4u);
     if (rc == DIG_OK)
         rc = lb_encode(&maps->d[1], CU_TENSOR_MAP_DATA_TYPE_UINT32, p2b + dsh, dpitch / 4, (dbytes - dsh + dpitch - 1) / dpitch,
-                       dpitch, LB_DSTRIDE / 4, 4u);
+                       dpitch, LB_DROW / 4, 4u);
     if (rc == DIG_OK)
         rc = lb_encode(&maps->m[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, nmb, mpitch / 4, (mbytes + mpitch - 1) / mpitch, mpitch,
-                       LB_MSTRIDE / 4, 4u);
+                       LB_MROW / 4, 4u);
     if (rc == DIG_OK)
         rc = lb_encode(&maps->m[1], CU_TENSOR_MAP_DATA_TYPE_UINT32, nmb + msh, mpitch / 4, (mbytes - msh + mpitch - 1) / mpitch,
-                       mpitch, LB_MSTRIDE / 4, 4u);
+                       mpitch, LB_MROW / 4, 4u);
     if (rc != DIG_OK) return rc;
     A.tile_w = tile_w;
     A.dshift = (int64_t)(dsh / 4);

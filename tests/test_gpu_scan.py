@@ -290,3 +290,42 @@ def test_empty_inputs_through_the_c_abi(dev):
     out = kernels.position_test(dg, [0], [0], [40], [3.0], [1.0], np.ones(64), e32, e64, 1, 1, 7)
     assert out["pval"].numel() == 6 and int(out["obs"].sum()) == 0           # 39 positions in bins of 7
     assert kernels.gene_dnds_sel(f, f, np.zeros((0, 6)), np.zeros((0, 6)), dev).shape == (24, 0)
+
+
+def test_fused_exchange_stores_rows_into_every_peer_buffer(dev):
+    """dig_scan_opts.peer_counts3_d (the all-gather fused into the scan for range-sharded runs): with peers given the
+    trinucleotide rows go to the same offsets of EVERY peer buffer instead of the local pointer -- here the "peers" are
+    two more buffers of this GPU, which exercises the per-peer store path of both lane-bank kernels (the multicast
+    path needs NVSwitch symmetric memory and is covered by bench.py's parity sample under torchrun) -- and
+    dig_peer_broadcast copies the totals block after them."""
+    from digdriver_b200 import kernels
+    from digdriver_b200.genome import DeviceGenome, tile_windows
+    lengths = np.array([1_500_000, 700_001], dtype=np.int64)
+    dg = DeviceGenome.synthetic(["a", "b"], lengths, seed=21, device=dev)
+    base = tile_windows(np.arange(2), lengths, 10_000)
+    wins = np.concatenate([base] * (64 * 160 // len(base) + 1))          # enough regions for the trinucleotide-only kernel
+    n = len(wins)
+    want5, want3, _, _ = kernels.count_contexts_fused53(dg, wins[:, 0], wins[:, 1], wins[:, 2])
+    bufs = [torch.full((n, 64), -7, dtype=torch.int32, device=dev) for _ in range(3)]
+    local = torch.full((n, 64), -7, dtype=torch.int32, device=dev)
+    got5, _, _, _ = kernels.count_contexts_fused53(dg, wins[:, 0], wins[:, 1], wins[:, 2], out3=local,
+                                                   peer_rows=[b.data_ptr() for b in bufs])
+    torch.cuda.synchronize()
+    assert torch.equal(got5, want5)
+    assert all(torch.equal(b, want3) for b in bufs)
+    assert bool((local == -7).all())                                      # the local pointer is not written in this mode
+    for b in bufs:
+        b.fill_(-7)
+    kernels.count_contexts(dg, wins[:, 0], wins[:, 1], wins[:, 2], 1, 1, out=local, peer_rows=[b.data_ptr() for b in bufs[:2]])
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[0], want3) and torch.equal(bufs[1], want3) and bool((bufs[2] == -7).all())
+    # too few regions for the lane-bank kernel: the request must be refused, not silently ignored
+    from digdriver_b200._lib import DigError
+    with pytest.raises(DigError):
+        kernels.count_contexts(dg, base[:, 0], base[:, 1], base[:, 2], 1, 1, peer_rows=[bufs[0].data_ptr()])
+    src = torch.arange(4096, dtype=torch.int32, device=dev)
+    dst = [torch.zeros(4096, dtype=torch.int32, device=dev) for _ in range(3)]
+    kernels.peer_broadcast(src[16:2064], [d[16:2064].data_ptr() for d in dst])
+    torch.cuda.synchronize()
+    for d in dst:
+        assert torch.equal(d[16:2064], src[16:2064]) and int(d[:16].sum()) == 0 and int(d[2064:].sum()) == 0
