@@ -256,6 +256,20 @@ def test_hexamer_pair_scan_adversarial(dev, oracle):
     # the per-base kernels stay available and agree
     c5, c3, _, _ = kernels.count_contexts_fused53(dg, chrom, start, end, variant=_lib.SCAN_PER_BASE)
     assert np.array_equal(c5.cpu().numpy(), want5) and np.array_equal(c3.cpu().numpy(), want3)
+    # trinucleotide-only lane-bank kernel (4-mer pairs): it takes over from 64 regions per SM, so the same adversarial
+    # set is repeated (and shuffled, so that every batch of 32 mixes chromosomes, lengths and parities); whole
+    # chromosomes of 300 kb run through ~150 chunks per lane while their batch neighbours have one
+    reps = 64 * 160 // len(chrom) + 1
+    order = np.random.default_rng(7).permutation(reps * len(chrom))
+    big_c, big_s, big_e = (np.tile(a, reps)[order] for a in (chrom, start, end))
+    want_big = np.tile(want3, (reps, 1))[order]
+    for limit in (0, 64):
+        k3, kt = kernels.count_contexts(dg, big_c, big_s, big_e, 1, 1, want_totals=True, totals_limit_kb=limit)
+        bad = np.flatnonzero((k3.cpu().numpy() != want_big).any(axis=1))
+        assert bad.size == 0, (limit, bad[:5], big_c[bad[:5]], big_s[bad[:5]], big_e[bad[:5]])
+        assert np.array_equal(kt.cpu().numpy(), want_big.astype(np.int64).sum(axis=0)), limit
+    k3b, _ = kernels.count_contexts(dg, big_c, big_s, big_e, 1, 1, variant=_lib.SCAN_PER_BASE)
+    assert np.array_equal(k3b.cpu().numpy(), want_big)
 
 
 def test_empty_inputs_through_the_c_abi(dev):
