@@ -104,11 +104,44 @@ struct LbRing {
 };
 constexpr uint32_t TRI_TAB_BYTES = 256u * 128u;                      // [256 4-mers][32 lanes] words
 template <>
-struct LbRing<2> {
+struct LbRing<2> {                                                   // trinucleotide-only, one team: four stages
     static constexpr uint32_t NST = 4u, LOG = 2u, STG0 = TRI_TAB_BYTES, FULL0 = 0u, EMPTY0 = 4u;
 };
+template <>
+struct LbRing<3> {                                                   // trinucleotide-only, two teams: two stages each
+    static constexpr uint32_t NST = 2u, LOG = 1u, STG0 = 0u /* per team, see TriL */, FULL0 = 0u, EMPTY0 = 2u;
+};
 enum { TBAR_OUTFULL = 8, TBAR_DONE = 9, TBAR_CLEAN = 10 };           // barrier slots of the trinucleotide-only mode
-static_assert(LbRing<2>::STG0 + 4u * LB_STAGE_BYTES <= OFF_TRI, "trinucleotide-only layout: stages end before the row block");
+
+// Shared-memory layout of the trinucleotide-only kernel.  TEAMS = 1: the sixteen consumer warps work on one batch at a
+// time (table 32 KB, four stages).  TEAMS = 2: two teams of eight consumer + two writer + two producer warps work on
+// alternate batches, each with its own table, two stages, row block, exception lists and barriers; a warp then takes
+// two spans of every chunk.  While one team is at its batch barrier, in its write-out or waiting for a chunk, the
+// other one keeps the integer and shared-memory pipes busy -- the overlap of phases that the pentanucleotide modes
+// cannot have for lack of room for a second 128 KB table.
+template <int TEAMS>
+struct TriL {
+    static constexpr int GM = TEAMS == 1 ? 2 : 3;
+    static constexpr int CW = LB_CW / TEAMS, WW = LB_WW / TEAMS, PW = LB_PW / TEAMS, SPW = TEAMS;     // warps per team, spans per warp
+    static constexpr uint32_t NST = LbRing<GM>::NST;
+    static constexpr uint32_t TAB = 0u;                                                  // + team * TRI_TAB_BYTES
+    static constexpr uint32_t STG = TEAMS * TRI_TAB_BYTES;                               // + team * NST * LB_STAGE_BYTES
+    static constexpr uint32_t TRI = STG + 4u * LB_STAGE_BYTES;                           // + team * TRI_BYTES
+    static constexpr uint32_t EXC = TRI + TEAMS * TRI_BYTES;                             // + team * 2 * EXC_BYTES
+    static constexpr uint32_t BAR = EXC + TEAMS * 2u * EXC_BYTES;                        // + team * 128
+    static constexpr uint32_t SMEM = BAR + TEAMS * 128u;
+    static constexpr uint32_t B_OUTFULL = TEAMS == 1 ? TBAR_OUTFULL : 4u, B_DONE = TEAMS == 1 ? TBAR_DONE : 5u,
+                              B_CLEAN = TEAMS == 1 ? TBAR_CLEAN : 6u;
+};
+static_assert(TriL<2>::SMEM <= 232448u && TriL<1>::SMEM <= 232448u, "shared memory budget");
+static_assert(TriL<1>::BAR % 16u == 0u && TriL<2>::BAR % 16u == 0u, "barrier block alignment");
+
+// which batches, barriers and stages a producer warp works for (one team = the whole CTA in the pentanucleotide modes)
+struct LbTeam {
+    int64_t b0, bstep;
+    uint32_t bar, stg0;
+    int lane_shift;           // producer warp pw stages the windows of the lanes with (lane >> lane_shift) == pw
+};
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt)
@@ -279,7 +312,7 @@ __device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, i
             if (ge[t] < gs[t]) ge[t] = gs[t];
         }
         int64_t lowc = gs[0], hic = ge[0];
-        if (GM == 2) {
+        if (GM >= 2) {
             lowc = gs[1];
             hic = ge[1];
         } else if (GM == 1) {
@@ -298,7 +331,7 @@ __device__ __forceinline__ LbGeom lb_geom2(bool active, int32_t c, int64_t rs, i
             // end in the same spans and no warp runs both bodies; measured 1 % slower -- one span in eighty does no work)
             const int64_t O = ((lowc - 2) >> 7) << 7;       // arithmetic shift: floor
             const int64_t nch = (hic - O - 2 + (LB_CHUNK - 1)) / LB_CHUNK;
-            if (nch > (GM == 2 ? LB_MAX_CHUNKS_TRI : LB_MAX_CHUNKS)) {
+            if (nch > (GM >= 2 ? LB_MAX_CHUNKS_TRI : LB_MAX_CHUNKS)) {
                 g.too_long = true;
             } else {
                 g.O = O;
@@ -455,14 +488,14 @@ struct LbMaps {
 };
 
 template <int GM>
-__device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps, uint32_t sbase, int pw, int lane)
+__device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps, const LbTeam T, int pw, int lane)
 {
-    const uint32_t bar = sbase + OFF_BAR;
+    const uint32_t bar = T.bar;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
     const int m = lane & 3;                                // row of the group's box
-    const bool mine = (lane >> 3) == pw;
+    const bool mine = (lane >> T.lane_shift) == pw;
     uint32_t ci = 0u;
-    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x) {
+    for (int64_t b = T.b0; b < n_batches; b += T.bstep) {
         const LbGeom g = lb_geom<GM>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const int nch = warp_max(g.nch);
         // regular group: every window has the leader's chunk count and sits m * 8 W bases after the leader's origin
@@ -494,7 +527,7 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
             mbar_wait_idle(bar + 8u * (R::EMPTY0 + stage), ((ci >> R::LOG) & 1u) ^ 1u);
             LB_T(t_e1);
             const uint32_t full = bar + 8u * (R::FULL0 + stage);
-            const uint32_t stg = sbase + R::STG0 + stage * LB_STAGE_BYTES;
+            const uint32_t stg = T.stg0 + stage * LB_STAGE_BYTES;
             if (!mine) {
                 // another producer warp's window
             } else if (regular && k < g.nch) {
@@ -951,10 +984,16 @@ __device__ __forceinline__ void lb_pairs4(const uint32_t (&D)[9], uint32_t tabl,
     }
 }
 
-__device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase, int warp, int lane)
+template <int TEAMS>
+__device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase, int team, int warp, int lane)
 {
-    const uint32_t bar = sbase + OFF_BAR;
-    const uint32_t tabl = sbase + OFF_TAB + (uint32_t)lane * 4u;
+    using L = TriL<TEAMS>;                                     // `warp` = index inside the team
+    using R = LbRing<L::GM>;
+    const uint32_t bar = sbase + L::BAR + (uint32_t)team * 128u;
+    const uint32_t tabl = sbase + L::TAB + (uint32_t)team * TRI_TAB_BYTES + (uint32_t)lane * 4u;
+    const uint32_t stg0 = sbase + L::STG + (uint32_t)team * R::NST * LB_STAGE_BYTES;
+    const uint32_t trib = sbase + L::TRI + (uint32_t)team * TRI_BYTES;
+    const int64_t b0 = (int64_t)blockIdx.x * TEAMS + team, bstep = (int64_t)gridDim.x * TEAMS;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
     const uint32_t k128 = A.k32 << 2;
     uint32_t cit = 0u, bi = 0u;
@@ -962,15 +1001,15 @@ __device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase,
     unsigned long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     LB_T(t_k0);
-    LbGeom gnext = lb_geom<2>((int64_t)blockIdx.x * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
-    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
+    LbGeom gnext = lb_geom<2>(b0 * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
+    for (int64_t b = b0; b < n_batches; b += bstep, ++bi) {
         const LbGeom g = gnext;
         const int nch = warp_max(g.nch);
-        const uint32_t exc = sbase + OFF_EXC + (bi & 1u) * EXC_BYTES;
+        const uint32_t exc = sbase + L::EXC + (uint32_t)team * 2u * EXC_BYTES + (bi & 1u) * EXC_BYTES;
         bool clean = bi == 0u;
         // the next batch's descriptor is requested at the start of this one: its two dependent loads resolve during the scan
-        const int64_t rn = (b + gridDim.x) * 32 + lb_win(lane);
-        const bool nact = b + gridDim.x < n_batches && rn < A.n_reg;
+        const int64_t rn = (b + bstep) * 32 + lb_win(lane);
+        const bool nact = b + bstep < n_batches && rn < A.n_reg;
         int32_t nc = 0;
         int64_t nrs = 0, nre = 0;
         if (nact) {
@@ -980,21 +1019,23 @@ __device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase,
         }
         for (int kq = 0; kq < nch; ++kq, ++cit) {
             const int k = lb_chunk_order(kq, nch);                           // the order the producers stage the chunks in
-            using R = LbRing<2>;
             const uint32_t stage = cit & (R::NST - 1u);
             LB_T(t_a);
             mbar_wait(bar + 8u * (R::FULL0 + stage), (cit >> R::LOG) & 1u);
             LB_T(t_b);
             LB_ACC(0, t_a, t_b);
-            const uint32_t stg = sbase + R::STG0 + stage * LB_STAGE_BYTES;
-            if (!__any_sync(0xffffffffu, k < g.nch && g.lo3 - (k * LB_CHUNK + warp * LB_SPAN) < 130 &&
-                                             g.hi3 - (k * LB_CHUNK + warp * LB_SPAN) > 2)) {
+            const uint32_t stg = stg0 + stage * LB_STAGE_BYTES;
+            if (kq == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
+#pragma unroll 1
+          for (int sp = 0; sp < L::SPW; ++sp) {                             // the warp's spans of this chunk
+            const int span = warp + sp * L::CW;
+            if (!__any_sync(0xffffffffu, k < g.nch && g.lo3 - (k * LB_CHUNK + span * LB_SPAN) < 130 &&
+                                             g.hi3 - (k * LB_CHUNK + span * LB_SPAN) > 2)) {
                 if (lane == 0) mbar_arrive(bar + 8u * (R::EMPTY0 + stage));   // no centre of any lane's window in this span
-                if (kq == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
                 continue;
             }
-            const uint32_t dptr = stg + lb_dstrip(lane) + (uint32_t)warp * 32u;
-            const uint32_t mptr = stg + lb_mstrip(lane) + (uint32_t)warp * 16u;
+            const uint32_t dptr = stg + lb_dstrip(lane) + (uint32_t)span * 32u;
+            const uint32_t mptr = stg + lb_mstrip(lane) + (uint32_t)span * 16u;
             uint32_t D[9], M[5];
             {
                 const uint4 a = lds128(dptr), c = lds128(dptr + 16u), m = lds128(mptr);
@@ -1009,13 +1050,13 @@ __device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase,
             if (lane == 0) mbar_arrive_after_loads(bar + 8u * (R::EMPTY0 + stage), dep, A.zero);
             if (!clean) {
                 LB_T(t_c);
-                mbar_wait(bar + 8u * TBAR_CLEAN, (bi - 1u) & 1u);
+                mbar_wait(bar + 8u * L::B_CLEAN, (bi - 1u) & 1u);
                 LB_T(t_d);
                 LB_ACC(1, t_c, t_d);
                 clean = true;
             }
             LB_T(t_p0);
-            const int base = k * LB_CHUNK + warp * LB_SPAN;
+            const int base = k * LB_CHUNK + span * LB_SPAN;
             const int lo3 = g.lo3 - base, hi3 = g.hi3 - base;                // centre c (local base index) valid: lo3 <= c < hi3
             const uint32_t any_n = M[0] | M[1] | M[2] | M[3] | (M[4] & 0xF0000000u);
             uint32_t PV[4] = {0u, 0u, 0u, 0u};
@@ -1041,32 +1082,34 @@ __device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase,
                 }
                 if ((PV[0] | PV[1] | PV[2] | PV[3]) != 0u) lb_pairs4<true>(D, tabl, k128, PV);
             }
-            if (kq == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
             LB_T(t_p1);
             LB_ACC(2, t_p0, t_p1);
+          }
         }
         if (nch == 0) gnext = lb_geom2<2>(nact, nc, nrs, nre, A.chrom_off, A.chrom_len);
-        if (!clean) mbar_wait(bar + 8u * TBAR_CLEAN, (bi - 1u) & 1u);
+        if (!clean) mbar_wait(bar + 8u * L::B_CLEAN, (bi - 1u) & 1u);
         LB_T(t_s0);
-        cons_sync();                                                         // every 4-mer of the batch is in the table
+        if constexpr (TEAMS == 1) cons_sync();                               // every 4-mer of the batch is in the table
+        else if (team == 0) asm volatile("bar.sync 1, %0;" ::"n"(L::CW * 32) : "memory");
+        else asm volatile("bar.sync 3, %0;" ::"n"(L::CW * 32) : "memory");
         LB_T(t_sa);
         LB_ACC(3, t_s0, t_sa);
-        mbar_wait(bar + 8u * TBAR_DONE, (bi & 1u) ^ 1u);                     // writer warp 0 has stored and re-zeroed the row block
+        mbar_wait(bar + 8u * L::B_DONE, (bi & 1u) ^ 1u);                     // writer warp 0 has stored and re-zeroed the row block
         LB_T(t_s1);
         LB_ACC(4, t_sa, t_s1);
-        // ---- write-out: bins 4 warp .. 4 warp + 3 of window `lane`
+        // ---- write-out: bins 64 / CW * warp .. of window `lane`
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const uint32_t bin = (uint32_t)(4 * warp + t);
+        for (int t = 0; t < 64 / L::CW; ++t) {
+            const uint32_t bin = (uint32_t)(64 / L::CW * warp + t);
             uint32_t acc = 0u;
 #pragma unroll
             for (int d = 0; d < 4; ++d) acc += lds32(tabl + (bin * 4u + (uint32_t)d) * 128u);       // trinucleotide + next base
 #pragma unroll
             for (int a = 0; a < 4; ++a) acc += lds32(tabl + ((uint32_t)a * 64u + bin) * 128u);      // previous base + trinucleotide
-            sts32(sbase + OFF_TRI + (bin * 33u + (uint32_t)lane) * 4u, acc);
+            sts32(trib + (bin * 33u + (uint32_t)lane) * 4u, acc);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar + 8u * TBAR_OUTFULL);                 // release: reads done, bins in place
+        if (lane == 0) mbar_arrive(bar + 8u * L::B_OUTFULL);                 // release: reads done, bins in place
         LB_T(t_s2);
         LB_ACC(6, t_s1, t_s2);
     }
@@ -1081,27 +1124,30 @@ __device__ __forceinline__ void lb_consumer_tri(const LbArgs &A, uint32_t sbase,
 #endif
 }
 
-template <bool TOT>
-__device__ __forceinline__ void lb_writer_tri(const LbArgs &A, uint32_t sbase, int q, int lane)
+template <bool TOT, int TEAMS>
+__device__ __forceinline__ void lb_writer_tri(const LbArgs &A, uint32_t sbase, int team, int q, int lane)
 {
-    const uint32_t bar = sbase + OFF_BAR;
+    using L = TriL<TEAMS>;
+    const uint32_t bar = sbase + L::BAR + (uint32_t)team * 128u;
+    const int64_t b0 = (int64_t)blockIdx.x * TEAMS + team, bstep = (int64_t)gridDim.x * TEAMS;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
     uint32_t bi = 0u;
     unsigned int tot3[2] = {0u, 0u};
     unsigned int acc_kb = 0u;
-    const uint32_t tri = sbase + OFF_TRI;
-    for (int64_t b = blockIdx.x; b < n_batches; b += gridDim.x, ++bi) {
+    const uint32_t tri = sbase + L::TRI + (uint32_t)team * TRI_BYTES;
+    for (int64_t b = b0; b < n_batches; b += bstep, ++bi) {
         const LbGeom g = lb_geom<2>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
-        const uint32_t exc = sbase + OFF_EXC + (bi & 1u) * EXC_BYTES;
+        const uint32_t exc = sbase + L::EXC + (uint32_t)team * 2u * EXC_BYTES + (bi & 1u) * EXC_BYTES;
         const int64_t r = b * 32 + lb_win(lane);
-        mbar_wait_idle(bar + 8u * TBAR_OUTFULL, bi & 1u);                    // all sixteen consumer warps are done with the table
-        // hand the consumers a clean table: a quarter (64 rows = 8 KB) per writer warp
+        mbar_wait_idle(bar + 8u * L::B_OUTFULL, bi & 1u);                    // all consumer warps of the team are done with the table
+        // hand the consumers a clean table: an equal share per writer warp of the team
 #pragma unroll 8
-        for (int i = 0; i < 16; ++i)
-            sts128(sbase + OFF_TAB + (uint32_t)q * 8192u + (uint32_t)(lane + 32 * i) * 16u, 0u, 0u, 0u, 0u);
+        for (int i = 0; i < 64 / L::WW; ++i)
+            sts128(sbase + L::TAB + (uint32_t)team * TRI_TAB_BYTES + (uint32_t)q * (TRI_TAB_BYTES / L::WW) + (uint32_t)(lane + 32 * i) * 16u,
+                   0u, 0u, 0u, 0u);
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar + 8u * TBAR_CLEAN);
+        if (lane == 0) mbar_arrive(bar + 8u * L::B_CLEAN);
         if (q == 0) {
             const uint32_t n_exc_raw = lds32(exc);
             const uint32_t n_exc = n_exc_raw < (uint32_t)LB_EXC_CAP ? n_exc_raw : (uint32_t)LB_EXC_CAP;
@@ -1155,7 +1201,7 @@ __device__ __forceinline__ void lb_writer_tri(const LbArgs &A, uint32_t sbase, i
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar + 8u * TBAR_DONE);
+            if (lane == 0) mbar_arrive(bar + 8u * L::B_DONE);
         }
     }
     if constexpr (TOT) {
@@ -1166,31 +1212,44 @@ __device__ __forceinline__ void lb_writer_tri(const LbArgs &A, uint32_t sbase, i
     }
 }
 
-template <bool TOT>
+template <bool TOT, int TEAMS>
 __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_tri_kernel(const LbArgs A, const __grid_constant__ LbMaps imaps)
 {
+    using L = TriL<TEAMS>;
+    using R = LbRing<L::GM>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     if ((sbase & 127u) != 0u) __trap();
-    for (uint32_t i = threadIdx.x; i < OFF_BAR / 16u; i += LB_THREADS) sts128(sbase + i * 16u, 0u, 0u, 0u, 0u);
+    for (uint32_t i = threadIdx.x; i < L::BAR / 16u; i += LB_THREADS) sts128(sbase + i * 16u, 0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) {
-        const uint32_t bar = sbase + OFF_BAR;
-        for (uint32_t st = 0; st < LbRing<2>::NST; ++st) {
-            mbar_init(bar + 8u * (LbRing<2>::FULL0 + st), 32u);
-            mbar_init(bar + 8u * (LbRing<2>::EMPTY0 + st), LB_CW);
+        for (int t = 0; t < TEAMS; ++t) {
+            const uint32_t bar = sbase + L::BAR + (uint32_t)t * 128u;
+            for (uint32_t st = 0; st < R::NST; ++st) {
+                mbar_init(bar + 8u * (R::FULL0 + st), 32u);
+                mbar_init(bar + 8u * (R::EMPTY0 + st), LB_CW);              // sixteen spans per chunk, one arrival each
+            }
+            mbar_init(bar + 8u * L::B_OUTFULL, L::CW);                      // all consumer warps of the team, per batch
+            mbar_init(bar + 8u * L::B_DONE, 1u);
+            mbar_init(bar + 8u * L::B_CLEAN, L::WW);
         }
-        mbar_init(bar + 8u * TBAR_OUTFULL, LB_CW);                          // all sixteen consumer warps per batch
-        mbar_init(bar + 8u * TBAR_DONE, 1u);
-        mbar_init(bar + 8u * TBAR_CLEAN, LB_WW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async();
     }
     __syncthreads();
-    if (warp >= LB_CW + LB_WW) lb_producer<2>(A, &imaps, sbase, warp - LB_CW - LB_WW, lane);
-    else if (warp >= LB_CW) lb_writer_tri<TOT>(A, sbase, warp - LB_CW, lane);
-    else lb_consumer_tri(A, sbase, warp, lane);
+    if (warp >= LB_CW + LB_WW) {
+        const int pw = warp - LB_CW - LB_WW, team = pw / L::PW;
+        lb_producer<L::GM>(A, &imaps,
+                           LbTeam{(int64_t)blockIdx.x * TEAMS + team, (int64_t)gridDim.x * TEAMS, sbase + L::BAR + (uint32_t)team * 128u,
+                                  sbase + L::STG + (uint32_t)team * R::NST * LB_STAGE_BYTES, TEAMS == 1 ? 3 : 4},
+                           pw % L::PW, lane);
+    } else if (warp >= LB_CW) {
+        const int ww = warp - LB_CW;
+        lb_writer_tri<TOT, TEAMS>(A, sbase, ww / L::WW, ww % L::WW, lane);
+    } else {
+        lb_consumer_tri<TEAMS>(A, sbase, warp / L::CW, warp % L::CW, lane);
+    }
 }
 
 template <bool TRI, bool TOT>
@@ -1221,7 +1280,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, 
         fence_async();
     }
     __syncthreads();
-    if (warp >= LB_CW + LB_WW) lb_producer<TRI>(A, &imaps, sbase, warp - LB_CW - LB_WW, lane);
+    if (warp >= LB_CW + LB_WW)
+        lb_producer<TRI>(A, &imaps, LbTeam{(int64_t)blockIdx.x, (int64_t)gridDim.x, sbase + OFF_BAR, sbase + LbRing<TRI>::STG0, 3},
+                         warp - LB_CW - LB_WW, lane);
     else if (warp >= LB_CW) lb_writer<TRI, TOT>(A, &tmap, sbase, warp - LB_CW, lane);
     else lb_consumer<TRI>(A, sbase, warp, lane);
 }
@@ -1299,19 +1360,23 @@ int lb_input_maps(LbMaps *maps, LbArgs &A, int64_t tile_w)
     return DIG_OK;
 }
 
+#ifndef DIG_LB_TRI_TEAMS
+#define DIG_LB_TRI_TEAMS 2
+#endif
 template <bool TOT>
 int launch_lb_tri(const LbArgs &A, const LbMaps &imaps, cudaStream_t stream)
 {
-    auto kern = scan_lb_tri_kernel<TOT>;
+    constexpr int TEAMS = DIG_LB_TRI_TEAMS;
+    auto kern = scan_lb_tri_kernel<TOT, TEAMS>;
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_SMEM));
+        DIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TriL<TEAMS>::SMEM));
         attr_set = true;
     }
     const int64_t n_batches = (A.n_reg + 31) >> 5;
     int64_t blocks = dig::sm_count();
-    if (blocks > n_batches) blocks = n_batches;
-    kern<<<(unsigned)blocks, LB_THREADS, LB_SMEM, stream>>>(A, imaps);
+    if (blocks > (n_batches + TEAMS - 1) / TEAMS) blocks = (n_batches + TEAMS - 1) / TEAMS;
+    kern<<<(unsigned)blocks, LB_THREADS, TriL<TEAMS>::SMEM, stream>>>(A, imaps);
     DIG_CHECK_LAUNCH();
     return DIG_OK;
 }
