@@ -272,6 +272,8 @@ def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
     if zero:
         tot5.zero_()
         tot3.zero_()
+    if shard is not None:
+        shard.mutation_contexts(dg)                      # 125 k - 500 k SNVs per rank: a few microseconds, outside the scan's events
     if ev is not None:
         ev[0].record()
     if getattr(di, "scan_ws", None) is None or di.scan_ws_n < hi - lo:
@@ -298,8 +300,9 @@ class StrongShard:
     (sharding.GatheredTable: the element stage reads the gathered buffer in place through a remapped window map);
     the pentanucleotide rows stay range-sharded (their consumer is the host).  Genes belong to the rank whose slice
     holds their first block (sharding.partition_elements) and are resolved against the gathered table, so a gene
-    that straddles a cut needs nothing else.  Mutation contexts (K3, 35 us for 1 M SNVs) are computed on every rank
-    -- cheaper than an all-reduce of the substitution counts; observed counts (K5) only for the rank's genes.
+    that straddles a cut needs nothing else.  Mutation contexts (K3): every rank handles the mutations inside its own
+    range, BEFORE the exchange, and the 192 partial substitution counts ride in the tail of its block next to the partial
+    genome totals, so the sequence model costs no collective of its own; observed counts (K5) only for the rank's genes.
     Further exchanges: all-reduce of the five scale-factor sums, all-gather of the result rows."""
 
     def __init__(self, d, di, coll, device, fused_exchange=True):
@@ -339,7 +342,7 @@ class StrongShard:
         # this rank's block, in place: the scan writes its rows and totals where the other ranks expect them
         self.local = self.gathered[self.rank]
         self.table_ready = False
-        self.rows, self.tot5, self.tot3 = gt.local_views(self.local)
+        self.rows, self.tot5, self.tot3, self.sub = gt.local_views(self.local)
         off, wmap = gt.window_map(wins[:, 0], wins[:, 1], WINDOW, len(d["lengths"]))
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)
         self.wmap_off, self.wmap = t(off, torch.int64), t(wmap, torch.int32)
@@ -378,11 +381,32 @@ class StrongShard:
         self.m_sample, self.m_cls = t(d["m_sample"][mine], torch.int32), t(d["m_cls"][mine], torch.uint8)
         self.n_syn = int(((d["m_cls"][mine] == 0)).sum())
         self.exchange_bytes = int(self.gathered.numel() * 4)
+        # mutation contexts (K3) of the mutations inside this rank's range; their 192 substitution counts travel in the
+        # tail of the rank's block, next to the partial genome totals.  A mutation belongs to the rank whose slice starts
+        # at or before it: the untiled tail of a chromosome goes with the chromosome's last window.
+        first_key = lambda r: (int(wins[parts[r][0], 0]) << 40) | int(wins[parts[r][0], 1])
+        lo_key = first_key(self.rank) if self.rank > 0 else -1
+        nxt = [r for r in range(self.rank + 1, self.world) if parts[r][1] > parts[r][0]]
+        hi_key = first_key(nxt[0]) if nxt else np.iinfo(np.int64).max
+        mk = (d["m_chrom"].astype(np.int64) << 40) | d["m_pos"]
+        self.k3_idx = np.flatnonzero((mk >= lo_key) & (mk < hi_key))
+        self.k3_host = tuple(np.ascontiguousarray(d[k][self.k3_idx]) for k in ("m_chrom", "m_pos", "m_ref", "m_alt"))
+        self.k3 = (t(self.k3_host[0], torch.int32), t(self.k3_host[1], torch.int64), t(self.k3_host[2], torch.uint8),
+                   t(self.k3_host[3], torch.uint8))
+        self.ctx_own = None
 
     def all_gather_table(self):
         """NCCL exchange (in place: this rank's block already sits at its offset of the output)."""
         import torch.distributed as dist
         dist.all_gather_into_tensor(self.gathered.view(-1, 64), self.local)
+
+    def mutation_contexts(self, dg, k3=None):
+        """K3 + substitution histogram of the rank's own mutations, written into the tail of its block (before the
+        exchange; it needs the genome only, not the scan)."""
+        from digdriver_b200 import kernels
+        mc, mp, mr, ma = k3 if k3 is not None else self.k3
+        self.ctx_own = kernels.mutation_contexts(dg, mc, mp, mr, 1, 1)
+        kernels.substitution_counts(self.ctx_own, ma, 1, 1, out=self.sub)
 
     def finish_fused_exchange(self):
         """After a scan that stored its rows into every rank's buffer: send the partial totals after them and meet the
@@ -436,7 +460,8 @@ def test_stage(dg, di, d, dist_ctx, sink=None):
 
 
 def strong_test_stage(dg, di, d, dist_ctx, shard, sink):
-    """The test stage of a range-sharded run: table exchange, then this rank's genes (see StrongShard)."""
+    """The test stage of a range-sharded run: (table exchange,) then this rank's genes (see StrongShard).  The mutation
+    contexts were computed before the exchange (StrongShard.mutation_contexts): their counts arrive in the block tails."""
     import torch
     from digdriver_b200 import kernels, pipeline
     dev = dg.device
@@ -444,34 +469,23 @@ def strong_test_stage(dg, di, d, dist_ctx, shard, sink):
     side = di.side_stream
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        # nothing below depends on the scan: observed counts of the rank's genes and the sequence model's numerator
+        # does not depend on the exchange: observed counts of the rank's genes
         obs, nsamp = kernels.tabulate_genes(shard.m_gene, shard.m_sample, shard.m_cls, max(shard.n_genes, 1), device=dev,
                                             status_sink=sink)
-        if getattr(shard, "k3_by_range", None) is None:
-            ctx = kernels.mutation_contexts(dg, di.m_chrom, di.m_pos, di.m_ref, 1, 1)
-            sub = kernels.substitution_counts(ctx, di.m_alt, 1, 1)
-        else:
-            # e2e leg: only the chromosomes of the rank's slice are resident, so the rank handles the mutations
-            # inside its slice and the 192 counts are all-reduced
-            mc, mp, mr, ma = shard.k3_by_range
-            ctx = kernels.mutation_contexts(dg, mc, mp, mr, 1, 1)
-            sub = kernels.substitution_counts(ctx, ma, 1, 1)
     if not shard.table_ready:
-        shard.all_gather_table()                         # THE exchange: trinucleotide rows + partial totals, one collective
+        shard.all_gather_table()                         # THE exchange: trinucleotide rows + partial totals + substitution counts
     tot = shard.totals()
     main.wait_stream(side)
     if not torch.cuda.is_current_stream_capturing():
-        for t in (obs, nsamp, ctx, sub):
+        for t in (obs, nsamp):
             t.record_stream(main)
-    if getattr(shard, "k3_by_range", None) is not None:
-        dist_ctx.all_reduce_sum(sub)
-    d_pr = kernels.sequence_freq(sub.contiguous(), tot[1024:1088].contiguous())
+    d_pr = kernels.sequence_freq(tot[1088:1280].contiguous(), tot[1024:1088].contiguous())
     pre = kernels.element_transfer(shard.g_chrom, shard.g_strand, shard.g_ptr, shard.g_bs, shard.g_be, WINDOW,
                                    shard.wmap_off, shard.wmap, shard.gathered.view(-1, 64), shard.y_pred_g, shard.std_g,
                                    shard.y_true_g, shard.flag_g, d_pr, L_elt=shard.L, device=dev,
                                    max_span=shard.max_span, status_sink=sink)
     res = pipeline.gene_burden_test(pre, obs, nsamp, shard.n_syn, collectives=dist_ctx)
-    res["D_PR"], res["CTX"], res["TOTALS"] = d_pr, ctx, tot
+    res["D_PR"], res["CTX"], res["TOTALS"] = d_pr, shard.ctx_own, tot
     return res
 
 
@@ -584,7 +598,12 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
             full[shard.gene_ids] = res[k].cpu().numpy()
             got[k] = full
         pools = {"win_pool": np.arange(shard.lo, shard.hi), "gene_pool": shard.gene_ids}
-    got.update({"ctx": res["CTX"].cpu().numpy(), "d_pr": res["D_PR"].cpu().numpy(), "sums": res["SUMS"].cpu().numpy()})
+    if shard is None:
+        ctx_all = res["CTX"].cpu().numpy()
+    else:
+        ctx_all = np.full(len(d["m_pos"]), -2, dtype=np.int32)           # the mutations inside this rank's range
+        ctx_all[shard.k3_idx] = res["CTX"].cpu().numpy()
+    got.update({"ctx": ctx_all, "d_pr": res["D_PR"].cpu().numpy(), "sums": res["SUMS"].cpu().numpy()})
     out = ps.check_sample(d["lengths"], dg.chrom_off, seed, WINDOW, d, got, n_windows=n_windows, n_genes=n_genes, **pools)
     if shard is not None:
         # rows of windows scanned by the OTHER ranks, as they arrived through the exchange
@@ -699,15 +718,6 @@ class HostPath:
         else:
             # range-sharded: this rank's genes and their mutations, the mutations inside its window slice (K3), and
             # the region parameters of all windows (2.5 MB each; K6 may touch a neighbour's windows)
-            # (a mutation belongs to the rank whose slice starts at or before it: the untiled tail of a chromosome
-            # goes with the chromosome's last window)
-            allw, parts = d["wins"], shard.table.parts
-            first_key = lambda r: (int(allw[parts[r][0], 0]) << 40) | int(allw[parts[r][0], 1])
-            lo_key = first_key(shard.rank) if shard.rank > 0 else -1
-            nxt = [r for r in range(shard.rank + 1, shard.world) if parts[r][1] > parts[r][0]]
-            hi_key = first_key(nxt[0]) if nxt else np.iinfo(np.int64).max
-            mk = (d["m_chrom"].astype(np.int64) << 40) | d["m_pos"]
-            sel = (mk >= lo_key) & (mk < hi_key)
             cpu = lambda t: t.cpu()
             self.host_in = {"y_pred_g": cpu(shard.y_pred_g).pin_memory(), "std_g": cpu(shard.std_g).pin_memory(),
                             "y_true_g": cpu(shard.y_true_g).pin_memory(), "flag_g": cpu(shard.flag_g).pin_memory(),
@@ -716,8 +726,8 @@ class HostPath:
                             "g_be": cpu(shard.g_be).pin_memory(), "L": cpu(shard.L).pin_memory(),
                             "m_gene": cpu(shard.m_gene).pin_memory(), "m_sample": cpu(shard.m_sample).pin_memory(),
                             "m_cls": cpu(shard.m_cls).pin_memory(),
-                            "k3_chrom": pin(d["m_chrom"][sel]), "k3_pos": pin(d["m_pos"][sel]),
-                            "k3_ref": pin(d["m_ref"][sel]), "k3_alt": pin(d["m_alt"][sel])}
+                            "k3_chrom": pin(shard.k3_host[0].astype(np.int32)), "k3_pos": pin(shard.k3_host[1]),
+                            "k3_ref": pin(shard.k3_host[2]), "k3_alt": pin(shard.k3_host[3])}
             n_out = max(shard.n_genes, 1)
         self.host_out = torch.empty((n_out, 14), dtype=torch.float64, pin_memory=True)
         self.table_stream = torch.cuda.Stream(device)
@@ -752,12 +762,13 @@ class HostPath:
             for k in ("y_pred_g", "std_g", "y_true_g", "flag_g", "g_chrom", "g_strand", "g_ptr", "g_bs", "g_be", "L",
                       "m_gene", "m_sample", "m_cls"):
                 setattr(sh, k, t[k])
-            sh.k3_by_range = (t["k3_chrom"], t["k3_pos"], t["k3_ref"], t["k3_alt"])
             sh.table_ready = False                            # the host path's rows are exchanged with NCCL
             n_loc = shard.hi - shard.lo
             sh.rows[:n_loc].copy_(hs.counts3)                 # into this rank's block of the exchange buffer
             sh.tot5.copy_(hs.totals)
             sh.tot3.copy_(hs.totals3)
+            # only the chromosomes of the rank's slice are resident: it handles the mutations inside its range
+            sh.mutation_contexts(hs.genome, (t["k3_chrom"], t["k3_pos"], t["k3_ref"], t["k3_alt"]))
             di2.shard = sh
             from digdriver_b200.sharding import Collectives
             res = test_stage(hs.genome, di2, d, Collectives(), sink=sink)

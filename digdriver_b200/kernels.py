@@ -371,11 +371,13 @@ def build_window_map(win_chrom_idx, win_start, window, n_chrom):
     return off, wmap
 
 
-def substitution_counts(ctx, alt, n_up=1, n_down=1, stream=None):
-    """Histogram of substitutions in sorted 'CTX>CTX2' order: int64 [3K] on the device of ``ctx``."""
+def substitution_counts(ctx, alt, n_up=1, n_down=1, stream=None, out=None):
+    """Histogram of substitutions in sorted 'CTX>CTX2' order: int64 [3K] on the device of ``ctx`` (overwrites `out`)."""
     dev = ctx.device
     al = _dev(alt, torch.uint8, dev)
-    out = torch.empty(3 * 4 ** (n_up + n_down + 1), dtype=torch.int64, device=dev)
+    if out is None:
+        out = torch.empty(3 * 4 ** (n_up + n_down + 1), dtype=torch.int64, device=dev)
+    assert out.dtype == torch.int64 and out.is_contiguous() and out.numel() == 3 * 4 ** (n_up + n_down + 1)
     with torch.cuda.device(dev):
         _lib.call("dig_substitution_counts", ctx.data_ptr(), al.data_ptr(), ctx.numel(), int(n_up), int(n_down),
                   out.data_ptr(), _stream(dev, stream))

@@ -141,13 +141,15 @@ def all_gather_rows(coll, t, sizes):
 # ONE genome over all ranks (strong scaling): layout of the all-gathered trinucleotide table
 # --------------------------------------------------------------------------------------------
 
-TOTALS_ROWS = 34      # 1024 + 64 genome-wide totals as int64 = 2176 int32 words = 34 rows of 64
+TAIL_I64 = 1024 + 64 + 192   # partial genome totals (pentanucleotide | trinucleotide) and partial substitution counts
+TOTALS_ROWS = 40             # TAIL_I64 int64 = 2560 int32 words = 40 rows of 64
 
 
 class GatheredTable:
     """Layout of the [world, m + TOTALS_ROWS, 64] int32 buffer that ONE all_gather_into_tensor fills: block r holds the
     trinucleotide rows of rank r's window slice (padded to the longest slice, m rows) followed by that rank's partial
-    genome-wide totals (pentanucleotide | trinucleotide, int64 viewed as 34 int32 rows).  The element stage indexes the
+    genome-wide totals and substitution counts (pentanucleotide | trinucleotide | 192 substitutions, int64 viewed as 40
+    int32 rows).  The element stage indexes the
     buffer in place through a window map that points at the gathered rows, so nothing is copied or compacted, and the
     totals ride in the same collective (replaces the df.sum(axis=0) of DigPreprocess.py:59 and the pd.concat of
     sequence_tools.py:125)."""
@@ -176,11 +178,15 @@ class GatheredTable:
         return off, out
 
     def local_views(self, local):
-        """(rows of the own slice [m, 64], totals5 int64 [1024], totals3 int64 [64]) as views of this rank's block."""
+        """(rows of the own slice [m, 64], totals5 int64 [1024], totals3 int64 [64], substitution counts int64 [192]) as
+        views of this rank's block.  The last one lets the ranks share the sequence model's numerator (the substitution
+        counts of the mutations inside their own ranges, train_sequence_model sequence_tools.py:336-339) through the same
+        exchange instead of an all-reduce."""
         tot = local[self.m:].view(torch.int64).reshape(-1)
-        return local[: self.m], tot[:1024], tot[1024:1088]
+        return local[: self.m], tot[:1024], tot[1024:1088], tot[1088:TAIL_I64]
 
     def summed_totals(self, gathered):
-        """int64 [1088]: the ranks' partial totals added up (gathered: [world, block_rows, 64] int32)."""
+        """int64 [1280]: the ranks' partial totals (1024 | 64) and substitution counts (192) added up (gathered:
+        [world, block_rows, 64] int32)."""
         g = gathered.view(self.world, self.block_rows, 64)[:, self.m:, :].contiguous()
         return g.view(torch.int64).reshape(self.world, -1).sum(dim=0)

@@ -180,10 +180,11 @@ def _gathered_worker(rank, world, port, ret):
     c3, _ = dig_oracle.count_regions(cat, off, sub.lengths, c, s, e, 1, 1)
     c5, _ = dig_oracle.count_regions(cat, off, sub.lengths, c, s, e, 2, 2)
     local = torch.zeros((gt.block_rows, 64), dtype=torch.int32)
-    rows, t5, t3 = gt.local_views(local)
+    rows, t5, t3, sub = gt.local_views(local)
     rows[: hi - lo] = torch.from_numpy(c3.astype(np.int32))
     t5.copy_(torch.from_numpy(c5.sum(axis=0)))
     t3.copy_(torch.from_numpy(c3.sum(axis=0)))
+    sub.copy_(torch.arange(192, dtype=torch.int64) * (rank + 1) + (1 << 33))          # partial substitution counts
     gathered = torch.zeros((world, gt.block_rows, 64), dtype=torch.int32)
     dist.all_gather_into_tensor(gathered.view(-1, 64), local)
     tot = gt.summed_totals(gathered).numpy()
@@ -193,7 +194,8 @@ def _gathered_worker(rank, world, port, ret):
     table = gathered.view(-1, 64).numpy()
     row_of = gt.row_of_window(len(wins))
     ok_rows = bool(np.array_equal(table[row_of], f3))
-    ok_tot = bool(np.array_equal(tot[:1024], f5.sum(axis=0)) and np.array_equal(tot[1024:], f3.sum(axis=0)))
+    ok_tot = bool(np.array_equal(tot[:1024], f5.sum(axis=0)) and np.array_equal(tot[1024:1088], f3.sum(axis=0)) and
+                  np.array_equal(tot[1088:], np.arange(192) * 3 + (1 << 34)) and len(tot) == 1280)
     # the window map resolves (chromosome, window number) to gathered rows; an element straddling the cut sees both
     moff, wmap = gt.window_map(wins[:, 0], wins[:, 1], W, 2)
     cut = parts[0][1]
