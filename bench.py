@@ -582,7 +582,10 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
     cols = ["MU", "SIGMA", "Pi_SYN", "Pi_MIS", "Pi_NONS", "Pi_SPL", "Pi_TRUNC", "Pi_NONSYN", "ALPHA", "THETA", "OBS_SYN",
             "OBS_MIS", "OBS_NONS", "OBS_SPL", "PVAL_INDEL_BURDEN", "PVAL_MUT_BURDEN"] + ["PVAL_%s_BURDEN" % c for c in ps.CLASSES]
     if shard is None:
-        got = {"counts5": rows(di.counts5), "counts3": rows(di.counts3), "n_syn": d["n_syn"]}
+        # (N independent genomes, --scaling weak: the scale factors are cohort-wide, so the synonymous count the kernel
+        # used is the all-reduced one that rides in SUMS[3])
+        got = {"counts5": rows(di.counts5), "counts3": rows(di.counts3),
+               "n_syn": float(res["SUMS"][3].item()) if res["SUMS"].numel() > 3 else d["n_syn"]}
         for k in cols:
             got[k] = res[k].cpu().numpy()
         pools = {}
