@@ -608,6 +608,18 @@ def parity_sample(dg, d, di, res, seed, n_windows=500, n_genes=200):
         ctx_all[shard.k3_idx] = res["CTX"].cpu().numpy()
     got.update({"ctx": ctx_all, "d_pr": res["D_PR"].cpu().numpy(), "sums": res["SUMS"].cpu().numpy()})
     out = ps.check_sample(d["lengths"], dg.chrom_off, seed, WINDOW, d, got, n_windows=n_windows, n_genes=n_genes, **pools)
+    # EVERY window this rank scanned (all 309 990 on one GPU), both tables, against the C oracle; the totals when the rank
+    # holds the whole genome
+    a0, b0 = (0, len(d["wins"])) if shard is None else (shard.lo, shard.hi)
+    c3rows = (lambda a, b: di.counts3[a:b].cpu().numpy()) if shard is None else \
+        (lambda a, b: got["counts3"](np.arange(a, b)))
+    allw = ps.check_all_windows(d["lengths"], dg.chrom_off, seed, d["wins"], lambda a, b: di.counts5[a:b].cpu().numpy(),
+                                c3rows, di.totals5.cpu().numpy() if shard is None else None,
+                                di.totals3.cpu().numpy() if shard is None else None, lo=a0, hi=b0)
+    out["all_windows_checked"] = allw["windows"]
+    if not allw["ok"]:
+        out["ok"] = False
+        out["detail"] += "; all windows: " + allw["detail"]
     if shard is not None:
         # rows of windows scanned by the OTHER ranks, as they arrived through the exchange
         other = np.setdiff1d(np.arange(len(d["wins"])), pools["win_pool"])

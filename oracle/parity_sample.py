@@ -169,3 +169,38 @@ def check_sample(lengths, chrom_off, seed, window, d, got, n_windows=500, n_gene
     return {"windows": int(len(idx)), "windows_beyond_2^31": hi_off, "mutations": n_mut_checked, "genes": int(len(gid)),
             "p_values": n_p, "max_rel_err_pretrain": worst, "max_dlog10_p": worst_p, "ok": not detail,
             "detail": "; ".join(detail)}
+
+
+def check_all_windows(lengths, chrom_off, seed, wins, rows5, rows3, totals5=None, totals3=None, lo=0, hi=None, n_frac16=16):
+    """EVERY window lo .. hi of the tiling (all of them by default) against the C oracle, one chromosome at a time: the
+    chromosome is regenerated on the host from the global position alone, counted for both context sizes
+    (sequence_tools.py:65-128), and compared bit for bit with the GPU rows that the callables rows5 / rows3
+    (a, b) -> [b - a, K] host arrays return.  totals5 / totals3 (host arrays, optional): the genome-wide sums
+    (DigPreprocess.py:59) of the same windows.  Returns {"windows": n, "ok": bool, "detail": str}."""
+    wins = np.asarray(wins)
+    hi = len(wins) if hi is None else hi
+    lengths = np.asarray(lengths, dtype=np.int64)
+    tot = {2: np.zeros(1024, dtype=np.int64), 1: np.zeros(64, dtype=np.int64)}
+    detail, n_rows = [], 0
+    for c in np.unique(wins[lo:hi, 0]):
+        sel = lo + np.flatnonzero(wins[lo:hi, 0] == c)
+        a, b = int(sel[0]), int(sel[-1]) + 1
+        if b - a != len(sel):
+            return {"windows": n_rows, "ok": False, "detail": "windows of chromosome %d are not contiguous" % c}
+        n = int(lengths[c])
+        seq = orc.synth_genome(int(chrom_off[c]), n, seed, n_frac16)
+        off0, ln, rc = np.zeros(1, dtype=np.int64), np.array([n], dtype=np.int64), np.zeros(len(sel), dtype=np.int32)
+        for nu, rows in ((2, rows5), (1, rows3)):
+            if rows is None:
+                continue
+            want, _ = orc.count_regions(seq, off0, ln, rc, wins[sel, 1], wins[sel, 2], nu, nu)
+            bad = np.flatnonzero((np.asarray(rows(a, b)) != want).any(axis=1))
+            if bad.size:
+                detail.append("chromosome %d, k = %d: %d rows differ, first window %d" % (c, 2 * nu + 1, bad.size, a + bad[0]))
+            tot[nu] += want.sum(axis=0)
+        n_rows += len(sel)
+    if totals5 is not None and not np.array_equal(np.asarray(totals5, dtype=np.int64), tot[2]):
+        detail.append("pentanucleotide totals differ")
+    if totals3 is not None and not np.array_equal(np.asarray(totals3, dtype=np.int64), tot[1]):
+        detail.append("trinucleotide totals differ")
+    return {"windows": int(n_rows), "ok": not detail and n_rows == hi - lo, "detail": "; ".join(detail)}

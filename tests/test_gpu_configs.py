@@ -370,25 +370,10 @@ def test_config2_parity_sample_at_full_size(oracle):
     # EVERY window of the 3.1 Gb genome (309 990 x 1088 bins) and the genome-wide totals against the C oracle, one
     # chromosome at a time: the synthetic genome is regenerated on the host from the global position alone
     import time
+    from oracle import parity_sample as ps
     t0 = time.time()
-    wins = d["wins"]
-    tot5, tot3 = np.zeros(1024, dtype=np.int64), np.zeros(64, dtype=np.int64)
-    n_rows = 0
-    for c in range(len(d["lengths"])):
-        sel = np.flatnonzero(wins[:, 0] == c)
-        lo, hi = int(sel[0]), int(sel[-1]) + 1
-        assert hi - lo == len(sel)                                       # tile_windows keeps chromosomes contiguous
-        n = int(d["lengths"][c])
-        seq = oracle.synth_genome(int(dg.chrom_off[c]), n, 1)
-        off0, ln, rc = np.zeros(1, dtype=np.int64), np.array([n], dtype=np.int64), np.zeros(len(sel), dtype=np.int32)
-        for (nu, tab, tot) in ((2, di.counts5, tot5), (1, di.counts3, tot3)):
-            want, _ = oracle.count_regions(seq, off0, ln, rc, wins[sel, 1], wins[sel, 2], nu, nu)
-            got = tab[lo:hi].cpu().numpy()
-            bad = np.flatnonzero((got != want).any(axis=1))
-            assert bad.size == 0, "chromosome %d, k = %d: %d rows differ, first window %d" % (c, 2 * nu + 1, bad.size, lo + bad[0])
-            tot += want.sum(axis=0)
-        n_rows += len(sel)
-    assert n_rows == len(wins)
-    assert np.array_equal(di.totals5.cpu().numpy(), tot5) and np.array_equal(di.totals3.cpu().numpy(), tot3)
+    allw = ps.check_all_windows(d["lengths"], dg.chrom_off, 1, d["wins"], lambda a, b: di.counts5[a:b].cpu().numpy(),
+                                lambda a, b: di.counts3[a:b].cpu().numpy(), di.totals5.cpu().numpy(), di.totals3.cpu().numpy())
+    assert allw["ok"] and allw["windows"] == len(d["wins"]), allw
     print("full-size parity: %d windows x (1024 + 64) bins and both totals equal the C oracle bit for bit (%.1f s of host work)"
-          % (n_rows, time.time() - t0))
+          % (allw["windows"], time.time() - t0))
