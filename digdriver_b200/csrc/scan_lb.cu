@@ -89,11 +89,26 @@ constexpr uint32_t OFF_CNT = OFF_EXC + 2u * EXC_BYTES;             // pairs coun
 constexpr uint32_t OFF_CHK = OFF_CNT + 256u;                       // sum of table bytes per window
 constexpr uint32_t OFF_FLG = OFF_CHK + 128u;                       // batch verdict, writer warp 0 -> the others
 constexpr uint32_t OFF_BAR = OFF_FLG + 16u;
-constexpr uint32_t LB_SMEM = OFF_BAR + 128u;
+constexpr uint32_t LB_SMEM = OFF_BAR + 256u;                       // 17 barriers of 8 bytes
 static_assert(OFF_BAR % 16u == 0u, "barrier block alignment");
 static_assert(LB_SMEM <= 232448u, "shared memory budget");
 
 enum { BAR_FULL = 0, BAR_EMPTY = 2, BAR_OUTFULL = 4, BAR_OUTEMPTY = 8, BAR_DONE = 12, BAR_CLEAN = 13 };
+
+// Third staging slot of the pentanucleotide modes.  Two stages are all that fits beside the 128 KB table and the four
+// slice buffers -- but the slice buffers (32 KB, directly behind the two stages) are idle while a batch is being counted,
+// and one stage is 26 KB.  Chunk kq of a batch goes to slot kq % 3, slot 2 being the slice buffers: chunks 0 and 1 of the
+// NEXT batch can still be fetched during the write-out (slots 0 and 1), and slot 2 is only filled once the last tile of
+// the previous batch has left the buffers (BAR_OUTFREE, one arrival per writer warp; waiting for BAR_DONE instead, which
+// comes after the table clearing and warp 0's closing work, held chunk 2 -- and the chunks queued behind it -- back by
+// ~2 k cycles) and is always read before the batch barrier that precedes the next write-out.  Inside a batch a chunk is then requested three chunks ahead instead of two.
+#ifndef DIG_LB_STAGE3
+#define DIG_LB_STAGE3 1
+#endif
+constexpr bool LB_ST3 = DIG_LB_STAGE3 != 0;
+enum { BAR_FULL2 = 14, BAR_EMPTY2 = 15, BAR_OUTFREE = 16 };           // OUTFREE: the four writer warps have shipped their last tile of the batch
+__device__ __forceinline__ uint32_t lb3_full(uint32_t stage) { return stage < 2u ? (uint32_t)BAR_FULL + stage : (uint32_t)BAR_FULL2; }
+__device__ __forceinline__ uint32_t lb3_empty(uint32_t stage) { return stage < 2u ? (uint32_t)BAR_EMPTY + stage : (uint32_t)BAR_EMPTY2; }
 
 // Staging ring per mode.  The pentanucleotide modes have room for two stages next to their 128 KB table and the slice
 // buffers; the trinucleotide-only mode (32 KB table, no slice buffers) runs FOUR, which hides the ~3 k cycles between a
@@ -495,9 +510,16 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
     const int m = lane & 3;                                // row of the group's box
     const bool mine = (lane >> T.lane_shift) == pw;
     uint32_t ci = 0u;
-    for (int64_t b = T.b0; b < n_batches; b += T.bstep) {
+    constexpr bool ST3 = LB_ST3 && GM < 2;                 // three slots, the third one aliasing the slice buffers
+    uint32_t uses = 0u, pbi = 0u;                          // bit s of uses: parity of the number of fills of slot s
+    for (int64_t b = T.b0; b < n_batches; b += T.bstep, ++pbi) {
         const LbGeom g = lb_geom<GM>(b * 32 + lb_win(lane), A.n_reg, A.chrom_off, A.chrom_len, A.reg_chrom, A.reg_start, A.reg_end);
         const int nch = warp_max(g.nch);
+        uint32_t st3 = 0u;
+        if constexpr (ST3) {
+            // batch pbi - 2 is closed (it practically always is): the parity wait for batch pbi - 1 below cannot alias
+            if (pbi >= 2u) mbar_wait_idle(bar + 8u * BAR_OUTFREE, pbi & 1u);
+        }
         // regular group: every window has the leader's chunk count and sits m * 8 W bases after the leader's origin
         const int lead = lane & ~3;
         const uint32_t olo = __shfl_sync(0xffffffffu, (uint32_t)(unsigned long long)g.O, lead);
@@ -522,11 +544,28 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
         for (int kq = 0; kq < nch; ++kq, ++ci) {
             const int k = lb_chunk_order(kq, nch);
             using R = LbRing<GM>;
-            const uint32_t stage = ci & (R::NST - 1u);
+            uint32_t stage, fpar, full_i, empty_i;
+            if constexpr (ST3) {
+                stage = st3;
+                st3 = st3 == 2u ? 0u : st3 + 1u;
+                fpar = (uses >> stage) & 1u;
+                uses ^= 1u << stage;
+                full_i = lb3_full(stage);
+                empty_i = lb3_empty(stage);
+            } else {
+                stage = ci & (R::NST - 1u);
+                fpar = (ci >> R::LOG) & 1u;
+                full_i = R::FULL0 + stage;
+                empty_i = R::EMPTY0 + stage;
+            }
             LB_T(t_e0);
-            mbar_wait_idle(bar + 8u * (R::EMPTY0 + stage), ((ci >> R::LOG) & 1u) ^ 1u);
+            mbar_wait_idle(bar + 8u * empty_i, fpar ^ 1u);
+            if constexpr (ST3) {
+                // the slice buffers are free once the previous batch's last tiles have left them
+                if (stage == 2u && pbi >= 1u) mbar_wait_idle(bar + 8u * BAR_OUTFREE, (pbi - 1u) & 1u);
+            }
             LB_T(t_e1);
-            const uint32_t full = bar + 8u * (R::FULL0 + stage);
+            const uint32_t full = bar + 8u * full_i;
             const uint32_t stg = T.stg0 + stage * LB_STAGE_BYTES;
             if (!mine) {
                 // another producer warp's window
@@ -570,7 +609,7 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
 #ifdef DIG_LB_TIMING
             if (pw == 0) {                                                   // copy latency: issued -> FULL complete
                 const long long t_i = clock64();
-                mbar_wait(full, (ci >> R::LOG) & 1u);
+                mbar_wait(full, fpar);
                 if (lane == 0 && A.timing != nullptr) {
                     atomicAdd(A.timing + 7, (unsigned long long)(clock64() - t_i));
                     atomicAdd(A.timing + 11, (unsigned long long)(t_e1 - t_e0));      // producer idle (EMPTY wait)
@@ -594,7 +633,7 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
     const uint32_t bar = sbase + OFF_BAR;
     const uint32_t tabl = sbase + OFF_TAB + (uint32_t)lane * 4u;
     const int64_t n_batches = (A.n_reg + 31) >> 5;
-    uint32_t cit = 0u, bi = 0u;
+    uint32_t cit = 0u, bi = 0u, uses = 0u;
     // one VECTOR-register copy of the PRMT constant: made formally lane-dependent (A.zero = 0), otherwise ptxas keeps it
     // in a uniform register and copies it into a fresh vector register for every PRMT
     const uint32_t top_r = A.top | (tabl & A.zero);
@@ -618,11 +657,25 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
         const uint32_t exc = sbase + OFF_EXC + par * EXC_BYTES;
         uint32_t npairs = 0u;
         bool clean = bi == 0u;                             // the kernel prologue zeroed the tables of the first batch
+        uint32_t st3 = 0u;
         for (int kq = 0; kq < nch; ++kq, ++cit) {
             const int k = lb_chunk_order(kq, nch);
-            const uint32_t stage = cit & 1u;
+            uint32_t stage, fpar, full_i, empty_i;
+            if constexpr (LB_ST3) {                        // slot kq % 3 (see BAR_FULL2); the producers count the same way
+                stage = st3;
+                st3 = st3 == 2u ? 0u : st3 + 1u;
+                fpar = (uses >> stage) & 1u;
+                uses ^= 1u << stage;
+                full_i = lb3_full(stage);
+                empty_i = lb3_empty(stage);
+            } else {
+                stage = cit & 1u;
+                fpar = (cit >> 1) & 1u;
+                full_i = BAR_FULL + stage;
+                empty_i = BAR_EMPTY + stage;
+            }
             LB_T(t_a);
-            mbar_wait(bar + 8u * (BAR_FULL + stage), (cit >> 1) & 1u);
+            mbar_wait(bar + 8u * full_i, fpar);
             LB_T(t_b);
             LB_ACC(0, t_a, t_b);
             LB_ACC((kq == 0 ? 8 : (kq == 1 ? 9 : 10)), t_a, t_b);
@@ -632,7 +685,7 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
                 const int base0 = k * LB_CHUNK + warp * LB_SPAN;
                 const int lo_u = TRI ? min(g.lo5, g.lo3) : g.lo5, hi_u = TRI ? max(g.hi5, g.hi3) : g.hi5;
                 if (!__any_sync(0xffffffffu, k < g.nch && lo_u - base0 < 130 && hi_u - base0 > 2)) {
-                    if (lane == 0) mbar_arrive(bar + 8u * (BAR_EMPTY + stage));
+                    if (lane == 0) mbar_arrive(bar + 8u * empty_i);
                     continue;
                 }
             }
@@ -652,7 +705,7 @@ __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int
             // scoreboard when the data of ALL lanes has been written, so lane 0's dependence covers the warp)
             const uint32_t dep = (D[0] | D[4]) ^ (D[8] | M[0]) ^ M[4];
             __syncwarp();
-            if (lane == 0) mbar_arrive_after_loads(bar + 8u * (BAR_EMPTY + stage), dep, A.zero);
+            if (lane == 0) mbar_arrive_after_loads(bar + 8u * empty_i, dep, A.zero);
             if (!clean) {                                                    // the writer warps have re-zeroed the tables
                 LB_T(t_c);
                 mbar_wait(bar + 8u * BAR_CLEAN, (bi - 1u) & 1u);
@@ -871,6 +924,9 @@ __device__ __forceinline__ void lb_writer(const LbArgs &A, const CUtensorMap *tm
             if (lane == 0) {
                 bulk_wait_read<0>();                                         // the tile has left shared memory
                 mbar_arrive_after_loads(bar + 8u * (BAR_OUTEMPTY + q), dep, A.zero);
+                if constexpr (LB_ST3) {
+                    if (s4 == 3) mbar_arrive_after_loads(bar + 8u * BAR_OUTFREE, dep, A.zero);
+                }
             }
             __syncwarp();
         }
@@ -1269,6 +1325,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) scan_lb_kernel(const LbArgs A, 
         mbar_init(bar + 8u * (BAR_FULL + 1), 32u);
         mbar_init(bar + 8u * (BAR_EMPTY + 0), LB_CW);
         mbar_init(bar + 8u * (BAR_EMPTY + 1), LB_CW);
+        mbar_init(bar + 8u * BAR_FULL2, 32u);
+        mbar_init(bar + 8u * BAR_EMPTY2, LB_CW);
+        mbar_init(bar + 8u * BAR_OUTFREE, LB_WW);
 #pragma unroll
         for (int i = 0; i < LB_NOUT; ++i) {
             mbar_init(bar + 8u * (BAR_OUTFULL + i), LB_CW / 2);            // the eight consumer warps that fill a slice
