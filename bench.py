@@ -43,7 +43,7 @@ N_SAMPLES = 200
 B_PER_BASE_K1024 = 0.25 + 0.125 + 4.0 * 1024 / WINDOW      # 0.7846 B/base
 B_PER_BASE_FUSED = 0.25 + 0.125 + 4.0 * (1024 + 64) / WINDOW  # both tables written by one pass: 0.8102
 B_PER_BASE_K64 = 0.25 + 0.125 + 4.0 * 64 / WINDOW
-SCAN_DRAM_TRAFFIC = 2.4667e9      # dram read + write bytes of one fused scan launch at 3.1 Gb (ncu --set full, profiles/)
+SCAN_DRAM_TRAFFIC = 2.4683e9      # dram read + write bytes of one fused scan launch at 3.1 Gb (ncu --set full, profiles/)
 
 
 _JSON_OUT = None

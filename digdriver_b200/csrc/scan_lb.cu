@@ -627,6 +627,11 @@ __device__ __forceinline__ void lb_producer(const LbArgs &A, const LbMaps *maps,
 // predicated edge span takes fewer spans afterwards -- the batch barrier wait fell from 3.5 k to 1.4 k cycles per batch
 // in the trinucleotide kernel, but every span then starts with a look + atomic + barrier wait on one lane followed by a
 // shuffle, and the stages are released less regularly: 0.687 vs 0.606 ms (K = 64), 0.995 vs 0.954 ms (fused).
+// Also tried on top of the three-slot ring: probing the NEXT chunk's FULL barrier (mbarrier.test_wait) right after a
+// chunk's registers are loaded and looking at the answer only after the chunk has been counted, and the same one slice
+// ahead for the slice buffers' OUTEMPTY barriers -- a barrier look is a round trip through the shared-memory pipe behind
+// the other warps' atomics.  Measured on one box, twice each: 0.925 ms without, 0.933-0.936 ms with the FULL probe,
+// 0.941-0.944 ms with the OUTEMPTY probe: the extra shared-memory operation costs more than the hidden latency.
 template <bool TRI>
 __device__ __forceinline__ void lb_consumer(const LbArgs &A, uint32_t sbase, int warp, int lane)
 {
