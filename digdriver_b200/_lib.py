@@ -48,6 +48,7 @@ SIGNATURES = {
     "dig_nb_burden_test": (_I, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "dig_fisher_combine2": (_I, [_P, _P, _I64, _P, _P]),
     "dig_sequence_freq": (_I, [_P, _P, _I, _P, _P]),
+    "dig_size_ratio": (_I, [_P, _P, _I64, _P, _P]),
     "dig_gene_scale_sums": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P]),
     "dig_gene_burden_test": (_I, [_P, _P, _P, _P, _P, _P, _I64, _P, _D, _D, _P, _P]),
     "dig_gene_dnds_sel": (_I, [_P, _P, _P, _P, _I64, _P, _P]),
@@ -87,7 +88,7 @@ KERNELS_PER_CALL = {
     "dig_pack_genome": 1, "dig_count_contexts": 1, "dig_count_contexts_fused53": 1, "dig_synth_genome": 1, "dig_mutation_contexts": 1,
     "dig_substitution_counts": 1, "dig_count_hits": 1, "dig_tabulate_elements": 3, "dig_tabulate_genes": 2, "dig_site_counts": 1,
     "dig_element_transfer": 1, "dig_nb_pvalue_greater_midp": 1, "dig_nb_burden_test": 1, "dig_fisher_combine2": 1,
-    "dig_sequence_freq": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
+    "dig_sequence_freq": 1, "dig_size_ratio": 1, "dig_gene_scale_sums": 1, "dig_gene_burden_test": 2,
     "dig_window_denominators": 1, "dig_site_test": 1, "dig_gene_dnds_sel": 1, "dig_selection_coefficient": 1, "dig_region_prob_norm": 1, "dig_position_obs": 1, "dig_position_test": 1, "dig_nb_pvalue_exact": 1,
     "dig_nb_pvalue_variant": 1, "dig_loglik": 1, "dig_gene_llr_test": 1, "dig_overlap_count": 1, "dig_overlap_fill": 1,
     "dig_element_region_counts": 1, "dig_element_psum": 1, "dig_narrow_counts_u16": 1, "dig_peer_broadcast": 1, "dig_nmask_fill_runs": 1,

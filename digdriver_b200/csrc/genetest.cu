@@ -142,9 +142,26 @@ __global__ void __launch_bounds__(256) seq_freq_kernel(const unsigned long long 
     if (j < n_sub) freq[j] = (double)counts[j] / (double)totals[j / 3];
 }
 
+__global__ void __launch_bounds__(256) size_ratio_kernel(const int64_t *__restrict__ num, const int64_t *__restrict__ den, int64_t n,
+                                                         double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __ddiv_rn((double)num[i], (double)den[i]);
+}
+
 }  // namespace
 
 extern "C" {
+
+int dig_size_ratio(const int64_t *num_d, const int64_t *den_d, int64_t n, double *out_d, void *stream)
+{
+    DIG_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return DIG_OK;
+    DIG_CHECK_ARG(num_d && den_d && out_d, "null pointer");
+    size_ratio_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(num_d, den_d, n, out_d);
+    DIG_CHECK_LAUNCH();
+    return DIG_OK;
+}
 
 int dig_sequence_freq(const unsigned long long *subst_counts_d, const unsigned long long *ctx_totals_d, int n_ctx,
                       double *freq_d, void *stream)

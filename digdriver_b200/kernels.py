@@ -402,6 +402,18 @@ GENE_OUT_ROWS = (["EXP_" + c for c in ("SYN", "MIS", "NONS", "SPL", "TRUNC", "NO
                   "Pi_TRUNC", "Pi_NONSYN"])
 
 
+def size_ratio(num, den, stream=None):
+    """float64 num / den of two int64 device tensors in one launch (Pi_INDEL = ELT_SIZE / R_SIZE,
+    genic_driver_tools.py:158-159)."""
+    dev = num.device
+    assert num.dtype == torch.int64 and den.dtype == torch.int64 and num.is_contiguous() and den.is_contiguous()
+    assert num.numel() == den.numel()
+    out = torch.empty(num.shape, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dig_size_ratio", num.data_ptr(), den.data_ptr(), num.numel(), out.data_ptr(), _stream(dev, stream))
+    return out
+
+
 def gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc_mask=None, tp53=-1, stream=None):
     """[sum_{g != TP53} MU*Pi_SYN, sum_{non-CGC} Pi_INDEL*ALPHA*THETA, sum_{non-CGC} OBS_INDEL] on the device."""
     dev = mu.device

@@ -69,7 +69,7 @@ def gene_burden_test(pre, obs, nsamp, n_syn_non_tp53, tp53=-1, cgc_mask=None, sc
     Returns a dict of [E] float64 device tensors with the reference's column names."""
     mu, sigma = pre["MU"][cohort].contiguous(), pre["SIGMA"][cohort].contiguous()
     P = pre["P"][cohort].contiguous()                        # silent, mis, nons, splice
-    pi_indel = pre["ELT_SIZE"].to(torch.float64) / pre["R_SIZE"].to(torch.float64)   # genic_driver_tools.py:158-159
+    pi_indel = kernels.size_ratio(pre["ELT_SIZE"], pre["R_SIZE"])                     # genic_driver_tools.py:158-159
     sums = kernels.gene_scale_sums(mu, sigma, P, pi_indel, obs, cgc_mask, tp53)
     n_syn = float(n_syn_non_tp53)
     if collectives is not None and collectives.world > 1:

@@ -300,8 +300,11 @@ int dig_fisher_combine2(const double *p1_d, const double *p2_d, int64_t n, doubl
  *   for the 3*n_ctx substitutions in sorted 'CTX>CTX2' order; inputs are the uint64 outputs of
  *   dig_substitution_counts and the totals of dig_count_contexts.
  * dig_gene_scale_sums: sums_d[0] = sum_{g != tp53} MU*Pi_SYN (:814), sums_d[1] = sum_{g not CGC}
- *   Pi_INDEL*ALPHA*THETA (:716), sums_d[2] = sum_{g not CGC} OBS_INDEL (:717).  One block, fixed summation
- *   order.  Multi-GPU callers all-reduce sums_d (and n_syn) between the two calls.
+ *   Pi_INDEL*ALPHA*THETA (:716), sums_d[2] = sum_{g not CGC} OBS_INDEL (:717).  One cluster of eight blocks,
+ *   fixed summation order.  Multi-GPU callers all-reduce sums_d (and n_syn) between the two calls.
+ * dig_size_ratio: out_d[i] = (double)num_d[i] / (double)den_d[i] -- Pi_INDEL = GENE_LENGTH / R_SIZE of
+ *   genic_driver_tools.py:158-159 (ELT_SIZE / R_SIZE for elements, :334-335) from the int64 outputs of
+ *   dig_element_transfer, in one launch.
  * dig_gene_burden_test: cj = n_syn / sums[0] (or scale_factor when it is not NaN), t_indel = sums[2] / sums[1];
  *   a NaN n_syn means "read it from sums_d[3]" (the all-reduced value of a multi-GPU run, never copied to the host);
  *   out_d [27, n_gene] rows: 0-5 EXP_{SYN,MIS,NONS,SPL,TRUNC,NONSYN}, 6-11 PVAL_*_BURDEN, 12-17
@@ -311,6 +314,7 @@ int dig_fisher_combine2(const double *p1_d, const double *p2_d, int64_t n, doubl
  */
 int dig_sequence_freq(const unsigned long long *subst_counts_d, const unsigned long long *ctx_totals_d, int n_ctx,
                       double *freq_d, void *stream);
+int dig_size_ratio(const int64_t *num_d, const int64_t *den_d, int64_t n, double *out_d, void *stream);
 int dig_gene_scale_sums(const double *mu_d, const double *sigma_d, const double *p_d, const double *pi_indel_d,
                         const int64_t *obs_d, const uint8_t *cgc_mask_d, int64_t tp53, int64_t n_gene,
                         double *sums_d, void *stream);
