@@ -249,3 +249,29 @@ def test_secondary_gene_tests_oracle_matches_reference_golden(oracle):
         sel, pv = oracle.selection_coefficient(obs6[:, j], z["out_EXP_" + c], alpha, theta, pi6[:, j])
         assert np.array_equal(sel, z["out_SEL_" + c], equal_nan=True)
         assert_pvals_close(pv, z["out_PVAL_%s_SEL" % c], tol=1e-9)
+
+
+def test_check_all_windows_detects_one_wrong_bin(oracle):
+    """oracle/parity_sample.check_all_windows (the exhaustive full-size check of the GPU suite and of bench.py): accepts the
+    oracle's own rows chromosome by chromosome, sub-ranges included, and names the window when one bin is off by one."""
+    from oracle import parity_sample as ps
+    lengths = np.array([250_000, 130_005], dtype=np.int64)
+    off = np.array([0, 250_112], dtype=np.int64)
+    wins = np.array([(c, s, min(s + 10_000, int(L))) for c, L in enumerate(lengths) for s in range(0, int(L), 10_000)],
+                    dtype=np.int64)
+    rows = {2: [], 1: []}
+    for c, L in enumerate(lengths):
+        seq = oracle.synth_genome(int(off[c]), int(L), 3)
+        sel = np.flatnonzero(wins[:, 0] == c)
+        z = np.zeros(len(sel), dtype=np.int32)
+        for nu in (2, 1):
+            rows[nu].append(oracle.count_regions(seq, np.zeros(1, dtype=np.int64), np.array([L]), z, wins[sel, 1],
+                                                 wins[sel, 2], nu, nu)[0])
+    f5, f3 = np.concatenate(rows[2]), np.concatenate(rows[1])
+    ok = ps.check_all_windows(lengths, off, 3, wins, lambda a, b: f5[a:b], lambda a, b: f3[a:b], f5.sum(0), f3.sum(0))
+    assert ok == {"windows": len(wins), "ok": True, "detail": ""}
+    part = ps.check_all_windows(lengths, off, 3, wins, lambda a, b: f5[a:b], lambda a, b: f3[a:b], lo=10, hi=30)
+    assert part["ok"] and part["windows"] == 20
+    f5[17, 3] += 1
+    bad = ps.check_all_windows(lengths, off, 3, wins, lambda a, b: f5[a:b], lambda a, b: f3[a:b], f5.sum(0), f3.sum(0))
+    assert not bad["ok"] and "first window 17" in bad["detail"] and "pentanucleotide totals differ" in bad["detail"]
