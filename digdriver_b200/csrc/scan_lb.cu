@@ -489,9 +489,10 @@ __global__ void __launch_bounds__(256) lb_publish_redo_kernel(const LbArgs A)
 __device__ __forceinline__ int lb_chunk_order(int kq, int nch) { return kq == 0 ? nch - 1 : kq - 1; }
 
 // ---- producer warps: producer warp pw stages groups 2 pw and 2 pw + 1 (lanes 8 pw .. 8 pw + 7) ----------------
-// The chunk sequence of a CTA is the concatenation of the chunks of its batches (each batch in lb_chunk_order); chunk
-// number ci lands in stage ci & 1 once the chunk that used the stage before (ci - 2) has been read into registers by
-// all sixteen consumer warps.
+// The chunk sequence of a CTA is the concatenation of the chunks of its batches (each batch in lb_chunk_order).  In the
+// trinucleotide-only rings chunk number ci lands in stage ci & (NST - 1) once the chunk that used the stage before has
+// been read into registers by all consumer warps of the team; in the pentanucleotide modes chunk kq of a batch lands in
+// slot kq % 3 (slot 2 = the slice buffers, see BAR_FULL2 / BAR_OUTFREE above), with one fill-parity bit per slot.
 //   * Regular group (the four windows lie at a pitch of 8 tile windows in one chromosome, nothing clipped): the group
 //     leader issues TWO 2-D TMA box loads per chunk (4 rows x 528 B of bases, 4 rows x 272 B of mask) through tensor
 //     maps that view each genome array as rows of one pitch (lb_input_maps).
