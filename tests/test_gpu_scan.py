@@ -270,6 +270,24 @@ def test_hexamer_pair_scan_adversarial(dev, oracle):
         assert np.array_equal(kt.cpu().numpy(), want_big.astype(np.int64).sum(axis=0)), limit
     k3b, _ = kernels.count_contexts(dg, big_c, big_s, big_e, 1, 1, variant=_lib.SCAN_PER_BASE)
     assert np.array_equal(k3b.cpu().numpy(), want_big)
+    # the same shuffled set through the FUSED lane-bank kernel, four times over: every CTA then works through several
+    # consecutive batches whose chunk counts differ (0 to 16 chunks, long regions on the redo list), which is what the
+    # three-slot staging ring (slot kq % 3, the third slot aliased onto the slice buffers, one fill parity per slot) and
+    # its hand-offs across batch boundaries have to survive; twice, with and without register-total spills
+    reps5 = 4 * reps
+    order5 = np.random.default_rng(11).permutation(reps5 * len(chrom))
+    f_c, f_s, f_e = (np.tile(a, reps5)[order5] for a in (chrom, start, end))
+    want_f5, want_f3 = np.tile(want5, (reps5, 1))[order5], np.tile(want3, (reps5, 1))[order5]
+    for limit in (0, 64):
+        c5, c3, t5, t3 = kernels.count_contexts_fused53(dg, f_c, f_s, f_e, want_totals=True, totals_limit_kb=limit)
+        bad = np.flatnonzero((c5.cpu().numpy() != want_f5).any(axis=1))
+        assert bad.size == 0, (limit, bad[:5], f_c[bad[:5]], f_s[bad[:5]], f_e[bad[:5]])
+        bad = np.flatnonzero((c3.cpu().numpy() != want_f3).any(axis=1))
+        assert bad.size == 0, (limit, bad[:5], f_c[bad[:5]], f_s[bad[:5]], f_e[bad[:5]])
+        assert np.array_equal(t5.cpu().numpy(), want_f5.astype(np.int64).sum(axis=0)), limit
+        assert np.array_equal(t3.cpu().numpy(), want_f3.astype(np.int64).sum(axis=0)), limit
+        p5, _ = kernels.count_contexts(dg, f_c, f_s, f_e, 2, 2, totals_limit_kb=limit)       # K = 1024 alone (TRI = 0)
+        assert np.array_equal(p5.cpu().numpy(), want_f5), limit
 
 
 def test_empty_inputs_through_the_c_abi(dev):
