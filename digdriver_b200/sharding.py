@@ -126,15 +126,28 @@ def all_gather_rows(coll, t, sizes):
         return t
     m = max(sizes)
     if t.shape[0] != m:                                   # ragged last slice: pad to the common block size
-        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad = torch.empty((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)    # the padding rows are dropped below
         pad[: t.shape[0]] = t
         t = pad
     out = torch.empty((coll.world * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t.contiguous())      # one collective straight into the final buffer
     if all(s_ == m for s_ in sizes):
         return out
-    keep = torch.cat([torch.arange(r * m, r * m + s_, device=t.device) for r, s_ in enumerate(sizes)])
-    return out.index_select(0, keep)
+    return out.index_select(0, _ragged_keep(tuple(int(s_) for s_ in sizes), m, t.device))
+
+
+_KEEP = {}
+
+
+def _ragged_keep(sizes, m, device):
+    """Row indices that drop the padding of a ragged all-gather.  Built once per (sizes, device): inside a stream-ordered
+    or CUDA-graph-captured stage it would otherwise cost one arange per rank plus a concatenation at every step."""
+    key = (sizes, m, str(device))
+    keep = _KEEP.get(key)
+    if keep is None:
+        idx = np.concatenate([np.arange(r * m, r * m + s_, dtype=np.int64) for r, s_ in enumerate(sizes)])
+        keep = _KEEP[key] = torch.from_numpy(idx).to(device)
+    return keep
 
 
 # --------------------------------------------------------------------------------------------
