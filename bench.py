@@ -511,8 +511,11 @@ def gather_strong_results(coll, shard, res):
     (rows are in owner-rank order; StrongShard.gene_ids maps them back to the annotation's order)."""
     import torch
     from digdriver_b200 import sharding
-    rows = torch.stack([res[c] for c in result_columns()], dim=1)
-    return sharding.all_gather_rows(coll, rows, shard.genes_per_rank)
+    cols = [res[c] for c in result_columns()]
+    # stacked straight into a block of the common (longest rank's) size: no separate padding copy before the collective
+    pad = torch.empty((max(shard.genes_per_rank), len(cols)), dtype=cols[0].dtype, device=cols[0].device)
+    torch.stack(cols, dim=1, out=pad[: cols[0].numel()])
+    return sharding.all_gather_rows(coll, pad, shard.genes_per_rank)
 
 
 class GraphedStep:
@@ -1055,6 +1058,21 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
+    # ---- the all-gathered result rows (range-sharded runs): every rank's block, as it arrived on EVERY rank, against the
+    #      rows that rank computed (bitwise, NaN = NaN); outside the timed region
+    gathered_ok = None
+    shard_ = getattr(di, "shard", None)
+    if shard_ is not None and dist_ctx is not None and stepper.gathered is not None:
+        mine = torch.stack([res[c] for c in result_columns()], dim=1).contiguous().cpu().numpy()
+        blocks = [None] * world
+        dist.all_gather_object(blocks, mine)
+        got_all = stepper.gathered.cpu().numpy()
+        want_all = np.concatenate(blocks, axis=0)
+        flag = torch.tensor([int(got_all.shape == want_all.shape and np.array_equal(got_all.view(np.int64), want_all.view(np.int64)))],
+                            dtype=torch.int64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gathered_ok = bool(int(flag[0]))
+
     # ---- parity at full size, outside every timed region (rank 0; the oracle regenerates the slices it needs)
     parity = None
     if rank == 0 and not args.no_parity_sample:
@@ -1062,6 +1080,11 @@ def main():
             parity = parity_sample(dg, d, di, res, seed=seed)
         except Exception as exc:      # report, never hide
             parity = {"ok": False, "detail": "parity sample failed to run: %r" % (exc,)}
+        if gathered_ok is not None:
+            parity["gathered_result_rows_ok"] = gathered_ok
+            if not gathered_ok:
+                parity["ok"] = False
+                parity["detail"] = parity.get("detail", "") + "; all-gathered result rows differ from the ranks' own rows"
 
     # ---- e2e leg: host buffers in and out, through digdriver_b200.host_pipeline
     e2e = None

@@ -59,6 +59,18 @@ def gene_pretrain(genes, window, win_map_off, win_map, win_counts64, y_pred, std
     return out
 
 
+_CONST = {}
+
+
+def _const_f64(value, device):
+    """A cached one-element float64 device tensor (a torch.full per step is one more node in a captured stage)."""
+    key = (float(value), str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = _CONST[key] = torch.full((1,), float(value), dtype=torch.float64, device=device)
+    return t
+
+
 def gene_burden_test(pre, obs, nsamp, n_syn_non_tp53, tp53=-1, cgc_mask=None, scale_factor=None, cohort=0,
                      collectives=None):
     """run_gene_model's arithmetic (transfer_tools.py:809-861) fused on the device: one reduction kernel for the
@@ -75,7 +87,7 @@ def gene_burden_test(pre, obs, nsamp, n_syn_non_tp53, tp53=-1, cgc_mask=None, sc
     if collectives is not None and collectives.world > 1:
         # sums[3] carries this shard's synonymous count; after the all-reduce the kernel reads the cohort-wide value
         # from the device (no host read: the whole stage stays stream-ordered and CUDA-graph capturable)
-        sums = torch.cat([sums, torch.full((1,), n_syn, dtype=torch.float64, device=sums.device)])
+        sums = torch.cat([sums, _const_f64(n_syn, sums.device)])
         collectives.all_reduce_sum(sums)
         n_syn = None
     out = kernels.gene_burden_test(mu, sigma, P, pi_indel, obs, nsamp, sums, n_syn, scale_factor)

@@ -201,5 +201,6 @@ class GatheredTable:
     def summed_totals(self, gathered):
         """int64 [1280]: the ranks' partial totals (1024 | 64) and substitution counts (192) added up (gathered:
         [world, block_rows, 64] int32)."""
-        g = gathered.view(self.world, self.block_rows, 64)[:, self.m:, :].contiguous()
-        return g.view(torch.int64).reshape(self.world, -1).sum(dim=0)
+        # each rank's tail is one contiguous run of its block, so the int64 view needs no copy: one reduction kernel
+        g = gathered.view(self.world, self.block_rows * 64)[:, self.m * 64:]
+        return g.view(torch.int64).sum(dim=0)
