@@ -252,8 +252,8 @@ class DeviceInputs:
         self.max_span = kernels.element_max_span(d["g_ptr"], d["g_bs"], d["g_be"], WINDOW)
         self.counts5 = torch.empty((n_win, 1024), dtype=torch.int32, device=device)
         self.counts3 = torch.empty((n_win, 64), dtype=torch.int32, device=device)
-        self.totals5 = torch.zeros(1024, dtype=torch.int64, device=device)
-        self.totals3 = torch.zeros(64, dtype=torch.int64, device=device)
+        self.totals53 = torch.zeros(1024 + 64, dtype=torch.int64, device=device)
+        self.totals5, self.totals3 = self.totals53[:1024], self.totals53[1024:]
         self.side_stream = torch.cuda.Stream(device)
 
 
@@ -270,8 +270,13 @@ def scan_stage(dg, di, ev=None, lo=0, hi=None, zero=True):
         hi = di.win_chrom.numel() if hi is None else hi
         out5, out3, tot5, tot3 = di.counts5[lo:hi], di.counts3[lo:hi], di.totals5, di.totals3
     if zero:
-        tot5.zero_()
-        tot3.zero_()
+        # both totals are adjacent views of one buffer: one fill kernel in front of the scan instead of two
+        both = getattr(shard if shard is not None else di, "totals53", None)
+        if both is not None:
+            both.zero_()
+        else:
+            tot5.zero_()
+            tot3.zero_()
     if shard is not None:
         shard.mutation_contexts(dg)                      # 125 k - 500 k SNVs per rank: a few microseconds, outside the scan's events
     if ev is not None:
@@ -343,6 +348,7 @@ class StrongShard:
         self.local = self.gathered[self.rank]
         self.table_ready = False
         self.rows, self.tot5, self.tot3, self.sub = gt.local_views(self.local)
+        self.totals53 = self.local[gt.m:].view(torch.int64).reshape(-1)[:1024 + 64]      # tot5 | tot3, adjacent in the tail
         off, wmap = gt.window_map(wins[:, 0], wins[:, 1], WINDOW, len(d["lengths"]))
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)
         self.wmap_off, self.wmap = t(off, torch.int64), t(wmap, torch.int32)
