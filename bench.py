@@ -321,7 +321,7 @@ class StrongShard:
         gt = self.table
         # The exchange buffer lives in symmetric (peer-mapped) memory when the platform offers it: the scan kernel then
         # stores every trinucleotide row straight into all ranks' copies (NVSwitch multicast store, or one store per peer),
-        # the 8.7 KB of partial totals follow with dig_peer_broadcast, and a device barrier replaces the collective.
+        # the 10 KB of partial totals and substitution counts follow with dig_peer_broadcast, and a device barrier replaces the collective.
         self.fused, self.fused_note, self.symm = False, "disabled (--exchange nccl)", None
         n_words = self.world * gt.block_rows * 64
         if fused_exchange:
